@@ -1,0 +1,328 @@
+// C ABI of libgpmpc.so (include/gpmpc.h): handle, workspace and kernel orchestration.
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/gpmpc.h"
+#include "gpmpc_common.cuh"
+#include "gpmpc_internal.h"
+
+using namespace gpmpc;
+
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct gpmpc_handle {
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  std::string err;
+  bool prepared = false, cost_set = false;
+  int N = 0, NP = 0, D = 0, DP = 0, E = 0, Na = 0;
+  DevBuf x, il2, s2, ls, noise, beta, iK, Kbuf, Zbuf, info;
+  DevBuf c_target, c_W, c_WT, c_smin, c_smax;
+  double kappa = 0.0;
+  int use_constraints = 0, clip = 0;
+  DevBuf ws_kk, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
+  long long launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_fwd = false, ev_bwd = false;
+};
+
+static int fail(gpmpc_handle* h, int code, const char* msg, cudaError_t ce = cudaSuccess) {
+  if (h) {
+    h->err = msg;
+    if (ce != cudaSuccess) {
+      h->err += ": ";
+      h->err += cudaGetErrorString(ce);
+    }
+  }
+  return code;
+}
+
+#define CU(call)                                                            \
+  do {                                                                      \
+    cudaError_t ce_ = (call);                                               \
+    if (ce_ != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, #call, ce_);     \
+  } while (0)
+
+extern "C" {
+
+int gpmpc_version(void) { return 100; }
+
+const char* gpmpc_last_error(const gpmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int gpmpc_create(gpmpc_handle** out, int device) {
+  if (!out) return GPMPC_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return GPMPC_ERR_NO_DEVICE;
+  }
+  gpmpc_handle* h = new gpmpc_handle();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return GPMPC_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return GPMPC_ERR_CUDA; }
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+  *out = h;
+  return GPMPC_OK;
+}
+
+int gpmpc_destroy(gpmpc_handle* h) {
+  if (!h) return GPMPC_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
+                   &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
+                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in};
+  for (DevBuf* b : all) b->release();
+  for (int i = 0; i < 4; i++)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return GPMPC_OK;
+}
+
+int gpmpc_prepare(gpmpc_handle* h, const double* x, const double* y, const double* lengthscale,
+                  const double* outputscale, const double* noise, int N, int D, int E, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!x || !y || !lengthscale || !outputscale || !noise || N < 1) return fail(h, GPMPC_ERR_BAD_ARG, "prepare: null pointer or N < 1");
+  if (E < 1 || E > GPMPC_MAX_STATE || D < E || D > GPMPC_MAX_INPUT)
+    return fail(h, GPMPC_ERR_UNSUPPORTED, "prepare: need 1 <= E <= 8 and E <= D <= 16");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  const int NP = (N + 63) / 64 * 64;
+  h->prepared = false;
+  CU(h->x.ensure(sizeof(double) * N * D));
+  CU(h->ls.ensure(sizeof(double) * E * D));
+  CU(h->il2.ensure(sizeof(double) * E * D));
+  CU(h->s2.ensure(sizeof(double) * E));
+  CU(h->noise.ensure(sizeof(double) * E));
+  CU(h->beta.ensure(sizeof(double) * E * NP));
+  CU(h->iK.ensure(sizeof(double) * (size_t)E * NP * NP));
+  CU(h->Kbuf.ensure(sizeof(double) * (size_t)E * NP * NP));
+  CU(h->Zbuf.ensure(sizeof(double) * (size_t)E * NP * (NP + 64)));
+  CU(h->info.ensure(sizeof(int) * GPMPC_MAX_STATE));
+  CU(cudaMemcpyAsync(h->x.ptr, x, sizeof(double) * N * D, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(h->ls.ptr, lengthscale, sizeof(double) * E * D, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(h->s2.ptr, outputscale, sizeof(double) * E, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(h->noise.ptr, noise, sizeof(double) * E, cudaMemcpyDeviceToDevice, st));
+  CU(launch_il2(h->ls.as<double>(), h->il2.as<double>(), E * D, st));
+  h->launches += 1;
+  CU(launch_prepare(h->x.as<double>(), y, h->ls.as<double>(), h->s2.as<double>(), h->noise.as<double>(), N, NP, D, E,
+                    h->Kbuf.as<double>(), h->Zbuf.as<double>(), h->iK.as<double>(), h->beta.as<double>(),
+                    h->info.as<int>(), st, &h->launches));
+  int info[GPMPC_MAX_STATE];
+  CU(cudaMemcpyAsync(info, h->info.ptr, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int a = 0; a < E; a++)
+    if (info[a] != 0) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "prepare: K + noise*I of GP %d is not positive definite (pivot %d)", a, info[a] - 1);
+      return fail(h, GPMPC_ERR_NOT_PD, msg);
+    }
+  h->N = N; h->NP = NP; h->D = D; h->DP = (D + 1) & ~1; h->E = E;
+  h->prepared = true;
+  return GPMPC_OK;
+}
+
+int gpmpc_get_factorization(gpmpc_handle* h, double* iK, double* beta, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!h->prepared) return fail(h, GPMPC_ERR_NOT_PREPARED, "get_factorization: call gpmpc_prepare first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  const int N = h->N, NP = h->NP, E = h->E;
+  if (iK)
+    for (int a = 0; a < E; a++)
+      CU(cudaMemcpy2DAsync(iK + (size_t)a * N * N, sizeof(double) * N, h->iK.as<double>() + (size_t)a * NP * NP,
+                           sizeof(double) * NP, sizeof(double) * N, N, cudaMemcpyDeviceToDevice, st));
+  if (beta)
+    CU(cudaMemcpy2DAsync(beta, sizeof(double) * N, h->beta.ptr, sizeof(double) * NP, sizeof(double) * N, E,
+                         cudaMemcpyDeviceToDevice, st));
+  return GPMPC_OK;
+}
+
+int gpmpc_set_cost(gpmpc_handle* h, const double* target, const double* W, const double* WT, double kappa,
+                   int use_constraints, const double* state_min, const double* state_max,
+                   int clip_lower_bound_cost_to_0, int Na, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!h->prepared) return fail(h, GPMPC_ERR_NOT_PREPARED, "set_cost: call gpmpc_prepare first (defines E, D)");
+  if (!target || !W || !WT) return fail(h, GPMPC_ERR_BAD_ARG, "set_cost: null pointer");
+  if (use_constraints && (!state_min || !state_max)) return fail(h, GPMPC_ERR_BAD_ARG, "set_cost: constraints need state_min/state_max");
+  const int E = h->E;
+  if (Na < 1 || E + Na > h->D) return fail(h, GPMPC_ERR_BAD_ARG, "set_cost: need 1 <= Na and E + Na <= D");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  const int Dc = E + Na;
+  CU(h->c_target.ensure(sizeof(double) * Dc));
+  CU(h->c_W.ensure(sizeof(double) * Dc * Dc));
+  CU(h->c_WT.ensure(sizeof(double) * E * E));
+  CU(h->c_smin.ensure(sizeof(double) * E));
+  CU(h->c_smax.ensure(sizeof(double) * E));
+  CU(cudaMemcpyAsync(h->c_target.ptr, target, sizeof(double) * Dc, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(h->c_W.ptr, W, sizeof(double) * Dc * Dc, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(h->c_WT.ptr, WT, sizeof(double) * E * E, cudaMemcpyDeviceToDevice, st));
+  if (use_constraints) {
+    CU(cudaMemcpyAsync(h->c_smin.ptr, state_min, sizeof(double) * E, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h->c_smax.ptr, state_max, sizeof(double) * E, cudaMemcpyDeviceToDevice, st));
+  }
+  h->kappa = kappa;
+  h->use_constraints = use_constraints ? 1 : 0;
+  h->clip = clip_lower_bound_cost_to_0 ? 1 : 0;
+  h->Na = Na;
+  h->cost_set = true;
+  return GPMPC_OK;
+}
+
+static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int B, int H, int Na, size_t* smem,
+                       int* grid) {
+  p.x = h->x.as<double>(); p.beta = h->beta.as<double>(); p.iK = h->iK.as<double>();
+  p.il2 = h->il2.as<double>(); p.s2 = h->s2.as<double>();
+  p.N = h->N; p.NP = h->NP; p.D = h->D; p.DP = h->DP; p.E = h->E; p.Na = Na;
+  p.B = B; p.H = H;
+  const int G = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, h->smem_optin);
+  if (G < 1) return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
+  p.group = G;
+  p.seg = 256;
+  *smem = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G, H, Na);
+  *grid = B < h->num_sms ? B : h->num_sms;
+  cudaError_t ce = h->ws_kk.ensure(sizeof(double) * (size_t)(*grid) * h->E * h->NP);
+  if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
+  p.ws_kk = h->ws_kk.as<double>();
+  return GPMPC_OK;
+}
+
+int gpmpc_predict_step(gpmpc_handle* h, const double* input_mu, const double* input_var, int B, int EV,
+                       double* M, double* S, double* V, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!h->prepared) return fail(h, GPMPC_ERR_NOT_PREPARED, "predict_step: call gpmpc_prepare first");
+  if (!input_mu || !input_var || B < 1) return fail(h, GPMPC_ERR_BAD_ARG, "predict_step: null pointer or B < 1");
+  if (EV < 1 || EV > GPMPC_MAX_EV || EV > h->D) return fail(h, GPMPC_ERR_UNSUPPORTED, "predict_step: need 1 <= EV <= min(8, D)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  RolloutParams p;
+  memset(&p, 0, sizeof(p));
+  size_t smem; int grid;
+  int rc = fill_common(h, p, EV, false, B, 0, 1, &smem, &grid);
+  if (rc) return rc;
+  p.mode = 1;
+  p.obs_mu = input_mu; p.obs_var = input_var;
+  p.stepM = M; p.stepS = S; p.stepV = V;
+  CU(launch_rollout(EV, false, p, grid, smem, st));
+  h->launches += 1;
+  return GPMPC_OK;
+}
+
+int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_mu, const double* obs_var,
+                  int per_candidate_init, int B, int H, int Na, int iter_ctrl, int limit_action_change,
+                  const double* max_change, const double* action_prev, double* cost, double* grad,
+                  double* states_mu, double* states_var, double* rewards, double* rewards_var,
+                  double* actions_model, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!h->prepared) return fail(h, GPMPC_ERR_NOT_PREPARED, "rollout: call gpmpc_prepare first");
+  if (!h->cost_set) return fail(h, GPMPC_ERR_NOT_PREPARED, "rollout: call gpmpc_set_cost first");
+  if (!actions_mpc || !obs_mu || !obs_var) return fail(h, GPMPC_ERR_BAD_ARG, "rollout: null input pointer");
+  if (B < 1 || H < 1 || Na != h->Na) return fail(h, GPMPC_ERR_BAD_ARG, "rollout: need B >= 1, H >= 1 and Na as given to set_cost");
+  const int E = h->E, D = h->D;
+  const int include_time = (D == E + Na + 1) ? 1 : 0;
+  if (D != E + Na + include_time) return fail(h, GPMPC_ERR_BAD_ARG, "rollout: D must be E + Na (+1 with a time input)");
+  if (limit_action_change && (!max_change || !action_prev)) return fail(h, GPMPC_ERR_BAD_ARG, "rollout: derivative action mapper needs max_change and action_prev");
+  if ((size_t)H * Na > 4096) return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: H * Na > 4096");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  const bool want_grad = grad != nullptr;
+  RolloutParams p;
+  memset(&p, 0, sizeof(p));
+  size_t smem; int grid;
+  int rc = fill_common(h, p, E, want_grad, B, H, Na, &smem, &grid);
+  if (rc) return rc;
+  p.mode = 0;
+  p.include_time = include_time; p.iter_ctrl = iter_ctrl; p.per_cand_init = per_candidate_init ? 1 : 0;
+  p.limit_change = limit_action_change ? 1 : 0;
+  p.actions_mpc = actions_mpc; p.obs_mu = obs_mu; p.obs_var = obs_var;
+  p.max_change = max_change; p.action_prev = action_prev;
+  p.c_target = h->c_target.as<double>(); p.c_W = h->c_W.as<double>(); p.c_WT = h->c_WT.as<double>();
+  p.c_smin = h->c_smin.as<double>(); p.c_smax = h->c_smax.as<double>();
+  p.kappa = h->kappa; p.use_constraints = h->use_constraints; p.clip = h->clip;
+  // outputs the caller did not ask for go to handle-owned scratch
+  if (!cost) { CU(h->t_cost.ensure(sizeof(double) * B)); cost = h->t_cost.as<double>(); }
+  if (!states_mu) { CU(h->t_mu.ensure(sizeof(double) * (size_t)B * (H + 1) * E)); states_mu = h->t_mu.as<double>(); }
+  if (!states_var) { CU(h->t_var.ensure(sizeof(double) * (size_t)B * (H + 1) * E * E)); states_var = h->t_var.as<double>(); }
+  if (!rewards) { CU(h->t_r.ensure(sizeof(double) * (size_t)B * (H + 1))); rewards = h->t_r.as<double>(); }
+  if (!rewards_var) { CU(h->t_rv.ensure(sizeof(double) * (size_t)B * (H + 1))); rewards_var = h->t_rv.as<double>(); }
+  if (!actions_model) { CU(h->t_am.ensure(sizeof(double) * (size_t)B * H * Na)); actions_model = h->t_am.as<double>(); }
+  p.cost = cost; p.states_mu = states_mu; p.states_var = states_var; p.rewards = rewards; p.rewards_var = rewards_var;
+  p.actions_model = actions_model;
+  const RecLayout RL = rec_layout(E, D);
+  if (want_grad) {
+    CU(h->records.ensure(sizeof(double) * (size_t)B * H * RL.size));
+    p.records = h->records.as<double>();
+  }
+  if (h->timing) CU(cudaEventRecord(h->ev[0], st));
+  CU(launch_rollout(E, want_grad, p, grid, smem, st));
+  h->launches += 1;
+  if (h->timing) { CU(cudaEventRecord(h->ev[1], st)); h->ev_fwd = true; }
+  h->ev_bwd = false;
+  if (want_grad) {
+    BackwardParams b;
+    memset(&b, 0, sizeof(b));
+    b.il2 = p.il2; b.s2 = p.s2; b.D = D; b.E = E; b.Na = Na; b.B = B; b.H = H;
+    b.limit_change = p.limit_change; b.include_time = include_time; b.max_change = max_change;
+    b.c_target = p.c_target; b.c_W = p.c_W; b.c_WT = p.c_WT; b.c_smin = p.c_smin; b.c_smax = p.c_smax;
+    b.kappa = p.kappa; b.use_constraints = p.use_constraints;
+    b.states_mu = states_mu; b.states_var = states_var; b.rewards_var = rewards_var; b.actions_model = actions_model;
+    b.records = p.records; b.grad = grad;
+    if (h->timing) CU(cudaEventRecord(h->ev[2], st));
+    CU(launch_backward(E, b, st));
+    h->launches += 1;
+    if (h->timing) { CU(cudaEventRecord(h->ev[3], st)); h->ev_bwd = true; }
+  }
+  return GPMPC_OK;
+}
+
+int gpmpc_enable_timing(gpmpc_handle* h, int on) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  h->timing = on != 0;
+  h->ev_fwd = h->ev_bwd = false;
+  return GPMPC_OK;
+}
+
+long long gpmpc_launch_count(const gpmpc_handle* h) { return h ? h->launches : 0; }
+
+float gpmpc_last_rollout_ms(gpmpc_handle* h) {
+  if (!h || !h->ev_fwd) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
+  return ms;
+}
+
+float gpmpc_last_backward_ms(gpmpc_handle* h) {
+  if (!h || !h->ev_bwd) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
+  return ms;
+}
+
+}  // extern "C"

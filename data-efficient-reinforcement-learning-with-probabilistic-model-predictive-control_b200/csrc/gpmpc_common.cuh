@@ -1,0 +1,142 @@
+// Shared device helpers for the GP-MPC kernels (sm_100a).  All arithmetic is float64: the
+// reference computes in float64 (config_classes/total_config.py:11) and the covariance sums
+// cancel by ~1e8 (hard part 1), so fp32 is not an option for this path.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define GPMPC_MAX_EV 8
+#define GPMPC_MAX_D 16
+#define GPMPC_MAX_PAIRS 36
+
+#define HD __host__ __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------
+// exp for the N^2 loop.  Arguments are <= log(s2_a s2_b) (bounded above) and may be very
+// negative.  Cody-Waite reduction by ln2 + degree-12 polynomial, 2^k applied through the exponent
+// field.  ~1 ulp on [-708, 40]; returns 0 below -708.  NaN inputs are screened per step by the
+// caller (a NaN candidate is poisoned explicitly), so no NaN handling is needed here.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exp_fast(double x) {
+  const double L2E = 1.4426950408889634074;
+  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52
+  double kd = __fma_rn(x, L2E, SHIFT);
+  int k = __double2loint(kd);
+  kd -= SHIFT;
+  double r = __fma_rn(kd, -6.93147180369123816490e-01, x);
+  r = __fma_rn(kd, -1.90821492927058770002e-10, r);
+  double p = 2.08767569878680989792e-09;            // 1/12!
+  p = __fma_rn(p, r, 2.50521083854417187751e-08);   // 1/11!
+  p = __fma_rn(p, r, 2.75573192239858906526e-07);   // 1/10!
+  p = __fma_rn(p, r, 2.75573192239858906526e-06);   // 1/9!
+  p = __fma_rn(p, r, 2.48015873015873015873e-05);   // 1/8!
+  p = __fma_rn(p, r, 1.98412698412698412698e-04);   // 1/7!
+  p = __fma_rn(p, r, 1.38888888888888888889e-03);   // 1/6!
+  p = __fma_rn(p, r, 8.33333333333333333333e-03);   // 1/5!
+  p = __fma_rn(p, r, 4.16666666666666666667e-02);   // 1/4!
+  p = __fma_rn(p, r, 1.66666666666666666667e-01);   // 1/3!
+  p = __fma_rn(p, r, 0.5);
+  p = __fma_rn(p, r, 1.0);
+  p = __fma_rn(p, r, 1.0);
+  int hi = __double2hiint(p) + (k << 20);
+  double res = __hiloint2double(hi, __double2loint(p));
+  return (k < -1021) ? 0.0 : res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small dense SPD helpers (n <= 8), used once per step per GP / pair.
+// ---------------------------------------------------------------------------------------------
+// inv = a^-1, det = det(a) for symmetric positive definite a (n x n, row-major).  A non-positive
+// pivot yields NaN, which then propagates like the reference's det/solve would.
+template <int n>
+HD void spd_inv_det(const double* a, double* inv, double& det) {
+  double L[n * n];
+  double Li[n * n];
+  det = 1.0;
+  for (int j = 0; j < n; j++) {
+    double d = a[j * n + j];
+    for (int k = 0; k < j; k++) d -= L[j * n + k] * L[j * n + k];
+    det *= d;
+    d = sqrt(d);
+    L[j * n + j] = d;
+    double id = 1.0 / d;
+    for (int i = j + 1; i < n; i++) {
+      double v = a[i * n + j];
+      for (int k = 0; k < j; k++) v -= L[i * n + k] * L[j * n + k];
+      L[i * n + j] = v * id;
+    }
+  }
+  for (int j = 0; j < n; j++) {
+    Li[j * n + j] = 1.0 / L[j * n + j];
+    for (int i = j + 1; i < n; i++) {
+      double v = 0.0;
+      for (int k = j; k < i; k++) v -= L[i * n + k] * Li[k * n + j];
+      Li[i * n + j] = v / L[i * n + i];
+    }
+  }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) {
+      double v = 0.0;
+      for (int k = i; k < n; k++) v += Li[k * n + i] * Li[k * n + j];
+      inv[i * n + j] = v;
+      inv[j * n + i] = v;
+    }
+}
+
+// Pair matrices of gp_model.py:156-163 restricted to the EV x EV block that carries variance:
+//   R = s W + I,  Rinv = R^-1,  Q = 1/2 R^-1 s,  detR = det R        (W = diag(Wd))
+// computed through the symmetric form  s~ = W^1/2 s W^1/2,  R = W^-1/2 (s~ + I) W^1/2.
+template <int n>
+HD void pair_matrices(const double* s, const double* Wd, double* Rinv, double* Q, double& detR) {
+  double st[n * n], Ti[n * n], sq[n];
+  for (int e = 0; e < n; e++) sq[e] = sqrt(Wd[e]);
+  for (int e = 0; e < n; e++)
+    for (int f = 0; f < n; f++) st[e * n + f] = sq[e] * s[e * n + f] * sq[f] + (e == f ? 1.0 : 0.0);
+  spd_inv_det<n>(st, Ti, detR);
+  for (int e = 0; e < n; e++)
+    for (int f = 0; f < n; f++) Rinv[e * n + f] = Ti[e * n + f] * sq[f] / sq[e];
+  for (int e = 0; e < n; e++)
+    for (int f = 0; f < n; f++) {
+      double v = 0.0;
+      for (int k = 0; k < n; k++) v += Rinv[e * n + k] * s[k * n + f];
+      Q[e * n + f] = 0.5 * v;
+    }
+}
+
+HD int pair_index(int a, int b, int E) {  // a <= b, row-major upper triangle
+  return a * E - (a * (a - 1)) / 2 + (b - a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Record written per (candidate, step) by the forward kernel in gradient mode and consumed by
+// the reverse sweep (tests/algo_spec.py step_forward/step_backward is the executable spec).
+// ---------------------------------------------------------------------------------------------
+struct RecLayout {
+  int E, D, P, offM, offV, offGp, gpStride, offPair, pairStride, size;
+  // per-GP block: h, c, gE[E], dh_dm[D], dh_dA[E*E], dg_dm[E*D], dg_dA[E*P]
+  // per-pair block: Sraw, detR, gm[D], gQ[E*E]
+};
+HD RecLayout rec_layout(int E, int D) {
+  RecLayout r;
+  r.E = E; r.D = D; r.P = E * (E + 1) / 2;
+  r.offM = 0;
+  r.offV = E;
+  r.offGp = E + E * E;
+  r.gpStride = 2 + E + D + E * E + E * D + E * r.P;
+  r.offPair = r.offGp + E * r.gpStride;
+  r.pairStride = 2 + D + E * E;
+  r.size = r.offPair + r.P * r.pairStride;
+  return r;
+}
+
+struct CostParams {
+  const double* target;  // (E+Na)
+  const double* W;       // (E+Na)^2
+  const double* WT;      // E^2
+  const double* smin;    // E
+  const double* smax;    // E
+  double kappa;
+  int use_constraints;
+  int clip;
+};

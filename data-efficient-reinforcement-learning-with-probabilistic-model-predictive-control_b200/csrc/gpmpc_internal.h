@@ -1,0 +1,63 @@
+// Internal declarations shared by the translation units of libgpmpc.so.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gpmpc {
+
+struct RolloutParams {
+  // ---- training block (resident in the handle; identical for every candidate -> L2 resident)
+  const double* x;      // (N, D)
+  const double* beta;   // (E, NP)   zero padded
+  const double* iK;     // (E, NP, NP) symmetric, zero padded
+  const double* il2;    // (E, D)  1 / lengthscale^2
+  const double* s2;     // (E)     outputscale
+  int N, NP, D, DP, E, Na;
+  // ---- candidates
+  int B, H, mode;            // mode 0: rollout, 1: single moment-matching step on given inputs
+  int include_time, iter_ctrl, per_cand_init, limit_change;
+  const double* actions_mpc; // (B, H*Na)
+  const double* obs_mu;      // (E) or (B,E)            [mode 1: input_mu (B, D)]
+  const double* obs_var;     // (E,E) or (B,E,E)        [mode 1: input_var (B, EV, EV)]
+  const double* max_change;  // (Na)
+  const double* action_prev; // (Na)
+  // ---- cost
+  const double* c_target; const double* c_W; const double* c_WT; const double* c_smin; const double* c_smax;
+  double kappa; int use_constraints, clip;
+  // ---- outputs (never NULL inside the kernel: the host substitutes workspace buffers)
+  double* cost;        // (B)
+  double* states_mu;   // (B, H+1, E)
+  double* states_var;  // (B, H+1, E, E)
+  double* rewards;     // (B, H+1)
+  double* rewards_var; // (B, H+1)
+  double* actions_model; // (B, H, Na)
+  double* stepM; double* stepS; double* stepV;   // mode 1 outputs (may be NULL)
+  double* records;     // (B, H, rec.size) gradient-mode records (NULL in value mode)
+  double* ws_kk;       // (gridDim.x, E, NP) per-CTA scratch
+  // ---- launch geometry
+  int group;           // pairs per N^2 phase
+  int seg;             // columns per work item
+};
+
+struct BackwardParams {
+  const double* il2; const double* s2;
+  int D, E, Na, B, H, limit_change, include_time;
+  const double* max_change;
+  const double* c_target; const double* c_W; const double* c_WT; const double* c_smin; const double* c_smax;
+  double kappa; int use_constraints;
+  const double* states_mu; const double* states_var; const double* rewards_var; const double* actions_model;
+  const double* records;
+  double* grad;        // (B, H*Na)
+};
+
+size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na);
+int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, size_t smem_limit);
+cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
+cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
+                           const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
+                           double* iK, double* beta, int* info, cudaStream_t st, long long* launches);
+cudaError_t launch_il2(const double* ls, double* il2, int n, cudaStream_t st);
+
+constexpr int ROLLOUT_THREADS = 512;
+
+}  // namespace gpmpc
