@@ -667,6 +667,8 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
             // dS/dm[:EV] -= 2 W (Q ybar), ybar = sum_ij w (z_a,i + z_b,j) = gm[:EV] before the correction
             const double* Qm = s_Q + pr * EV * EV;
             double yb[EV];
+            if (a == b)  // upper-triangle sweep: (rho_up + gam_up) is the full row sum only once
+              for (int e = 1; e < L.paccN; e++) acc[e] *= 2.0;
             for (int e = 0; e < EV; e++) yb[e] = acc[1 + e];
             for (int e = 0; e < EV; e++) {
               double v = 0.0;

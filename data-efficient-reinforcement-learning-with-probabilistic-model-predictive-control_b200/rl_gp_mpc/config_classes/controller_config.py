@@ -1,0 +1,22 @@
+"""ControllerConfig: same constructor and fields as the reference's config_classes/controller_config.py:1-26."""
+
+_DEFAULT_OPTIMIZER_PARAMS = {
+    "disp": None, "maxcor": 30, "ftol": 1e-99, "gtol": 1e-99, "eps": 1e-2, "maxfun": 30,
+    "maxiter": 30, "iprint": -1, "maxls": 30, "finite_diff_rel_step": None,
+}
+
+
+class ControllerConfig:
+    def __init__(self, len_horizon: int = 15, actions_optimizer_params: dict = None,
+                 init_from_previous_actions: bool = True, restarts_optim: int = 1, optimize: bool = True,
+                 num_repeat_actions: int = 1):
+        """len_horizon: MPC steps; actions_optimizer_params: scipy L-BFGS-B options; init_from_previous_actions:
+        warm start from the shifted previous solution; restarts_optim: optimiser restarts; optimize: False =
+        random actions (debug); num_repeat_actions: each action is held this many env steps."""
+        self.len_horizon = len_horizon
+        self.actions_optimizer_params = dict(_DEFAULT_OPTIMIZER_PARAMS) if actions_optimizer_params is None \
+            else actions_optimizer_params
+        self.init_from_previous_actions = init_from_previous_actions
+        self.restarts_optim = restarts_optim
+        self.optimize = optimize
+        self.num_repeat_actions = num_repeat_actions

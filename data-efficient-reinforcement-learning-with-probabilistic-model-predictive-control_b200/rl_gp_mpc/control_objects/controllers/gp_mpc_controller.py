@@ -1,0 +1,197 @@
+"""GP-MPC controller with the reference's interface (control_objects/controllers/gp_mpc_controller.py),
+its objective evaluated by the B200 CUDA engine.
+
+  compute_mean_lcb_trajectory        gp_mpc_controller.py:229-285 -> one gpmpc_rollout call (value + gradient)
+  compute_mean_lcb_trajectory_batch  NEW: B candidate sequences in one call -> costs (B,), grads (B, H*Na)
+  get_action / _get_optimal_actions  gp_mpc_controller.py:52-153  same orchestration (scipy L-BFGS-B, restarts)
+The five side-effect tensors (:279-283) are kept; for a batch they describe the best candidate."""
+import multiprocessing
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+
+from rl_gp_mpc.config_classes.total_config import Config
+from rl_gp_mpc.control_objects.actions_mappers.action_init_functions import (
+    generate_mpc_action_init_frompreviousiter, generate_mpc_action_init_random)
+from rl_gp_mpc.control_objects.actions_mappers.derivative_action_mapper import DerivativeActionMapper
+from rl_gp_mpc.control_objects.actions_mappers.normalization_action_mapper import NormalizationActionMapper
+from rl_gp_mpc.control_objects.memories.gp_memory import Memory
+from rl_gp_mpc.control_objects.models.gp_model import GpStateTransitionModel
+from rl_gp_mpc.control_objects.observations_states_mappers.normalization_observation_state_mapper import \
+    NormalizationObservationStateMapper
+from rl_gp_mpc.control_objects.states_reward_mappers.setpoint_distance_reward_mapper import SetpointStateRewardMapper
+from rl_gp_mpc.control_objects.utils.pytorch_utils import Clamp
+
+from .abstract_controller import BaseControllerObject
+from .iteration_info_class import IterationInformation
+
+
+class GpMpcController(BaseControllerObject):
+    def __init__(self, observation_low, observation_high, action_low, action_high, config: Config, device=None):
+        self.config = config
+        self.observation_state_mapper = NormalizationObservationStateMapper(
+            config=config.observation, observation_low=observation_low, observation_high=observation_high)
+        mapper_cls = DerivativeActionMapper if config.actions.limit_action_change else NormalizationActionMapper
+        self.actions_mapper = mapper_cls(config=config.actions, action_low=action_low, action_high=action_high,
+                                         len_horizon=config.controller.len_horizon)
+        self.transition_model = GpStateTransitionModel(config=config.model,
+                                                       dim_state=self.observation_state_mapper.dim_observation,
+                                                       dim_action=self.actions_mapper.dim_action, device=device)
+        self.state_reward_mapper = SetpointStateRewardMapper(config=config.reward)
+        self.memory = Memory(config.memory, dim_input=self.transition_model.dim_input,
+                             dim_state=self.transition_model.dim_state,
+                             include_time_model=self.transition_model.config.include_time_model,
+                             step_model=config.controller.num_repeat_actions)
+        self.actions_mpc_previous_iter = None
+        self.clamp_lcb_class = Clamp()
+        self.iter_ctrl = 0
+        self.num_cores_main = multiprocessing.cpu_count()
+        self.ctx = multiprocessing.get_context("spawn")
+        self.queue_train = self.ctx.Queue()
+        self.info_iters = {}
+        self._cost_bound = False
+
+    # ------------------------------------------------------------------ control step
+    def get_action(self, obs_mu, obs_var=None, random: bool = False):
+        """Optimal (or random) raw action for the current observation (reference :52-112)."""
+        self.check_and_close_processes()
+        ctl = self.config.controller
+        if self.iter_ctrl % ctl.num_repeat_actions == 0:
+            self.memory.prepare_for_model()
+            state_mu, state_var = self.observation_state_mapper.get_state(obs=obs_mu, obs_var=obs_var,
+                                                                          update_internals=True)
+            actions_model = self._get_random_actions(state_mu, state_var) if random \
+                else self._get_optimal_actions(state_mu, state_var)
+            actions_raw = self.actions_mapper.transform_action_model_to_action_raw(actions_model, update_internals=True)
+            next_action_raw = actions_raw[0]
+            reward, reward_var = self.state_reward_mapper.get_reward(state_mu, state_var, actions_model[0])
+            states_std_pred = torch.diagonal(self.states_var_pred, dim1=-2, dim2=-1).sqrt()
+            idxs = np.arange(self.iter_ctrl, self.iter_ctrl + ctl.len_horizon * ctl.num_repeat_actions,
+                             ctl.num_repeat_actions)
+            self.iter_info = IterationInformation(
+                iteration=self.iter_ctrl, state=self.states_mu_pred[0], cost=-reward.item(),
+                cost_std=reward_var.sqrt().item(),
+                mean_predicted_cost=np.min([-self.rewards_trajectory.mean().item(), 3]),
+                mean_predicted_cost_std=self.rewards_traj_var.sqrt().mean().item(),
+                lower_bound_mean_predicted_cost=self.cost_traj_mean_lcb.item(), predicted_idxs=idxs,
+                predicted_states=self.states_mu_pred, predicted_states_std=states_std_pred,
+                predicted_actions=actions_model, predicted_costs=-self.rewards_trajectory,
+                predicted_costs_std=self.rewards_traj_var.sqrt())
+            self.store_iter_info(self.iter_info)
+            self.past_action = next_action_raw
+        else:
+            next_action_raw = self.past_action
+        self.iter_ctrl += 1
+        return np.array(next_action_raw)
+
+    def _prepare(self):
+        x_mem, y_mem = self.memory.get()
+        self.transition_model.prepare_inference(x_mem, y_mem)
+
+    def _get_optimal_actions(self, state_mu, state_var):
+        self._prepare()
+        ctl = self.config.controller
+        h, na = ctl.len_horizon, self.actions_mapper.dim_action
+        best_val, best_actions = np.inf, None
+        for idx_restart in range(ctl.restarts_optim):
+            warm = ctl.init_from_previous_actions and self.actions_mpc_previous_iter is not None and idx_restart == 0
+            x0 = generate_mpc_action_init_frompreviousiter(self.actions_mpc_previous_iter, dim_action=na) if warm \
+                else generate_mpc_action_init_random(len_horizon=h, dim_action=na)
+            if ctl.optimize:
+                res = minimize(fun=self.compute_mean_lcb_trajectory, x0=x0, jac=True, args=(state_mu, state_var),
+                               method="L-BFGS-B", bounds=self.actions_mapper.bounds,
+                               options=ctl.actions_optimizer_params)
+                cand, val = res.x, res.fun
+            else:
+                cand = generate_mpc_action_init_random(len_horizon=h, dim_action=na)
+                val, _ = self.compute_mean_lcb_trajectory(cand, state_mu, state_var)
+            if val < best_val or (best_actions is None and np.isnan(val)):
+                best_val, best_actions = val, cand
+        self.actions_mpc_previous_iter = best_actions.copy()
+        return self.actions_mapper.transform_action_mpc_to_action_model(torch.as_tensor(best_actions))
+
+    def _get_random_actions(self, state_mu, state_var):
+        h, na = self.config.controller.len_horizon, self.actions_mapper.dim_action
+        actions_mpc = generate_mpc_action_init_random(len_horizon=h, dim_action=na)
+        actions_model = self.actions_mapper.transform_action_mpc_to_action_model(torch.as_tensor(actions_mpc))
+        self._prepare()
+        self.compute_mean_lcb_trajectory(actions_mpc, state_mu, state_var)   # stores the trajectory info
+        return actions_model
+
+    # ------------------------------------------------------------------ memory / training hooks
+    def add_memory(self, obs, action, obs_new, reward, predicted_state=None, predicted_state_std=None):
+        state_mu, _ = self.observation_state_mapper.get_state(obs=obs, update_internals=False)
+        state_mu_new, _ = self.observation_state_mapper.get_state(obs=obs_new, update_internals=False)
+        action_model = self.actions_mapper.transform_action_raw_to_action_model(action)
+        self.memory.add(state_mu, action_model, state_mu_new, reward, iter_ctrl=self.iter_ctrl - 1,
+                        predicted_state=predicted_state, predicted_state_std=predicted_state_std)
+        busy = "p_train" in self.__dict__ and not self.p_train._closed
+        if self.iter_ctrl % self.config.training.training_frequency == 0 and not busy:
+            self.start_training_process()
+
+    def start_training_process(self):
+        """Reference :201-214 spawns the hyper-parameter trainer; fitting is outside the accelerated path
+        (GpStateTransitionModel.train keeps the current hyper-parameters), so nothing is spawned here."""
+        return None
+
+    def check_and_close_processes(self):
+        if "p_train" in self.__dict__ and not self.p_train._closed and not self.p_train.is_alive():
+            params = self.queue_train.get()
+            self.p_train.join()
+            for model, p in zip(self.transition_model.models, params):
+                model.initialize(**p)
+            self.p_train.close()
+            self._prepare()
+
+    # ------------------------------------------------------------------ objective
+    def _bind_cost(self):
+        if not self._cost_bound or self.transition_model._cost_key != id(self.config.reward):
+            self.transition_model.set_cost(self.config.reward)
+            self._cost_bound = True
+
+    def _rollout(self, actions_mpc, obs_mu, obs_var, need_grad=True):
+        self._bind_cost()
+        am = self.actions_mapper
+        limit = bool(self.config.actions.limit_action_change)
+        return self.transition_model.engine.rollout(
+            actions_mpc, obs_mu, obs_var, self.config.controller.len_horizon, iter_ctrl=self.iter_ctrl,
+            limit_action_change=limit,
+            max_change=self.config.actions.max_change_action_norm if limit else None,
+            action_prev=am.action_model_previous_iter if limit else None, need_grad=need_grad)
+
+    def _store_side_effects(self, out, idx):
+        self.cost_traj_mean_lcb = -out["cost"][idx].cpu()
+        self.states_mu_pred = out["states_mu_pred"][idx].cpu()
+        self.rewards_trajectory = out["rewards_trajectory"][idx].cpu()
+        self.rewards_traj_var = out["rewards_traj_var"][idx].cpu()
+        self.states_var_pred = out["states_var_pred"][idx].cpu()
+
+    def compute_mean_lcb_trajectory(self, actions_mpc, obs_mu, obs_var):
+        """(H*Na,) numpy -> (float, numpy (H*Na,)): LCB of the mean trajectory cost and its gradient."""
+        a = torch.as_tensor(np.asarray(actions_mpc, dtype=np.float64)).reshape(1, -1)
+        out = self._rollout(a, obs_mu, obs_var, need_grad=True)
+        self._store_side_effects(out, 0)
+        return out["cost"][0].item(), out["grad"][0].cpu().numpy()
+
+    def compute_mean_lcb_trajectory_batch(self, actions_mpc, obs_mu, obs_var, need_grad=True):
+        """(B, H*Na) -> costs (B,), grads (B, H*Na) as CUDA tensors; side effects = best candidate."""
+        a = torch.as_tensor(actions_mpc)
+        out = self._rollout(a.reshape(a.shape[0], -1), obs_mu, obs_var, need_grad=need_grad)
+        best = int(torch.argmin(torch.nan_to_num(out["cost"], nan=float("inf"))).item())
+        self._store_side_effects(out, best)
+        self.best_candidate = best
+        return out["cost"], out.get("grad")
+
+    def compute_cost_unnormalized(self, obs, action, obs_var=None):
+        state_mu, state_var = self.observation_state_mapper.get_state(obs=obs, obs_var=obs_var, update_internals=False)
+        action_model = self.actions_mapper.transform_action_raw_to_action_model(action)
+        reward_mu, reward_var = self.state_reward_mapper.get_reward(state_mu, state_var, action_model)
+        return -reward_mu.item(), reward_var.item()
+
+    def get_iter_info(self):
+        return self.iter_info
+
+    def store_iter_info(self, iter_info: IterationInformation):
+        for key, value in iter_info.__dict__.items():
+            self.info_iters.setdefault(key, []).append(value)

@@ -1,0 +1,197 @@
+"""GP state-transition model with the reference's interface (control_objects/models/gp_model.py), backed by
+the B200 CUDA engine (rl_gp_mpc/_cabi.py -> libgpmpc.so).
+
+  prepare_inference         gp_model.py:182-191   -> gpmpc_prepare  (Gram + Cholesky + iK + beta on device)
+  calculate_factorizations  gp_model.py:400-431   -> gpmpc_prepare / gpmpc_get_factorization
+  predict_next_state_change gp_model.py:112-180   -> gpmpc_predict_step   (also batched: (B,D), (B,D,D))
+  predict_trajectory        gp_model.py:60-110    -> gpmpc_rollout        (also batched: (B,H,Na))
+Legacy single-input calls take and return float64 tensors with the reference's shapes; the batched forms are
+additive.  There is no CPU fallback: without the extension / a CUDA device these methods raise."""
+import numpy as np
+import torch
+
+from rl_gp_mpc import _cabi
+from rl_gp_mpc.config_classes.model_config import ModelConfig
+
+from .abstract_model import AbstractStateTransitionModel
+from .gp_hyperparameters import ExactGPModelMonoTask, Interval
+
+
+class SavedState:
+    """Picklable bundle of the model (reference gp_model.py:13-36)."""
+
+    def __init__(self, inputs, states_change, parameters, constraints_hyperparams, models=None):
+        self.inputs = inputs
+        self.states_change = states_change
+        self.parameters = parameters
+        self.constraints_hyperparams = constraints_hyperparams
+        self.state_dicts_models = None if models is None else [m.state_dict() for m in models]
+
+    def to_arrays(self):
+        self.inputs = np.asarray(self.inputs)
+        self.states_change = np.asarray(self.states_change)
+        self.parameters = [{k: np.asarray(v) for k, v in p.items()} for p in self.parameters]
+        self.constraints_hyperparams = {k: (v.numpy() if isinstance(v, torch.Tensor) else v)
+                                        for k, v in self.constraints_hyperparams.items()}
+
+    def to_tensors(self):
+        self.inputs = torch.as_tensor(self.inputs)
+        self.states_change = torch.as_tensor(self.states_change)
+        self.parameters = [{k: torch.as_tensor(v) for k, v in p.items()} for p in self.parameters]
+        self.constraints_hyperparams = {k: (torch.as_tensor(v) if isinstance(v, np.ndarray) else v)
+                                        for k, v in self.constraints_hyperparams.items()}
+
+
+def create_models(gp_init_dict, constraints_gp, inputs=None, targets=None, num_models=None, num_inputs=None):
+    """Builds the per-state hyper-parameter containers with Interval constraints and init values
+    (reference gp_model.py:318-384)."""
+    if inputs is not None and targets is not None:
+        num_models = len(targets[0])
+        models = [ExactGPModelMonoTask(inputs, targets[:, i], len(inputs[0])) for i in range(num_models)]
+    else:
+        if num_models is None or num_inputs is None:
+            raise ValueError("If train_inputs or train_targets are None, num_models and num_inputs must be defined")
+        models = [ExactGPModelMonoTask(None, None, num_inputs) for _ in range(num_models)]
+    for i, model in enumerate(models):
+        if constraints_gp is not None:
+            if "min_std_noise" in constraints_gp and "max_std_noise" in constraints_gp:
+                model.likelihood.noise_covar.register_constraint(
+                    "raw_noise", Interval(torch.as_tensor(constraints_gp["min_std_noise"])[i] ** 2,
+                                          torch.as_tensor(constraints_gp["max_std_noise"])[i] ** 2))
+            if "min_outputscale" in constraints_gp:
+                model.covar_module.register_constraint(
+                    "raw_outputscale", Interval(constraints_gp["min_outputscale"][i], constraints_gp["max_outputscale"][i]))
+            if "min_lengthscale" in constraints_gp:
+                model.covar_module.base_kernel.register_constraint(
+                    "raw_lengthscale", Interval(constraints_gp["min_lengthscale"][i], constraints_gp["max_lengthscale"][i]))
+        if isinstance(gp_init_dict, list):
+            model.load_state_dict(gp_init_dict[i])
+        else:
+            model.likelihood.initialize(**{"noise_covar.noise": gp_init_dict["noise_covar.noise"][i]})
+            model.covar_module.initialize(**{"base_kernel.lengthscale": gp_init_dict["base_kernel.lengthscale"][i],
+                                             "outputscale": gp_init_dict["outputscale"][i]})
+    return models
+
+
+def _hyperparameters(models):
+    ls = torch.stack([m.covar_module.base_kernel.lengthscale[0] for m in models])
+    s2 = torch.stack([m.covar_module.outputscale.reshape(()) for m in models])
+    noise = torch.stack([m.likelihood.noise.reshape(()) for m in models])
+    return ls, s2, noise
+
+
+def calculate_factorizations(x, y, models, engine=None):
+    """iK = (K + noise I)^-1 (E,N,N) and beta = iK y (E,N) (reference gp_model.py:400-431), on the device."""
+    eng = engine or _cabi.Engine()
+    ls, s2, noise = _hyperparameters(models)
+    eng.prepare(x, y, ls, s2, noise)
+    return eng.factorization()
+
+
+class GpStateTransitionModel(AbstractStateTransitionModel):
+    def __init__(self, config: ModelConfig, dim_state, dim_action, device=None):
+        super().__init__(config, dim_state, dim_action)
+        if self.config.include_time_model:
+            self.dim_input += 1
+        self.config.extend_dimensions_params(dim_state=self.dim_state, dim_input=self.dim_input)
+        self.models = create_models(gp_init_dict=self.config.gp_init, constraints_gp=self.config.__dict__,
+                                    inputs=None, targets=None, num_models=self.dim_state, num_inputs=self.dim_input)
+        for m in self.models:
+            m.eval()
+        self._device = device
+        self._engine = None
+        self._cost_key = None
+        self.x_mem = self.y_mem = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = _cabi.Engine(self._device)   # raises without the extension / a CUDA device
+        return self._engine
+
+    def set_cost(self, reward_config):
+        """Binds the cost description used by the fused rollout (SetpointStateRewardMapper's config)."""
+        c = reward_config
+        self.engine.set_cost(c.target_state_action_norm, c.weight_matrix_cost, c.weight_matrix_cost_terminal,
+                             c.exploration_factor, c.use_constraints, c.state_min, c.state_max,
+                             c.clip_lower_bound_cost_to_0)
+        self._cost_key = id(reward_config)
+
+    def _ensure_cost(self):
+        if self._cost_key is None:   # predict_trajectory alone: a zero cost keeps the fused kernel happy
+            n = self.dim_state + self.dim_action
+            self.engine.set_cost(torch.zeros(n), torch.zeros((n, n)), torch.zeros((self.dim_state, self.dim_state)), 0.0)
+            self._cost_key = "zero"
+
+    # ------------------------------------------------------------------ reference API
+    def prepare_inference(self, inputs, state_changes):
+        self.x_mem = inputs
+        self.y_mem = state_changes
+        self.lengthscales, self.variances, noise = _hyperparameters(self.models)
+        self.engine.prepare(inputs, state_changes, self.lengthscales, self.variances, noise)
+        self.iL = torch.diag_embed(1.0 / self.lengthscales)
+        self._fact = None
+        if self._cost_key is not None and self._cost_key != "zero":
+            pass  # cost buffers live in the handle and survive prepare
+
+    def _factorization(self):
+        if self._fact is None:
+            self._fact = self.engine.factorization()
+        return self._fact
+
+    @property
+    def iK(self):
+        return self._factorization()[0].cpu()
+
+    @property
+    def beta(self):
+        return self._factorization()[1].cpu()
+
+    def predict_next_state_change(self, input_mu, input_var):
+        """(D,),(D,D) -> (M^T (1,E), S (E,E), V^T (D,E)); or batched (B,D),(B,D,D) -> (B,E),(B,E,E),(B,D,E)."""
+        mu = torch.as_tensor(input_mu)
+        var = torch.as_tensor(input_var)
+        single = mu.dim() == 1
+        if single:
+            mu, var = mu[None], var[None]
+        ev = self._uncertain_block(var)
+        M, S, V = self.engine.predict_step(mu, var[:, :ev, :ev])
+        if single:
+            return M.cpu(), S[0].cpu(), V[0].cpu()
+        return M, S, V
+
+    def _uncertain_block(self, var):
+        """Smallest leading block of the input covariance holding all non-zeros (E for rollouts, gp_model.py:96-97)."""
+        nz = (var != 0).any(0)
+        idx = torch.nonzero(nz.any(0) | nz.any(1)).flatten()
+        ev = int(idx.max().item()) + 1 if idx.numel() else 1
+        ev = max(ev, min(self.dim_state, 8))
+        if ev > 8:
+            raise _cabi.GpmpcError("input covariance has variance on more than 8 leading input dimensions")
+        return ev
+
+    def predict_trajectory(self, actions, obs_mu, obs_var, len_horizon, current_time_idx):
+        """actions (H,Na) -> (H+1,E),(H+1,E,E) like the reference; actions (B,H,Na) -> (B,H+1,E),(B,H+1,E,E)."""
+        self._ensure_cost()
+        a = torch.as_tensor(actions)
+        single = a.dim() == 2
+        if single:
+            a = a[None]
+        out = self.engine.rollout(a.reshape(a.shape[0], -1), obs_mu, obs_var, len_horizon, iter_ctrl=current_time_idx,
+                                  need_grad=False)
+        if single:
+            return out["states_mu_pred"][0].cpu(), out["states_var_pred"][0].cpu()
+        return out["states_mu_pred"], out["states_var_pred"]
+
+    @staticmethod
+    def train(queue, saved_state, lr_train, num_iter_train, clip_grad_value, print_train=False, step_print_train=25):
+        """Hyper-parameter fitting (reference gp_model.py:193-306) is outside the accelerated hot path
+        (SURVEY.md section 8(f) N2); the prior hyper-parameters are returned unchanged."""
+        saved_state.to_tensors()
+        queue.put([{k: np.asarray(v) for k, v in p.items()} for p in saved_state.parameters])
+
+    def save_state(self):
+        return SavedState(inputs=self.x_mem, states_change=self.y_mem,
+                          parameters=[m.state_dict() for m in self.models],
+                          constraints_hyperparams=self.config.__dict__)
