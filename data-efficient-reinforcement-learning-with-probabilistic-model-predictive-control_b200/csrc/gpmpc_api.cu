@@ -65,9 +65,50 @@ static int fail(gpmpc_handle* h, int code, const char* msg, cudaError_t ce = cud
     if (ce_ != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, #call, ce_);     \
   } while (0)
 
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+      v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
 extern "C" {
 
 int gpmpc_version(void) { return 100; }
+
+int gpmpc_fp64_peak(int device, double* flops_per_s) {
+  if (!flops_per_s) return GPMPC_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return GPMPC_ERR_NO_DEVICE; }
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GPMPC_ERR_CUDA;
+  const int grid = prop.multiProcessorCount * 4, blk = 512, iters = 4096;
+  double* buf = nullptr;
+  if (cudaMalloc(&buf, sizeof(double) * grid * blk) != cudaSuccess) return GPMPC_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<grid, blk>>>(buf, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  if (cudaGetLastError() != cudaSuccess) return GPMPC_ERR_CUDA;
+  *flops_per_s = 2.0 * 64.0 * (double)iters * grid * blk / (best * 1e-3);
+  return GPMPC_OK;
+}
 
 const char* gpmpc_last_error(const gpmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
 

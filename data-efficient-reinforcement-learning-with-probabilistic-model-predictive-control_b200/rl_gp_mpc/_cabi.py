@@ -31,6 +31,7 @@ _SIGNATURES = {
     "gpmpc_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "gpmpc_last_rollout_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "gpmpc_last_backward_ms": (ctypes.c_float, [ctypes.c_void_p]),
+    "gpmpc_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 }
 
 
@@ -72,6 +73,15 @@ def _f64(t, device, shape=None):
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(t.shape)))
     return t
+
+
+def measure_fp64_peak(device_index=0):
+    """Achieved float64 FLOP/s of a register-resident DFMA loop on this device (roofline denominator)."""
+    out = ctypes.c_double(0.0)
+    rc = load_library().gpmpc_fp64_peak(int(device_index), ctypes.byref(out))
+    if rc != GPMPC_OK:
+        raise GpmpcError("gpmpc_fp64_peak failed: %s" % _STATUS.get(rc, rc))
+    return out.value
 
 
 class Engine:

@@ -109,6 +109,10 @@ long long gpmpc_launch_count(const gpmpc_handle* h);
 float gpmpc_last_rollout_ms(gpmpc_handle* h);
 float gpmpc_last_backward_ms(gpmpc_handle* h);
 
+/* Measurement aid for bench.py: times a register-resident DFMA loop (8 independent chains per thread,
+ * 4 x 512 threads per SM) and returns the achieved float64 FLOP/s, the compute roofline of this path. */
+int gpmpc_fp64_peak(int device, double* flops_per_s);
+
 #ifdef __cplusplus
 }
 #endif
