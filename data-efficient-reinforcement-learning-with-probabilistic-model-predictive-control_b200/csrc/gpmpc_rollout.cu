@@ -28,7 +28,7 @@ namespace gpmpc {
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
   int nu, grp, kap, gam, rho, xi, out, nOut, PV;
-  int m, s, mu, A, c, il2, s2, logs2, Q, Wd, detR, Sraw, M, V, pacc, paccN, am, r, rv, ints, total;
+  int m, s, mu, A, c, il2, s2, logs2, Q, Wd, detR, Sraw, M, V, pacc, paccN, am, r, rv, ints, tab, total;
 };
 
 HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G, int H, int Na) {
@@ -65,6 +65,8 @@ HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G
   L.r = o; o += H + 1;
   L.rv = o; o += H + 1;
   L.ints = o; o += 2 + P;  // counter, bad flag, pair table (packed a*16+b)
+  o = (o + 1) & ~1;
+  L.tab = o; o += 32;      // 2^(j/32) for exp_tab
   L.total = (o + 1) & ~1;
   return L;
 }
@@ -207,7 +209,7 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
                                           const double* __restrict__ kka, const double* __restrict__ beta_a,
                                           const double* __restrict__ beta_b, const double* __restrict__ iKa,
                                           int I, int jbeg, int jend, int lane, double* s_gam, double* s_rho,
-                                          double* s_xi, double* s_acc) {
+                                          double* s_xi, double* s_acc, const double* __restrict__ s_tab) {
   const int NP = p.NP, DP = p.DP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
   double u0[EV], u1[EV], kr0, kr1;
@@ -265,8 +267,8 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
         t0 = fma(u0[e], nj[e], t0);
         t1 = fma(u1[e], nj[e], t1);
       }
-      double w0 = c0 * exp_fast(t0);
-      double w1 = c1 * exp_fast(t1);
+      double w0 = c0 * exp_tab(t0, s_tab);
+      double w1 = c1 * exp_tab(t1, s_tab);
       if (masked) {
         w0 = (j > i0) ? w0 : ((j == i0) ? 0.5 * w0 : 0.0);
         w1 = (j > i1) ? w1 : ((j == i1) ? 0.5 * w1 : 0.0);
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   double* s_r = sm + L.r;
   double* s_rv = sm + L.rv;
   int* s_int = reinterpret_cast<int*>(sm + L.ints);  // [0] counter, [1] bad flag, [2..] pair table
+  double* s_tab = sm + L.tab;
   const int nOut = L.nOut, PV = L.PV;
   const RecLayout RL = rec_layout(E, D);
   const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
@@ -345,6 +348,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   // ---- candidate-independent constants
   for (int o = tid; o < E * D; o += NT) s_il2[o] = p.il2[o];
   if (tid < E) { s_s2[tid] = p.s2[tid]; s_logs2[tid] = log(p.s2[tid]); }
+  if (tid >= 64 && tid < 96) s_tab[tid - 64] = exp2((double)(tid - 64) * 0.03125);
   if (tid == 0) {
     int pr = 0;
     for (int a = 0; a < E; a++)
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
             if (d < D) tail = fma(nu[d] * nu[d], la[d], tail);
           double lb = 0.0, kv = 0.0;
           if (i < N) {
-            lb = __ldg(p.beta + (size_t)a * NP + i) * exp_fast(-0.5 * (quad + tail));
+            lb = __ldg(p.beta + (size_t)a * NP + i) * exp_tab(-0.5 * (quad + tail), s_tab);
             kv = s_logs2[a] - 0.5 * (head + tail);
           }
           s_lb[a * NP + i] = lb;
@@ -599,12 +603,12 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
               pair_item<EV, GRAD, true>(p, s_nu, s_kap + pl * NP, Qm, s_il2 + a * D, s_il2 + b * D, kk + a * NP,
                                         p.beta + (size_t)a * NP, p.beta + (size_t)b * NP,
                                         p.iK + (size_t)a * NP * NP, I, jbeg, jend, lane, s_gam + pl * NP,
-                                        s_rho + pl * NP, s_xi + (size_t)pl * NP * EV, s_pacc + pl * L.paccN);
+                                        s_rho + pl * NP, s_xi + (size_t)pl * NP * EV, s_pacc + pl * L.paccN, s_tab);
             } else {
               pair_item<EV, GRAD, false>(p, s_nu, s_kap + pl * NP, Qm, s_il2 + a * D, s_il2 + b * D, kk + a * NP,
                                          p.beta + (size_t)a * NP, p.beta + (size_t)b * NP, nullptr, I, jbeg, jend,
                                          lane, s_gam + pl * NP, s_rho + pl * NP, s_xi + (size_t)pl * NP * EV,
-                                         s_pacc + pl * L.paccN);
+                                         s_pacc + pl * L.paccN, s_tab);
             }
           }
         }

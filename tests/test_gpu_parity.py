@@ -85,18 +85,20 @@ def test_cuda_matches_cpu_oracle(kw):
 
 
 def test_batched_equals_looped_and_is_order_independent():
-    """B candidates in one call == B single-candidate calls (bit-for-bit: no cross-candidate arithmetic)."""
+    """B candidates in one call == B single-candidate calls: no cross-candidate arithmetic.  Not bit-for-bit:
+    the N^2 partial sums are combined with shared-memory float64 atomics in warp-scheduling order, and the
+    covariance sums cancel by ~1e8, so repeated evaluations of the SAME candidate differ by ~1e-10."""
     cfg = make_workload("C2", B=300, H=4, seed=21)           # > 148 CTAs: exercises the persistent loop
     eng = make_engine(cfg)
     full = rollout(eng, cfg)
     for b in (0, 147, 148, 299):
         one = rollout(eng, cfg, actions=cfg["actions"][b:b + 1])
-        assert np.array_equal(one["cost"][0], full["cost"][b])
-        assert np.array_equal(one["grad"][0], full["grad"][b])
-        assert np.array_equal(one["states_var_pred"][0], full["states_var_pred"][b])
+        np.testing.assert_allclose(one["cost"][0], full["cost"][b], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(one["grad"][0], full["grad"][b], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(one["states_var_pred"][0], full["states_var_pred"][b], rtol=0, atol=1e-9)
     perm = np.random.default_rng(0).permutation(300)
     shuf = rollout(eng, cfg, actions=cfg["actions"][perm])
-    assert np.array_equal(shuf["cost"], full["cost"][perm])
+    np.testing.assert_allclose(shuf["cost"], full["cost"][perm], rtol=0, atol=1e-9)
 
 
 def test_gradient_against_central_differences():
@@ -126,7 +128,7 @@ def test_full_size_properties_headline_shape():
     np.testing.assert_allclose(out["cost"], -ucb.mean(1), rtol=0, atol=1e-14)
     # duplicated candidates give identical results; two oracle spot checks at full N
     dup = rollout(eng, cfg, actions=np.concatenate([cfg["actions"][:2], cfg["actions"][:2]]))
-    assert np.array_equal(dup["cost"][:2], dup["cost"][2:])
+    np.testing.assert_allclose(dup["cost"][:2], dup["cost"][2:], rtol=0, atol=1e-9)
     want = orc.evaluate_workload(cfg, candidates=[5])
     np.testing.assert_allclose(out["cost"][5], want["cost"][0], rtol=0, atol=ATOL)
     np.testing.assert_allclose(out["grad"][5], want["grad"][0], rtol=0, atol=ATOL_GRAD)
@@ -148,7 +150,7 @@ def test_per_candidate_initial_state_and_nan_propagation():
     mu[1, 0] = np.nan                                   # NaN flows out like in the reference, others unaffected
     out2 = eng.rollout(cfg["actions"], mu, var, cfg["H"], need_grad=False)
     torch.cuda.synchronize()
-    assert np.isnan(out2["cost"][1].item()) and abs(out2["cost"][0].item() - out["cost"][0].item()) == 0
+    assert np.isnan(out2["cost"][1].item()) and abs(out2["cost"][0].item() - out["cost"][0].item()) < 1e-9
 
 
 def test_error_codes():
