@@ -7,6 +7,7 @@
 #include "../../include/gpmpc.h"
 #include "gpmpc_common.cuh"
 #include "gpmpc_internal.h"
+#include "gpmpc_uniform_layout.cuh"
 
 using namespace gpmpc;
 
@@ -37,7 +38,9 @@ struct gpmpc_handle {
   std::string err;
   bool prepared = false, cost_set = false;
   int N = 0, NP = 0, D = 0, DP = 0, E = 0, Na = 0;
-  DevBuf x, il2, s2, ls, noise, beta, iK, Kbuf, Zbuf, info;
+  DevBuf x, il2, s2, ls, noise, beta, betaT, iK, Kbuf, Zbuf, info;
+  bool uniform = false;      // all GPs share one hyper-parameter set -> uniform-kernel fast path
+  int path_mode = 0;         // 0 auto, 1 force the general path
   DevBuf c_target, c_W, c_WT, c_smin, c_smax;
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
@@ -136,7 +139,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   if (!h) return GPMPC_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
+  DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
                    &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in};
   for (DevBuf* b : all) b->release();
@@ -162,6 +165,7 @@ int gpmpc_prepare(gpmpc_handle* h, const double* x, const double* y, const doubl
   CU(h->s2.ensure(sizeof(double) * E));
   CU(h->noise.ensure(sizeof(double) * E));
   CU(h->beta.ensure(sizeof(double) * E * NP));
+  CU(h->betaT.ensure(sizeof(double) * E * NP));
   CU(h->iK.ensure(sizeof(double) * (size_t)E * NP * NP));
   CU(h->Kbuf.ensure(sizeof(double) * (size_t)E * NP * NP));
   CU(h->Zbuf.ensure(sizeof(double) * (size_t)E * NP * (NP + 64)));
@@ -174,10 +178,20 @@ int gpmpc_prepare(gpmpc_handle* h, const double* x, const double* y, const doubl
   h->launches += 1;
   CU(launch_prepare(h->x.as<double>(), y, h->ls.as<double>(), h->s2.as<double>(), h->noise.as<double>(), N, NP, D, E,
                     h->Kbuf.as<double>(), h->Zbuf.as<double>(), h->iK.as<double>(), h->beta.as<double>(),
-                    h->info.as<int>(), st, &h->launches));
+                    h->betaT.as<double>(), h->info.as<int>(), st, &h->launches));
   int info[GPMPC_MAX_STATE];
   CU(cudaMemcpyAsync(info, h->info.ptr, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
+  double hyp[GPMPC_MAX_STATE * (GPMPC_MAX_INPUT + 2)];
+  CU(cudaMemcpyAsync(hyp, h->ls.ptr, sizeof(double) * E * D, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hyp + E * D, h->s2.ptr, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hyp + E * D + E, h->noise.ptr, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  bool uni = true;   // identical hyper-parameters for every GP (bitwise)
+  for (int a = 1; a < E && uni; a++) {
+    for (int d = 0; d < D; d++) uni = uni && (hyp[a * D + d] == hyp[d]);
+    uni = uni && (hyp[E * D + a] == hyp[E * D]) && (hyp[E * D + E + a] == hyp[E * D + E]);
+  }
+  h->uniform = uni;
   for (int a = 0; a < E; a++)
     if (info[a] != 0) {
       char msg[160];
@@ -321,6 +335,34 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     CU(h->records.ensure(sizeof(double) * (size_t)B * H * RL.size));
     p.records = h->records.as<double>();
   }
+  p.betaT = h->betaT.as<double>();
+  const bool use_uniform = h->uniform && h->path_mode == 0;
+  if (use_uniform) {
+    // uniform-kernel fast path: one exp per (i, j) for all output pairs; reverse-mode second sweep for the gradient
+    const UniRecLayout UR = uni_rec_layout(E);
+    if (want_grad) {
+      CU(h->records.ensure(sizeof(double) * (size_t)B * H * UR.size));
+      p.records = h->records.as<double>();
+    } else {
+      p.records = nullptr;
+    }
+    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na);
+    const size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na);
+    if (smf > h->smem_optin || smb > h->smem_optin)
+      return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
+    if (h->timing) CU(cudaEventRecord(h->ev[0], st));
+    CU(launch_uniform(E, false, p, nullptr, grid, smf, st));
+    h->launches += 1;
+    if (h->timing) { CU(cudaEventRecord(h->ev[1], st)); h->ev_fwd = true; }
+    h->ev_bwd = false;
+    if (want_grad) {
+      if (h->timing) CU(cudaEventRecord(h->ev[2], st));
+      CU(launch_uniform(E, true, p, grad, grid, smb, st));
+      h->launches += 1;
+      if (h->timing) { CU(cudaEventRecord(h->ev[3], st)); h->ev_bwd = true; }
+    }
+    return GPMPC_OK;
+  }
   if (h->timing) CU(cudaEventRecord(h->ev[0], st));
   CU(launch_rollout(E, want_grad, p, grid, smem, st));
   h->launches += 1;
@@ -342,6 +384,14 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
   }
   return GPMPC_OK;
 }
+
+int gpmpc_set_path(gpmpc_handle* h, int mode) {
+  if (!h || mode < 0 || mode > 1) return GPMPC_ERR_BAD_ARG;
+  h->path_mode = mode;
+  return GPMPC_OK;
+}
+
+int gpmpc_uses_uniform_path(const gpmpc_handle* h) { return (h && h->uniform && h->path_mode == 0) ? 1 : 0; }
 
 int gpmpc_enable_timing(gpmpc_handle* h, int on) {
   if (!h) return GPMPC_ERR_BAD_ARG;

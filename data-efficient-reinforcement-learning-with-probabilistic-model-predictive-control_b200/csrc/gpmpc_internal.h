@@ -8,6 +8,7 @@ struct RolloutParams {
   // ---- training block (resident in the handle; identical for every candidate -> L2 resident)
   const double* x;      // (N, D)
   const double* beta;   // (E, NP)   zero padded
+  const double* betaT;  // (NP, E)   transposed copy (uniform-kernel path)
   const double* iK;     // (E, NP, NP) symmetric, zero padded
   const double* il2;    // (E, D)  1 / lengthscale^2
   const double* s2;     // (E)     outputscale
@@ -53,9 +54,11 @@ size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int g
 int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, size_t smem_limit);
 cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
+size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na);
+cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
-                           double* iK, double* beta, int* info, cudaStream_t st, long long* launches);
+                           double* iK, double* beta, double* betaT, int* info, cudaStream_t st, long long* launches);
 cudaError_t launch_il2(const double* ls, double* il2, int n, cudaStream_t st);
 
 constexpr int ROLLOUT_THREADS = 512;

@@ -205,7 +205,7 @@ chol_solve_kernel(const double* __restrict__ Lall, const double* __restrict__ y,
 
 // iK[a][i][j] = 1/2 (X[i][j] + X[j][i]) (zero padded to NP x NP), beta[a][i] = X[i][N]
 __global__ void finalize_kernel(const double* __restrict__ Zall, double* __restrict__ iK,
-                                double* __restrict__ beta, int N, int NP) {
+                                double* __restrict__ beta, double* __restrict__ betaT, int N, int NP, int E) {
   const int a = blockIdx.z;
   const int NC = NP + 64;
   const double* Z = Zall + (size_t)a * NP * NC;
@@ -215,12 +215,16 @@ __global__ void finalize_kernel(const double* __restrict__ Zall, double* __restr
   double v = 0.0;
   if (i < N && j < N) v = 0.5 * (Z[(size_t)i * NC + j] + Z[(size_t)j * NC + i]);
   iK[((size_t)a * NP + i) * NP + j] = v;
-  if (j == 0) beta[(size_t)a * NP + i] = (i < N) ? Z[(size_t)i * NC + N] : 0.0;
+  if (j == 0) {
+    const double b = (i < N) ? Z[(size_t)i * NC + N] : 0.0;
+    beta[(size_t)a * NP + i] = b;
+    betaT[(size_t)i * E + a] = b;
+  }
 }
 
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
-                           double* iK, double* beta, int* info, cudaStream_t st, long long* launches) {
+                           double* iK, double* beta, double* betaT, int* info, cudaStream_t st, long long* launches) {
   dim3 blk(32, 8);
   dim3 grd((NP + 31) / 32, (NP + 7) / 8, E);
   cudaMemsetAsync(info, 0, sizeof(int) * E, st);
@@ -230,7 +234,7 @@ cudaError_t launch_prepare(const double* x, const double* y, const double* ls, c
   cholesky_kernel<<<E, 1024, sm1, st>>>(Kbuf, N, NP, info);
   size_t sm2 = NP * sizeof(double);
   chol_solve_kernel<<<E, 1024, sm2, st>>>(Kbuf, y, Zbuf, N, NP, E);
-  finalize_kernel<<<grd, blk, 0, st>>>(Zbuf, iK, beta, N, NP);
+  finalize_kernel<<<grd, blk, 0, st>>>(Zbuf, iK, beta, betaT, N, NP, E);
   *launches += 4;
   return cudaGetLastError();
 }

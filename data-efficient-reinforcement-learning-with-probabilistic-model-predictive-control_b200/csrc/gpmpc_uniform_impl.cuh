@@ -1,0 +1,785 @@
+// "Uniform-kernel" fast path: all E GPs share one hyper-parameter set (ARD lengthscales, outputscale, noise)
+// -- the reference's configuration before hyper-parameter training (examples/*/config_*.py:41-45 give every GP
+// the same values).  Then K_a = K for all a, hence ONE iK, and in gp_model.py:156-169 R_ab, Q_ab, z_a,i and the
+// whole exponent are independent of (a, b):
+//       L^{ab}_ij = s2^2 * Eh_ij ,   Eh_ij = exp(kap_i + kap_j + u_i . nu_j)
+//       S^raw_ab  = s2^2 * ( beta_a^T Eh beta_b  -  [a==b] tr(iK Eh) )
+// so one N x N sweep with ONE exp per element serves all E(E+1)/2 output pairs: N^2 exps per prediction
+// instead of (E/2 + E(E-1)/2) N^2.  The mean part shares A = (s + Lambda)^-1 and exp(-q_i/2) as well.
+//
+// Gradient: reverse mode.  With P = E(E+1)/2 scalar outputs per exp, emitting forward-mode Jacobians (general
+// path) would cost ~4x more than a second N^2 sweep with the adjoint-weighted coefficient
+//       W_ij = (Omega beta_i) . beta_j - wbar * iK_ij ,    w_ij = W_ij Eh_ij   (symmetric, upper-triangle sweep)
+// from which dS/dm and dS/dQ follow exactly as for a diagonal pair of the general path (rho, gamma, xi sums).
+// uniform_fwd_kernel stores only (M, V^E, h, g^E, S^raw) per step; uniform_bwd_kernel runs the reverse sweep
+// with one CTA per candidate.  tests/algo_spec.py remains the executable spec of the mathematics.
+#pragma once
+#include "gpmpc_rollout_impl.cuh"
+#include "gpmpc_uniform_layout.cuh"
+
+namespace gpmpc {
+
+// ---------------------------------------------------------------------------------------------
+// forward hot loop: full sweep, rows {64 I + lane, +32}, columns [jbeg, jend)
+//   r_b,i += Eh_ij beta_b,j  (E FMAs),  tr += Eh_ij iK_ij  (1 FMA)   [gp_model.py:169-175 for all (a,b) at once]
+// ---------------------------------------------------------------------------------------------
+template <int EV>
+__device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_nu,
+                                             const double* __restrict__ s_kap, const double* __restrict__ Qm,
+                                             const double* __restrict__ il2, int I, int jbeg, int jend, int lane,
+                                             double* s_acc, const double* __restrict__ s_tab) {
+  constexpr int E = EV;
+  const int NP = p.NP, DP = p.DP;
+  const int i0 = 64 * I + lane, i1 = i0 + 32;
+  double u0[EV], u1[EV];
+  {
+    double z0[EV], z1[EV];
+#pragma unroll
+    for (int e = 0; e < EV; e++) { z0[e] = s_nu[i0 * DP + e] * il2[e]; z1[e] = s_nu[i1 * DP + e] * il2[e]; }
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+      for (int f = 0; f < EV; f++) { q0 = fma(Qm[e * EV + f], z0[f], q0); q1 = fma(Qm[e * EV + f], z1[f], q1); }
+      u0[e] = 2.0 * q0 * il2[e];
+      u1[e] = 2.0 * q1 * il2[e];
+    }
+  }
+  const double kr0 = s_kap[i0], kr1 = s_kap[i1];
+  double r0[E], r1[E], tr = 0.0;
+#pragma unroll
+  for (int b = 0; b < E; b++) { r0[b] = 0.0; r1[b] = 0.0; }
+  const double* __restrict__ betaT = p.betaT;   // [j][E]
+  const double* __restrict__ iK = p.iK;
+#pragma unroll 4
+  for (int j = jbeg; j < jend; j++) {
+    double nj[EV], bj[E];
+#pragma unroll
+    for (int e = 0; e < EV; e++) nj[e] = s_nu[j * DP + e];
+#pragma unroll
+    for (int b = 0; b < E; b++) bj[b] = __ldg(betaT + (size_t)j * E + b);
+    const double kj = s_kap[j];
+    const double k0 = __ldg(iK + (size_t)j * NP + i0), k1 = __ldg(iK + (size_t)j * NP + i1);
+    double t0 = kr0 + kj, t1 = kr1 + kj;
+#pragma unroll
+    for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
+    const double e0 = exp_tab(t0, s_tab), e1 = exp_tab(t1, s_tab);
+#pragma unroll
+    for (int b = 0; b < E; b++) { r0[b] = fma(e0, bj[b], r0[b]); r1[b] = fma(e1, bj[b], r1[b]); }
+    tr = fma(e0, k0, tr);
+    tr = fma(e1, k1, tr);
+  }
+  // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace
+  double bi0[E], bi1[E];
+#pragma unroll
+  for (int b = 0; b < E; b++) { bi0[b] = __ldg(betaT + (size_t)i0 * E + b); bi1[b] = __ldg(betaT + (size_t)i1 * E + b); }
+  int pr = 0;
+#pragma unroll
+  for (int a = 0; a < E; a++)
+#pragma unroll
+    for (int b = a; b < E; b++) {
+      double v = warp_sum(bi0[a] * r0[b] + bi1[a] * r1[b]);
+      if (lane == 0) atomicAdd(s_acc + pr, v);
+      pr++;
+    }
+  tr = warp_sum(tr);
+  if (lane == 0) atomicAdd(s_acc + pr, tr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// uniform forward kernel (value + small per-step record when p.records != NULL)
+// ---------------------------------------------------------------------------------------------
+template <int EV>
+__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) uniform_fwd_kernel(const RolloutParams p) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int E = EV;
+  const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+  const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
+  constexpr int P = E * (E + 1) / 2;
+  const UniLayout L = make_uni_layout(EV, false, NP, DP, D, H, Na);
+  double* s_nu = sm + L.nu; double* s_kap = sm + L.kap; double* s_lb = sm + L.lb; double* s_out = sm + L.out;
+  double* s_m = sm + L.m; double* s_s = sm + L.s; double* s_mu = sm + L.mu; double* s_A = sm + L.A;
+  double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
+  double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
+  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
+  const int nOut = L.nOut;
+  const UniRecLayout RL = uni_rec_layout(E);
+  const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
+  const double* il2 = p.il2;            // row 0 (all rows equal)
+  const double s2 = p.s2[0];
+  if (tid >= 64 && tid < 96) s_tab[tid - 64] = exp2((double)(tid - 64) * 0.03125);
+  __syncthreads();
+
+  for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
+    if (tid < E) {
+      double v = p.obs_mu[(p.per_cand_init ? (size_t)cand * E : 0) + tid];
+      s_mu[tid] = v;
+      p.states_mu[((size_t)cand * (H + 1)) * E + tid] = v;
+    }
+    if (tid < E * E) {
+      double v = p.obs_var[(p.per_cand_init ? (size_t)cand * E * E : 0) + tid];
+      s_s[tid] = v;
+      p.states_var[((size_t)cand * (H + 1)) * E * E + tid] = v;
+    }
+    if (tid < Na) {
+      double cum = 0.0;
+      for (int t = 0; t < H; t++) {
+        double raw = p.actions_mpc[(size_t)cand * H * Na + t * Na + tid], am;
+        if (p.limit_change) {
+          double mc = p.max_change[tid];
+          raw = raw * 2.0 * mc - mc;
+          if (t == 0) raw += p.action_prev[tid];
+          cum += raw;
+          am = fmin(fmax(cum, 0.0), 1.0);
+        } else {
+          am = raw;
+        }
+        s_am[t * Na + tid] = am;
+        p.actions_model[(size_t)cand * H * Na + t * Na + tid] = am;
+      }
+    }
+    __syncthreads();
+    for (int t = 1; t <= H; t++) {
+      // ---- P0: model input, stage cost, shared small matrices
+      if (tid < D) {
+        double v;
+        if (tid < E) v = s_mu[tid];
+        else if (tid < E + Na) v = s_am[(t - 1) * Na + (tid - E)];
+        else v = (double)(p.iter_ctrl + t - 1);
+        s_m[tid] = v;
+      }
+      if (tid == 32) {
+        double cmu, cvar;
+        stage_cost(cv, E, Na, s_mu, s_s, s_am + (t - 1) * Na, cmu, cvar);
+        s_r[t - 1] = -cmu;
+        s_rv[t - 1] = cvar;
+      }
+      if (tid == 64) {
+        double Ca[EV * EV], Ai[EV * EV], det, pl = 1.0;
+        for (int e = 0; e < EV; e++)
+          for (int f = 0; f < EV; f++) Ca[e * EV + f] = s_s[e * EV + f] + (e == f ? 1.0 / il2[e] : 0.0);
+        spd_inv_det<EV>(Ca, Ai, det);
+        for (int e = 0; e < EV; e++) pl *= il2[e];
+        for (int e = 0; e < EV * EV; e++) s_A[e] = Ai[e];
+        s_misc[0] = s2 / sqrt(det * pl);   // c (same for all GPs)
+      }
+      if (tid == 96) {
+        double Wd[EV], Rinv[EV * EV], Qm[EV * EV], detR;
+        for (int e = 0; e < EV; e++) Wd[e] = 2.0 * il2[e];
+        pair_matrices<EV>(s_s, Wd, Rinv, Qm, detR);
+        for (int e = 0; e < EV * EV; e++) s_Q[e] = Qm[e];
+        s_misc[1] = detR;
+      }
+      if (tid < P + 1) s_acc[tid] = 0.0;
+      if (tid == 0) s_int[0] = 0;
+      __syncthreads();
+      if (tid == 100) {
+        double chk = 0.0;
+        for (int d = 0; d < D; d++) chk += s_m[d];
+        for (int e = 0; e < EV * EV; e++) chk += s_s[e];
+        s_int[1] = isfinite(chk) ? 0 : 1;
+      }
+      // ---- P1: nu, shared exponent terms, kap
+      for (int i = tid; i < NP; i += NT) {
+        double nu[GPMPC_MAX_D];
+#pragma unroll
+        for (int d = 0; d < GPMPC_MAX_D; d++) {
+          if (d < DP) {
+            double v = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
+            nu[d] = v;
+            s_nu[i * DP + d] = v;
+          } else {
+            nu[d] = 0.0;
+          }
+        }
+        double quad = 0.0, head = 0.0, tail = 0.0, zqz = 0.0;
+#pragma unroll
+        for (int e = 0; e < EV; e++) {
+          double r = 0.0, q = 0.0;
+#pragma unroll
+          for (int f = 0; f < EV; f++) {
+            r = fma(s_A[e * EV + f], nu[f], r);
+            q = fma(s_Q[e * EV + f], nu[f] * il2[f], q);
+          }
+          quad = fma(nu[e], r, quad);
+          head = fma(nu[e] * nu[e], il2[e], head);
+          zqz = fma(nu[e] * il2[e], q, zqz);
+        }
+#pragma unroll
+        for (int d = EV; d < GPMPC_MAX_D; d++)
+          if (d < D) tail = fma(nu[d] * nu[d], il2[d], tail);
+        const double ei = (i < N) ? exp_tab(-0.5 * (quad + tail), s_tab) : 0.0;
+#pragma unroll
+        for (int a = 0; a < E; a++) s_lb[a * NP + i] = ei * __ldg(p.betaT + (size_t)i * E + a);
+        s_kap[i] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;   // log s2 factored out (s2^2 applied at the end)
+      }
+      __syncthreads();
+      // ---- P2: h_a, g_a
+      for (int o = tid; o < E * nOut; o += NT) {
+        const int a = o / nOut, q = o - a * nOut;
+        const double* lb = s_lb + a * NP;
+        double acc = 0.0;
+        if (q == 0) {
+          for (int i = 0; i < N; i++) acc += lb[i];
+        } else {
+          const int d1 = q - 1;
+          for (int i = 0; i < N; i++) acc = fma(lb[i], s_nu[i * DP + d1], acc);
+        }
+        s_out[o] = acc;
+      }
+      // ---- P3: one N x N sweep for all pairs
+      {
+        const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg, nitems = nrb * nseg;
+        for (;;) {
+          int item = 0;
+          if (lane == 0) item = atomicAdd(&s_int[0], 1);
+          item = __shfl_sync(0xffffffffu, item, 0);
+          if (item >= nitems) break;
+          const int I = item / nseg, js = item - I * nseg;
+          const int jbeg = js * p.seg, jend = min(NP, jbeg + p.seg);
+          uni_fwd_item<EV>(p, s_nu, s_kap, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab);
+        }
+      }
+      __syncthreads();
+      // ---- P4: mean, V, S, recurrence
+      if (tid == 0) {
+        const double c = s_misc[0], detR = s_misc[1], rs = 1.0 / sqrt(detR);
+        const bool bad = s_int[1] != 0;
+        double S[GPMPC_MAX_EV * GPMPC_MAX_EV];
+        double* rec = p.records ? p.records + ((size_t)cand * H + (t - 1)) * RL.size : nullptr;
+        for (int a = 0; a < E; a++) {
+          const double* out = s_out + a * nOut;
+          const double h = out[0];
+          const double* g = out + 1;
+          s_M[a] = c * h;
+          for (int e = 0; e < EV; e++) {
+            double v = 0.0;
+            for (int f = 0; f < EV; f++) v += s_A[e * EV + f] * g[f];
+            s_V[a * D + e] = c * v;
+          }
+          for (int d = EV; d < D; d++) s_V[a * D + d] = c * g[d] * il2[d];
+          if (rec) {
+            rec[RL.offM + a] = s_M[a];
+            rec[RL.offH + a] = h;
+            for (int e = 0; e < E; e++) { rec[RL.offV + a * E + e] = s_V[a * D + e]; rec[RL.offG + a * E + e] = g[e]; }
+          }
+        }
+        const double trc = s_acc[P];
+        int pr = 0;
+        for (int a = 0; a < E; a++)
+          for (int b = a; b < E; b++) {
+            const double Sraw = s2 * s2 * (s_acc[pr] - (a == b ? trc : 0.0));
+            if (rec) rec[RL.offS + pr] = Sraw;
+            double v = Sraw * rs - s_M[a] * s_M[b] + (a == b ? s2 : 0.0);
+            if (bad) v = nan("");
+            S[a * E + b] = v;
+            S[b * E + a] = v;
+            pr++;
+          }
+        double sv[GPMPC_MAX_EV * GPMPC_MAX_EV], sn[GPMPC_MAX_EV * GPMPC_MAX_EV];
+        for (int e = 0; e < E; e++)
+          for (int a = 0; a < E; a++) {
+            double v = 0.0;
+            for (int k = 0; k < E; k++) v += s_s[e * E + k] * s_V[a * D + k];
+            sv[e * E + a] = v;
+          }
+        for (int e = 0; e < E; e++)
+          for (int f = 0; f < E; f++) sn[e * E + f] = S[e * E + f] + s_s[e * E + f] + sv[e * E + f] + sv[f * E + e];
+        for (int e = 0; e < E; e++) {
+          double v = s_mu[e] + s_M[e];
+          if (bad) v = nan("");
+          s_mu[e] = v;
+          p.states_mu[((size_t)cand * (H + 1) + t) * E + e] = v;
+        }
+        for (int e = 0; e < E * E; e++) {
+          s_s[e] = sn[e];
+          p.states_var[((size_t)cand * (H + 1) + t) * E * E + e] = sn[e];
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      double cmu, cvar;
+      terminal_cost(cv, E, s_mu, s_s, cmu, cvar);
+      s_r[H] = -cmu;
+      s_rv[H] = cvar;
+      double acc = 0.0;
+      for (int t = 0; t <= H; t++) {
+        double ucb = s_r[t] + p.kappa * sqrt(s_rv[t]);
+        if (p.clip) ucb = fmin(ucb, 0.0);
+        acc += ucb;
+        p.rewards[(size_t)cand * (H + 1) + t] = s_r[t];
+        p.rewards_var[(size_t)cand * (H + 1) + t] = s_rv[t];
+      }
+      p.cost[cand] = -acc / (double)(H + 1);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reverse sweep hot loop: upper-triangle sweep with the adjoint-weighted coefficient
+//   W_ij = p_i . beta_j - wbar iK_ij ,  w_ij = W_ij Eh_ij ; rows: rho_i, xi_i ; columns: gam_j
+// ---------------------------------------------------------------------------------------------
+template <int EV>
+__device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_nu,
+                                             const double* __restrict__ s_kap, const double* __restrict__ Qm,
+                                             const double* __restrict__ il2, const double* __restrict__ Om,
+                                             double wbar, int I, int jbeg, int jend, int lane, double* s_gam,
+                                             double* s_rho, double* s_xi, const double* __restrict__ s_tab) {
+  constexpr int E = EV;
+  const int NP = p.NP, DP = p.DP;
+  const int i0 = 64 * I + lane, i1 = i0 + 32;
+  double u0[EV], u1[EV], p0[E], p1[E];
+  {
+    double z0[EV], z1[EV];
+#pragma unroll
+    for (int e = 0; e < EV; e++) { z0[e] = s_nu[i0 * DP + e] * il2[e]; z1[e] = s_nu[i1 * DP + e] * il2[e]; }
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+      for (int f = 0; f < EV; f++) { q0 = fma(Qm[e * EV + f], z0[f], q0); q1 = fma(Qm[e * EV + f], z1[f], q1); }
+      u0[e] = 2.0 * q0 * il2[e];
+      u1[e] = 2.0 * q1 * il2[e];
+    }
+    double b0[E], b1[E];
+#pragma unroll
+    for (int b = 0; b < E; b++) { b0[b] = __ldg(p.betaT + (size_t)i0 * E + b); b1[b] = __ldg(p.betaT + (size_t)i1 * E + b); }
+#pragma unroll
+    for (int a = 0; a < E; a++) {
+      double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+      for (int b = 0; b < E; b++) { v0 = fma(Om[a * E + b], b0[b], v0); v1 = fma(Om[a * E + b], b1[b], v1); }
+      p0[a] = v0;
+      p1[a] = v1;
+    }
+  }
+  const double kr0 = s_kap[i0], kr1 = s_kap[i1];
+  double rho0 = 0.0, rho1 = 0.0, xi0[EV], xi1[EV];
+#pragma unroll
+  for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
+  const double* __restrict__ betaT = p.betaT;
+  const double* __restrict__ iK = p.iK;
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    const bool masked = (j0 < 64 * I + 64);
+    double v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const int j = j0 + jj;
+      double nj[EV];
+#pragma unroll
+      for (int e = 0; e < EV; e++) nj[e] = s_nu[j * DP + e];
+      double c0 = -wbar * __ldg(iK + (size_t)j * NP + i0), c1 = -wbar * __ldg(iK + (size_t)j * NP + i1);
+#pragma unroll
+      for (int b = 0; b < E; b++) {
+        const double bj = __ldg(betaT + (size_t)j * E + b);
+        c0 = fma(p0[b], bj, c0);
+        c1 = fma(p1[b], bj, c1);
+      }
+      const double kj = s_kap[j];
+      double t0 = kr0 + kj, t1 = kr1 + kj;
+#pragma unroll
+      for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
+      double w0 = c0 * exp_tab(t0, s_tab), w1 = c1 * exp_tab(t1, s_tab);
+      if (masked) {
+        w0 = (j > i0) ? w0 : ((j == i0) ? 0.5 * w0 : 0.0);
+        w1 = (j > i1) ? w1 : ((j == i1) ? 0.5 * w1 : 0.0);
+      }
+      rho0 += w0;
+      rho1 += w1;
+#pragma unroll
+      for (int e = 0; e < EV; e++) { xi0[e] = fma(w0, nj[e], xi0[e]); xi1[e] = fma(w1, nj[e], xi1[e]); }
+      v[jj] = w0 + w1;
+    }
+    int col;
+    double tot = col_reduce8(v, lane, col);
+    if ((lane & 3) == 0) atomicAdd(s_gam + j0 + col, tot);
+  }
+  atomicAdd(s_rho + i0, rho0);
+  atomicAdd(s_rho + i1, rho1);
+#pragma unroll
+  for (int e = 0; e < EV; e++) { atomicAdd(s_xi + i0 * EV + e, xi0[e]); atomicAdd(s_xi + i1 * EV + e, xi1[e]); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
+// ---------------------------------------------------------------------------------------------
+template <int EV>
+__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int E = EV, P = E * (E + 1) / 2;
+  const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+  const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H, Dc = E + Na;
+  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na);
+  double* s_nu = sm + L.nu; double* s_kap = sm + L.kap; double* s_lb = sm + L.lb;
+  double* s_rho = sm + L.rho; double* s_gam = sm + L.gam; double* s_xi = sm + L.xi;
+  double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
+  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
+  double* s2p = sm + L.small2;
+  // small2 carve: mu_bar[E], s_bar[E2], Om[E2], Rinv[E2], Ub[E2], Vb[E2], hg[E + E2] (h_bar, g_bar), scal[16]
+  double* s_mubar = s2p; double* s_sbar = s_mubar + GPMPC_MAX_EV; double* s_Om = s_sbar + EV * EV;
+  double* s_Rinv = s_Om + EV * EV; double* s_U = s_Rinv + EV * EV; double* s_Vb = s_U + EV * EV;
+  double* s_hbar = s_Vb + EV * EV; double* s_gbar = s_hbar + GPMPC_MAX_EV; double* s_scal = s_gbar + EV * EV;
+  const UniRecLayout RL = uni_rec_layout(E);
+  const double* il2 = p.il2;
+  const double s2 = p.s2[0];
+  const double wmu = 1.0 / (double)(H + 1);
+  if (tid >= 64 && tid < 96) s_tab[tid - 64] = exp2((double)(tid - 64) * 0.03125);
+  __syncthreads();
+  // accumulator layout: [0] unused, [1 .. D] G_m, [1+D .. 1+D+E2) G_Q, then N-pass: Phi_m[D], Phi_A[P]
+  const int accGm = 1, accGQ = 1 + D, accPm = 1 + D + EV * EV, accPA = accPm + D;
+
+  for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
+    const double* mus = p.states_mu + (size_t)cand * (H + 1) * E;
+    const double* vars = p.states_var + (size_t)cand * (H + 1) * E * E;
+    const double* rvs = p.rewards_var + (size_t)cand * (H + 1);
+    const double* ams = p.actions_model + (size_t)cand * H * Na;
+    double* gout = grad + (size_t)cand * H * Na;
+    if (tid == 0) {  // terminal adjoint (setpoint_distance_reward_mapper.py:124-142)
+      const double* mu = mus + (size_t)H * E;
+      const double* s = vars + (size_t)H * E * E;
+      const double wv = -p.kappa * wmu * 0.5 / sqrt(rvs[H]);
+      double e[E], We[E], sWe[E], t1[E * E];
+      for (int d = 0; d < E; d++) e[d] = mu[d] - p.c_target[d];
+      for (int d = 0; d < E; d++) { double v = 0.0; for (int k = 0; k < E; k++) v += p.c_WT[d * E + k] * e[k]; We[d] = v; }
+      for (int d = 0; d < E; d++) { double v = 0.0; for (int k = 0; k < E; k++) v += s[d * E + k] * We[k]; sWe[d] = v; }
+      for (int d = 0; d < E; d++) {
+        double v = 0.0;
+        for (int k = 0; k < E; k++) v += p.c_WT[k * E + d] * sWe[k];
+        s_mubar[d] = wmu * 2.0 * We[d] + wv * 8.0 * v;
+      }
+      for (int i = 0; i < E; i++)
+        for (int k = 0; k < E; k++) { double v = 0.0; for (int l = 0; l < E; l++) v += p.c_WT[l * E + i] * s[k * E + l]; t1[i * E + k] = v; }
+      for (int i = 0; i < E; i++)
+        for (int k = 0; k < E; k++) {
+          double v = 0.0;
+          for (int l = 0; l < E; l++) v += t1[i * E + l] * p.c_WT[k * E + l];
+          s_sbar[i * E + k] = wmu * p.c_WT[k * E + i] + wv * (4.0 * v + 4.0 * We[i] * We[k]);
+        }
+    }
+    __syncthreads();
+    for (int t = H; t >= 1; t--) {
+      const double* rec = p.records + ((size_t)cand * H + (t - 1)) * RL.size;
+      const double* sp = vars + (size_t)(t - 1) * E * E;
+      const double* mup = mus + (size_t)(t - 1) * E;
+      const double* am = ams + (size_t)(t - 1) * Na;
+      // ---- B0: model input, shared matrices, adjoint coefficients (thread 0: O(E^3))
+      if (tid < D) s_m[tid] = (tid < E) ? mup[tid] : (tid < E + Na ? am[tid - E] : (double)(p.iter_ctrl + t - 1));
+      for (int o = tid; o < L.accN + 1; o += NT) s_acc[o] = 0.0;
+      for (int o = tid; o < NP; o += NT) { s_rho[o] = 0.0; s_gam[o] = 0.0; }
+      for (int o = tid; o < NP * EV; o += NT) s_xi[o] = 0.0;
+      if (tid == 0) {
+        s_int[0] = 0;
+        double Ca[EV * EV], Ai[EV * EV], det, pl = 1.0, Wd[EV], Rinv[EV * EV], Qm[EV * EV], detR;
+        for (int e = 0; e < EV; e++)
+          for (int f = 0; f < EV; f++) Ca[e * EV + f] = sp[e * EV + f] + (e == f ? 1.0 / il2[e] : 0.0);
+        spd_inv_det<EV>(Ca, Ai, det);
+        for (int e = 0; e < EV; e++) { pl *= il2[e]; Wd[e] = 2.0 * il2[e]; }
+        const double c = s2 / sqrt(det * pl);
+        pair_matrices<EV>(sp, Wd, Rinv, Qm, detR);
+        for (int e = 0; e < EV * EV; e++) { s_A[e] = Ai[e]; s_Q[e] = Qm[e]; s_Rinv[e] = Rinv[e]; }
+        const double rs = 1.0 / sqrt(detR);
+        const double* Mrec = rec + RL.offM;
+        // U = s_bar + s_bar^T ; V_bar[a][e] = sum_k sp[k][e] U[k][a]
+        for (int i = 0; i < E; i++)
+          for (int k = 0; k < E; k++) s_U[i * E + k] = s_sbar[i * E + k] + s_sbar[k * E + i];
+        for (int a = 0; a < E; a++)
+          for (int e = 0; e < E; e++) {
+            double v = 0.0;
+            for (int k = 0; k < E; k++) v += sp[k * E + e] * s_U[k * E + a];
+            s_Vb[a * E + e] = v;
+          }
+        double M_bar[E], detR_bar = 0.0, wbar = 0.0;
+        for (int a = 0; a < E; a++) M_bar[a] = s_mubar[a];
+        int pr = 0;
+        for (int a = 0; a < E; a++)
+          for (int b = a; b < E; b++) {
+            const double sb = s_sbar[a * E + b] + (a != b ? s_sbar[b * E + a] : 0.0);
+            M_bar[a] -= sb * Mrec[b];
+            M_bar[b] -= sb * Mrec[a];
+            const double Sraw = rec[RL.offS + pr];
+            detR_bar += -0.5 * sb * Sraw * rs / detR;
+            const double om = sb * rs * s2 * s2;          // d L / d Shat_ab
+            if (a == b) { s_Om[a * E + a] = om; wbar += om; }
+            else { s_Om[a * E + b] = 0.5 * om; s_Om[b * E + a] = 0.5 * om; }
+            pr++;
+          }
+        // mean part adjoints: c_bar (summed), h_bar_a, g_bar_a, A_bar (direct part)
+        double cbar_c = 0.0;     // sum_a c_bar_a * c
+        double A_bar[EV * EV];
+        for (int e = 0; e < EV * EV; e++) A_bar[e] = 0.0;
+        for (int a = 0; a < E; a++) {
+          const double h = rec[RL.offH + a];
+          const double* gE = rec + RL.offG + a * E;
+          double cb = M_bar[a] * h;
+          for (int e = 0; e < E; e++) {
+            double v = 0.0;
+            for (int f = 0; f < E; f++) v += Ai[e * E + f] * gE[f];
+            cb += s_Vb[a * E + e] * v;
+          }
+          cbar_c += cb * c;
+          s_hbar[a] = M_bar[a] * c;
+          for (int e = 0; e < E; e++) {
+            double v = 0.0;
+            for (int f = 0; f < E; f++) v += Ai[f * E + e] * s_Vb[a * E + f];
+            s_gbar[a * E + e] = c * v;
+          }
+          for (int k = 0; k < E; k++)
+            for (int l = 0; l < E; l++) A_bar[k * E + l] += c * s_Vb[a * E + k] * gE[l];
+        }
+        s_scal[0] = c; s_scal[1] = detR; s_scal[2] = detR_bar; s_scal[3] = wbar; s_scal[4] = cbar_c;
+        for (int e = 0; e < EV * EV; e++) s_scal[8 + e] = A_bar[e];   // needs 8 + E2 <= 72 doubles
+      }
+      __syncthreads();
+      // ---- B1: nu, exponent terms, lb (as in the forward)
+      for (int i = tid; i < NP; i += NT) {
+        double nu[GPMPC_MAX_D];
+#pragma unroll
+        for (int d = 0; d < GPMPC_MAX_D; d++) {
+          if (d < DP) {
+            double v = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
+            nu[d] = v;
+            s_nu[i * DP + d] = v;
+          } else {
+            nu[d] = 0.0;
+          }
+        }
+        double quad = 0.0, head = 0.0, tail = 0.0, zqz = 0.0, an[GPMPC_MAX_D];
+#pragma unroll
+        for (int e = 0; e < EV; e++) {
+          double r = 0.0, q = 0.0;
+#pragma unroll
+          for (int f = 0; f < EV; f++) {
+            r = fma(s_A[e * EV + f], nu[f], r);
+            q = fma(s_Q[e * EV + f], nu[f] * il2[f], q);
+          }
+          an[e] = r;
+          quad = fma(nu[e], r, quad);
+          head = fma(nu[e] * nu[e], il2[e], head);
+          zqz = fma(nu[e] * il2[e], q, zqz);
+        }
+#pragma unroll
+        for (int d = EV; d < GPMPC_MAX_D; d++) {
+          an[d] = 0.0;
+          if (d < D) { tail = fma(nu[d] * nu[d], il2[d], tail); an[d] = nu[d] * il2[d]; }
+        }
+        const double ei = (i < N) ? exp_tab(-0.5 * (quad + tail), s_tab) : 0.0;
+        s_kap[i] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;
+        // N pass of the mean part: phi_i = sum_a lb_a,i (h_bar_a + g_bar_a . nu_i^E)
+        double phi = 0.0;
+#pragma unroll
+        for (int a = 0; a < E; a++) {
+          double w = s_hbar[a];
+#pragma unroll
+          for (int e = 0; e < EV; e++) w = fma(s_gbar[a * E + e], nu[e], w);
+          phi = fma(ei * __ldg(p.betaT + (size_t)i * E + a), w, phi);
+        }
+        // reduce phi * an (D) and phi * nu nu^T (P) over the block
+#pragma unroll
+        for (int d = 0; d < GPMPC_MAX_D; d++)
+          if (d < D) {
+            double v = warp_sum(phi * an[d]);
+            if (lane == 0) atomicAdd(s_acc + accPm + d, v);
+          }
+        int w = 0;
+#pragma unroll
+        for (int k = 0; k < EV; k++)
+#pragma unroll
+          for (int l = k; l < EV; l++) {
+            double v = warp_sum(phi * nu[k] * nu[l]);
+            if (lane == 0) atomicAdd(s_acc + accPA + w, v);
+            w++;
+          }
+      }
+      __syncthreads();
+      // ---- B2: adjoint-weighted N^2 sweep (upper triangle)
+      {
+        const double wbar = s_scal[3];
+        const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg, nitems = nrb * nseg;
+        for (;;) {
+          int item = 0;
+          if (lane == 0) item = atomicAdd(&s_int[0], 1);
+          item = __shfl_sync(0xffffffffu, item, 0);
+          if (item >= nitems) break;
+          const int I = item / nseg, js = item - I * nseg;
+          int jbeg = js * p.seg;
+          const int jend = min(NP, jbeg + p.seg);
+          if (jend <= 64 * I) continue;
+          jbeg = max(jbeg, 64 * I);
+          uni_bwd_item<EV>(p, s_nu, s_kap, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam, s_rho, s_xi, s_tab);
+        }
+      }
+      __syncthreads();
+      // ---- B3: reduce (rho, gam, xi) -> G_m (D), G_Q (E x E)   [same formulas as a diagonal pair]
+      {
+        double gm[GPMPC_MAX_D], gQ[EV * EV];
+#pragma unroll
+        for (int d = 0; d < GPMPC_MAX_D; d++) gm[d] = 0.0;
+#pragma unroll
+        for (int e = 0; e < EV * EV; e++) gQ[e] = 0.0;
+        for (int i = tid; i < N; i += NT) {
+          const double rg = s_rho[i] + s_gam[i];
+          double z[EV], xs[EV];
+#pragma unroll
+          for (int d = 0; d < GPMPC_MAX_D; d++)
+            if (d < D) gm[d] = fma(rg * il2[d], s_nu[i * DP + d], gm[d]);
+#pragma unroll
+          for (int e = 0; e < EV; e++) { z[e] = s_nu[i * DP + e] * il2[e]; xs[e] = s_xi[(size_t)i * EV + e] * il2[e]; }
+#pragma unroll
+          for (int e = 0; e < EV; e++)
+#pragma unroll
+            for (int f = 0; f < EV; f++) gQ[e * EV + f] += rg * z[e] * z[f] + z[e] * xs[f] + z[f] * xs[e];
+        }
+        for (int d = 0; d < D; d++) {
+          double v = warp_sum(gm[d]);
+          if (lane == 0) atomicAdd(s_acc + accGm + d, v);
+        }
+#pragma unroll
+        for (int e = 0; e < EV * EV; e++) {
+          double v = warp_sum(gQ[e]);
+          if (lane == 0) atomicAdd(s_acc + accGQ + e, v);
+        }
+      }
+      __syncthreads();
+      // ---- B4: small algebra (thread 0): assemble m_bar, s_prev_bar, stage-cost adjoints
+      if (tid == 0) {
+        const double c = s_scal[0], detR = s_scal[1], detR_bar = s_scal[2], cbar_c = s_scal[4];
+        double m_bar[GPMPC_MAX_D], sp_bar[EV * EV], Wd[EV], A_bar[EV * EV];
+        for (int e = 0; e < EV; e++) Wd[e] = 2.0 * il2[e];
+        for (int e = 0; e < EV * EV; e++) { sp_bar[e] = 0.0; A_bar[e] = s_scal[8 + e]; }
+        // pair part: x2 for the upper-triangle sweep, ybar correction, then Q/detR adjoints
+        double Gm[GPMPC_MAX_D], GQ[EV * EV], yb[EV];
+        for (int d = 0; d < D; d++) Gm[d] = 2.0 * s_acc[accGm + d];
+        for (int e = 0; e < EV * EV; e++) GQ[e] = 2.0 * s_acc[accGQ + e];
+        for (int e = 0; e < EV; e++) yb[e] = Gm[e];
+        for (int e = 0; e < EV; e++) {
+          double v = 0.0;
+          for (int f = 0; f < EV; f++) v += s_Q[e * EV + f] * yb[f];
+          Gm[e] -= 2.0 * Wd[e] * v;
+        }
+        for (int d = 0; d < D; d++) m_bar[d] = Gm[d];
+        double RQ[EV * EV];
+        for (int i = 0; i < E; i++)
+          for (int k = 0; k < E; k++) {
+            double v = 0.0;
+            for (int l = 0; l < E; l++) v += s_Rinv[l * E + i] * GQ[l * E + k];
+            RQ[i * E + k] = v;
+          }
+        for (int i = 0; i < E; i++)
+          for (int k = 0; k < E; k++) {
+            double v = 0.0;
+            for (int l = 0; l < E; l++) v += RQ[i * E + l] * s_Q[k * E + l];
+            sp_bar[i * E + k] += 0.5 * RQ[i * E + k] - v * Wd[k] + detR_bar * detR * s_Rinv[k * E + i] * Wd[k];
+          }
+        // mean part: m_bar += Phi_m - sum_a h_a g_bar_a (state dims) ; A_bar += -1/2 Phi_A
+        for (int d = 0; d < D; d++) m_bar[d] += s_acc[accPm + d];
+        for (int a = 0; a < E; a++) {
+          const double h = rec[RL.offH + a];
+          for (int e = 0; e < E; e++) m_bar[e] -= h * s_gbar[a * E + e];
+        }
+        {
+          int w = 0;
+          for (int k = 0; k < E; k++)
+            for (int l = k; l < E; l++) {
+              const double v = -0.5 * s_acc[accPA + w];
+              A_bar[k * E + l] += v;
+              if (l != k) A_bar[l * E + k] += v;
+              w++;
+            }
+        }
+        double t1[EV * EV];
+        for (int i = 0; i < E; i++)
+          for (int k = 0; k < E; k++) {
+            double v = 0.0;
+            for (int l = 0; l < E; l++) v += s_A[l * E + i] * A_bar[l * E + k];
+            t1[i * E + k] = v;
+          }
+        for (int i = 0; i < E; i++)
+          for (int k = 0; k < E; k++) {
+            double v = 0.0;
+            for (int l = 0; l < E; l++) v += t1[i * E + l] * s_A[k * E + l];
+            sp_bar[i * E + k] += -0.5 * cbar_c * s_A[k * E + i] - v;
+          }
+        (void)c;
+        // recurrence terms
+        const double* Vrec = rec + RL.offV;
+        double X[EV * EV], nsb[EV * EV], nmu[EV], a_bar[GPMPC_MAX_D];
+        for (int i = 0; i < E; i++)
+          for (int k = 0; k < E; k++) {
+            double v = 0.0;
+            for (int a = 0; a < E; a++) v += s_U[i * E + a] * Vrec[a * E + k];
+            X[i * E + k] = v;
+          }
+        for (int i = 0; i < E; i++)
+          for (int k = 0; k < E; k++)
+            nsb[i * E + k] = 0.5 * (sp_bar[i * E + k] + sp_bar[k * E + i]) + 0.5 * (s_sbar[i * E + k] + s_sbar[k * E + i]) +
+                             0.5 * (X[i * E + k] + X[k * E + i]);
+        for (int e = 0; e < E; e++) nmu[e] = s_mubar[e] + m_bar[e];
+        for (int k = 0; k < Na; k++) a_bar[k] = m_bar[E + k];
+        {  // stage cost at t-1
+          const double wv = -p.kappa * wmu * 0.5 / sqrt(rvs[t - 1]);
+          double e[GPMPC_MAX_D], We[GPMPC_MAX_D], sWe[EV];
+          for (int d = 0; d < Dc; d++) e[d] = (d < E ? mup[d] : am[d - E]) - p.c_target[d];
+          for (int d = 0; d < Dc; d++) { double v = 0.0; for (int k = 0; k < Dc; k++) v += p.c_W[d * Dc + k] * e[k]; We[d] = v; }
+          for (int i = 0; i < E; i++) { double v = 0.0; for (int k = 0; k < E; k++) v += sp[i * E + k] * We[k]; sWe[i] = v; }
+          for (int d = 0; d < Dc; d++) {
+            double v = 0.0;
+            for (int i = 0; i < E; i++) v += p.c_W[i * Dc + d] * sWe[i];
+            const double gd = wmu * 2.0 * We[d] + wv * 8.0 * v;
+            if (d < E) nmu[d] += gd; else a_bar[d - E] += gd;
+          }
+          for (int i = 0; i < E; i++)
+            for (int k = 0; k < E; k++) { double v = 0.0; for (int l = 0; l < E; l++) v += p.c_W[l * Dc + i] * sp[k * E + l]; t1[i * E + k] = v; }
+          for (int i = 0; i < E; i++)
+            for (int k = 0; k < E; k++) {
+              double v = 0.0;
+              for (int l = 0; l < E; l++) v += t1[i * E + l] * p.c_W[k * Dc + l];
+              const double full_ik = wmu * p.c_W[k * Dc + i] + wv * (4.0 * v + 4.0 * We[i] * We[k]);
+              nsb[i * E + k] += 0.5 * full_ik;
+              nsb[k * E + i] += 0.5 * full_ik;
+            }
+          if (p.use_constraints) {
+            const double rt2 = 1.4142135623730951, ispi = 0.5641895835477563;
+            for (int d = 0; d < E; d++) {
+              double sig = sp[d * E + d];
+              double zmin = (p.c_smin[d] - mup[d]) / (sig * rt2), zmax = (p.c_smax[d] - mup[d]) / (sig * rt2);
+              double pmin = exp(-zmin * zmin) * ispi, pmax = exp(-zmax * zmax) * ispi;
+              nmu[d] += wmu * (pmin - pmax) * (-1.0 / (sig * rt2));
+              nsb[d * E + d] += wmu * (pmin * (-zmin / sig) - pmax * (-zmax / sig));
+            }
+          }
+        }
+        for (int k = 0; k < Na; k++) gout[(size_t)(t - 1) * Na + k] = a_bar[k];
+        for (int e = 0; e < E; e++) s_mubar[e] = nmu[e];
+        for (int e = 0; e < E * E; e++) s_sbar[e] = nsb[e];
+      }
+      __syncthreads();
+    }
+    if (p.limit_change && tid < Na) {
+      double cum = 0.0;
+      for (int t = H - 1; t >= 0; t--) {
+        cum += gout[(size_t)t * Na + tid];
+        gout[(size_t)t * Na + tid] = cum * 2.0 * p.max_change[tid];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int EV>
+cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  if (bwd) {
+    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    uniform_bwd_kernel<EV><<<grid, ROLLOUT_THREADS, smem, st>>>(p, grad);
+  } else {
+    e = cudaFuncSetAttribute(uniform_fwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    uniform_fwd_kernel<EV><<<grid, ROLLOUT_THREADS, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace gpmpc

@@ -1,0 +1,54 @@
+// Shared-memory plan and per-step record of the uniform-kernel path (host sizing + device carving).
+#pragma once
+#include "gpmpc_common.cuh"
+#include "gpmpc_internal.h"
+
+namespace gpmpc {
+
+struct UniLayout {
+  int nu, kap, lb, rho, gam, xi, out, nOut;
+  int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
+};
+
+// bwd=false: forward kernel; bwd=true: reverse-sweep kernel (needs rho/gam/xi arrays)
+HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int Na) {
+  UniLayout L;
+  const int E = EV, P = E * (E + 1) / 2;
+  int o = 0;
+  L.nu = o; o += NP * DP;
+  L.kap = o; o += NP;
+  L.lb = o; if (!bwd) o += E * NP; // lb[a][i]: forward P1/P2 only (the reverse sweep recomputes it inline)
+  L.rho = o; L.gam = o; L.xi = o;
+  if (bwd) { L.rho = o; o += NP; L.gam = o; o += NP; L.xi = o; o += NP * EV; }
+  L.nOut = 1 + D;
+  L.out = o; o += E * L.nOut;
+  L.m = o; o += GPMPC_MAX_D;
+  L.s = o; o += EV * EV;
+  L.mu = o; o += GPMPC_MAX_EV;
+  L.A = o; o += EV * EV;
+  L.Q = o; o += EV * EV;
+  L.misc = o; o += 16;             // c, detR, detB, s2, ...
+  L.M = o; o += GPMPC_MAX_EV;
+  L.V = o; o += E * D;
+  L.accN = bwd ? (1 + D + EV * EV + D + P) : (P + 1);
+  L.acc = o; o += L.accN + 1;
+  L.am = o; o += H * Na + 1;
+  L.r = o; o += H + 1;
+  L.rv = o; o += H + 1;
+  L.ints = o; o += 4;
+  o = (o + 1) & ~1;
+  L.tab = o; o += 32;
+  L.small2 = o; o += bwd ? (8 * EV * EV + 8 * GPMPC_MAX_D + E * E + 64) : 0;
+  L.total = (o + 1) & ~1;
+  return L;
+}
+
+struct UniRecLayout { int offM, offV, offH, offG, offS, size; };
+HD UniRecLayout uni_rec_layout(int E) {
+  UniRecLayout r;
+  r.offM = 0; r.offV = E; r.offH = E + E * E; r.offG = r.offH + E; r.offS = r.offG + E * E;
+  r.size = r.offS + E * (E + 1) / 2;
+  return r;
+}
+
+}  // namespace gpmpc

@@ -27,6 +27,8 @@ _SIGNATURES = {
     "gpmpc_predict_step": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 4),
     "gpmpc_rollout": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
                       + [ctypes.c_void_p] * 7 + [ctypes.c_void_p]),
+    "gpmpc_set_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "gpmpc_uses_uniform_path": (ctypes.c_int, [ctypes.c_void_p]),
     "gpmpc_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gpmpc_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "gpmpc_last_rollout_ms": (ctypes.c_float, [ctypes.c_void_p]),
@@ -197,6 +199,13 @@ class Engine:
                                                 _ptr(grad), _ptr(smu), _ptr(svar), _ptr(rew), _ptr(rewv), _ptr(am),
                                                 self._stream()))
         return o
+
+    def set_path(self, mode):
+        """0: automatic (uniform-kernel fast path when all GPs share their hyper-parameters), 1: general path."""
+        self._check(self._lib.gpmpc_set_path(self._h, int(mode)))
+
+    def uses_uniform_path(self):
+        return bool(self._lib.gpmpc_uses_uniform_path(self._h))
 
     def enable_timing(self, on=True):
         self._lib.gpmpc_enable_timing(self._h, int(on))

@@ -101,6 +101,13 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
                   double* cost, double* grad, double* states_mu, double* states_var,
                   double* rewards, double* rewards_var, double* actions_model, void* stream);
 
+/* Kernel-path selection.  When every GP has bitwise-identical hyper-parameters (the reference's state before
+ * hyper-parameter training, examples/<env>/config_<env>.py:41-45) gpmpc_rollout uses the "uniform-kernel" path
+ * (one exp per (i,j) for all output pairs).  mode 0: automatic (default); mode 1: always the general path.
+ * gpmpc_uses_uniform_path reports which one the next rollout will take. */
+int gpmpc_set_path(gpmpc_handle* h, int mode);
+int gpmpc_uses_uniform_path(const gpmpc_handle* h);
+
 /* Introspection for benchmarks/tests: number of kernels launched by this handle so far, and the
  * device time [ms] of the last rollout's forward kernel measured with CUDA events on `stream`
  * (valid after the stream has been synchronised; <0 if timing was not enabled). */

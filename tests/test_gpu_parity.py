@@ -18,9 +18,12 @@ ATOL = 1e-8
 ATOL_GRAD = 1e-7
 
 
-def make_engine(cfg):
+def make_engine(cfg, path=0):
+    """path 0: automatic kernel selection (uniform-kernel fast path when all GPs share their hyper-parameters),
+    path 1: force the general per-pair path."""
     from rl_gp_mpc import _cabi
     eng = _cabi.Engine()
+    eng.set_path(path)
     eng.prepare(cfg["x"], cfg["y"], full_lengthscale(cfg), cfg["outputscale"], cfg["noise"])
     r = cfg["reward"]
     W = np.diag(np.concatenate([r["weight_state"], r["weight_action"]]).astype(float))
@@ -39,10 +42,12 @@ def rollout(eng, cfg, actions=None, need_grad=True):
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
+@pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("name", case_names())
-def test_cuda_matches_reference_golden(name):
+def test_cuda_matches_reference_golden(name, path):
     cfg, gold = load_case(name)
-    eng = make_engine(cfg)
+    eng = make_engine(cfg, path)
+    assert eng.uses_uniform_path() == (path == 0 and name != "distinct_ls_e4")
     iK, beta = eng.factorization()
     scale = np.abs(gold["iK"]).max()
     assert np.abs(iK.cpu().numpy() - gold["iK"]).max() <= 1e-9 * scale          # calculate_factorizations
@@ -72,9 +77,12 @@ def test_cuda_matches_reference_golden(name):
     dict(E=8, Na=3, N=96, H=2, B=2, ls=0.7, seed=16),                     # C5 dims, small N
     dict(E=3, Na=1, N=70, H=4, B=3, ls=0.5, seed=17, limit_action_change=True, include_time_model=True, iter_ctrl=9),
 ])
-def test_cuda_matches_cpu_oracle(kw):
+@pytest.mark.parametrize("path", [0, 1])
+def test_cuda_matches_cpu_oracle(kw, path):
     cfg = make_workload(**kw)
-    eng = make_engine(cfg)
+    if path == 1 and kw.get("distinct_lengthscales"):
+        pytest.skip("already on the general path")
+    eng = make_engine(cfg, path)
     want = orc.evaluate_workload(cfg)
     got = rollout(eng, cfg)
     np.testing.assert_allclose(got["cost"], want["cost"], rtol=0, atol=ATOL)
@@ -84,11 +92,12 @@ def test_cuda_matches_cpu_oracle(kw):
     np.testing.assert_allclose(got["rewards_traj_var"], want["rewards_traj_var"], rtol=0, atol=ATOL)
 
 
-def test_batched_equals_looped_and_is_order_independent():
+@pytest.mark.parametrize("distinct", [False, True])
+def test_batched_equals_looped_and_is_order_independent(distinct):
     """B candidates in one call == B single-candidate calls: no cross-candidate arithmetic.  Not bit-for-bit:
     the N^2 partial sums are combined with shared-memory float64 atomics in warp-scheduling order, and the
     covariance sums cancel by ~1e8, so repeated evaluations of the SAME candidate differ by ~1e-10."""
-    cfg = make_workload("C2", B=300, H=4, seed=21)           # > 148 CTAs: exercises the persistent loop
+    cfg = make_workload("C2", B=300, H=4, seed=21, distinct_lengthscales=distinct)   # > 148 CTAs: persistent loop
     eng = make_engine(cfg)
     full = rollout(eng, cfg)
     for b in (0, 147, 148, 299):
@@ -113,9 +122,10 @@ def test_gradient_against_central_differences():
     np.testing.assert_allclose(base["grad"][0], fd, rtol=0, atol=5e-7)
 
 
-def test_full_size_properties_headline_shape():
+@pytest.mark.parametrize("distinct", [False, True])
+def test_full_size_properties_headline_shape(distinct):
     """BASELINE config 4 sizes (N=500, E=4, Na=2) on a slice of the batch: invariants that need no oracle."""
-    cfg = make_workload("C4b", B=64, H=5, seed=23)
+    cfg = make_workload("C4b", B=64, H=5, seed=23, distinct_lengthscales=distinct)
     eng = make_engine(cfg)
     out = rollout(eng, cfg)
     var = out["states_var_pred"]

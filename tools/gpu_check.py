@@ -15,8 +15,9 @@ from rl_gp_mpc import _cabi  # noqa: E402
 from tests.golden_utils import case_names, load_case  # noqa: E402
 
 
-def engine_for(cfg):
+def engine_for(cfg, path=0):
     eng = _cabi.Engine()
+    eng.set_path(path)
     eng.prepare(cfg["x"], cfg["y"], full_lengthscale(cfg), cfg["outputscale"], cfg["noise"])
     r = cfg["reward"]
     E, Na = cfg["E"], cfg["Na"]
@@ -41,8 +42,10 @@ def err(a, b):
 def main():
     print(torch.cuda.get_device_name(0))
     for name in case_names():
+      for path in (0, 1):
         cfg, gold = load_case(name)
-        eng = engine_for(cfg)
+        eng = engine_for(cfg, path)
+        name = name + ("/U" if eng.uses_uniform_path() else "/G")
         iK, beta = eng.factorization()
         E = cfg["E"]
         M, S, V = eng.predict_step(gold["step_in_mu"][None], gold["step_in_var"][None, :E, :E])
@@ -56,17 +59,22 @@ def main():
             err(out["states_mu_pred"].cpu(), gold["states_mu_pred"]), err(out["states_var_pred"].cpu(), gold["states_var_pred"]),
             err(out["rewards_traj_var"].cpu(), gold["rewards_traj_var"]), err(out2["cost"].cpu(), gold["cost"])), flush=True)
     # quick timing on the headline shape (small batch, short horizon)
-    for wl, B, H in (("C4b", 296, 4), ("C4a", 296, 4), ("C2", 296, 4)):
+    for wl, B, H, path in (("C4b", 296, 4, 0), ("C4b", 296, 4, 1), ("C4b", 1184, 6, 0), ("C4a", 296, 4, 0), ("C2", 296, 4, 0), ("C5", 148, 2, 0), ("C5", 148, 2, 1)):
         cfg = make_workload(wl, B=B, H=H)
-        eng = engine_for(cfg)
+        eng = engine_for(cfg, path)
+        wl = wl + ("/U" if eng.uses_uniform_path() else "/G")
         eng.enable_timing(True)
         for need_grad in (False, True):
-            for it in range(2):
-                run_rollout(eng, cfg, need_grad=need_grad)
-                torch.cuda.synchronize()
-            ms = eng.last_rollout_ms()
-            print("%s B=%d H=%d grad=%d: fwd %.2f ms -> %.0f preds/s ; bwd %.3f ms" % (
-                wl, B, H, need_grad, ms, B * H / ms * 1e3, eng.last_backward_ms()), flush=True)
+            try:
+                for it in range(2):
+                    run_rollout(eng, cfg, need_grad=need_grad)
+                    torch.cuda.synchronize()
+            except Exception as exc:
+                print("%s B=%d H=%d grad=%d: FAILED %s" % (wl, B, H, need_grad, exc), flush=True)
+                continue
+            ms, mb = eng.last_rollout_ms(), max(eng.last_backward_ms(), 0.0)
+            print("%s B=%d H=%d grad=%d: fwd %.2f ms bwd %.3f ms -> %.0f preds/s" % (
+                wl, B, H, need_grad, ms, mb, B * H / (ms + mb) * 1e3), flush=True)
         t0 = time.time(); eng.prepare(cfg["x"], cfg["y"], full_lengthscale(cfg), cfg["outputscale"], cfg["noise"]); torch.cuda.synchronize()
         print("prepare N=%d: %.1f ms" % (cfg["N"], (time.time() - t0) * 1e3))
 
