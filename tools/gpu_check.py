@@ -45,7 +45,7 @@ def main():
       for path in (0, 1):
         cfg, gold = load_case(name)
         eng = engine_for(cfg, path)
-        name = name + ("/U" if eng.uses_uniform_path() else "/G")
+        label = name + ("/U" if eng.uses_uniform_path() else "/G")
         iK, beta = eng.factorization()
         E = cfg["E"]
         M, S, V = eng.predict_step(gold["step_in_mu"][None], gold["step_in_var"][None, :E, :E])
@@ -53,7 +53,7 @@ def main():
         out2 = run_rollout(eng, cfg, need_grad=False)
         torch.cuda.synchronize()
         print("%-20s iK %.1e (scale %.1e) beta %.1e | step M %.1e S %.1e V %.1e | cost %.1e grad %.1e mu %.1e var %.1e rv %.1e | fwd-only cost %.1e" % (
-            name, err(iK.cpu(), gold["iK"]), np.abs(gold["iK"]).max(), err(beta.cpu(), gold["beta"]),
+            label, err(iK.cpu(), gold["iK"]), np.abs(gold["iK"]).max(), err(beta.cpu(), gold["beta"]),
             err(M.cpu()[0], gold["step_M"][0]), err(S.cpu()[0], gold["step_S"]), err(V.cpu()[0], gold["step_V"]),
             err(out["cost"].cpu(), gold["cost"]), err(out["grad"].cpu(), gold["grad"]),
             err(out["states_mu_pred"].cpu(), gold["states_mu_pred"]), err(out["states_var_pred"].cpu(), gold["states_var_pred"]),
