@@ -1,5 +1,6 @@
 // C ABI of libgpmpc.so (include/gpmpc.h): handle, workspace and kernel orchestration.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -252,15 +253,24 @@ int gpmpc_set_cost(gpmpc_handle* h, const double* target, const double* W, const
 }
 
 static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int B, int H, int Na, size_t* smem,
-                       int* grid) {
+                       int* grid, bool uniform = false) {
   p.x = h->x.as<double>(); p.beta = h->beta.as<double>(); p.iK = h->iK.as<double>();
   p.il2 = h->il2.as<double>(); p.s2 = h->s2.as<double>();
   p.N = h->N; p.NP = h->NP; p.D = h->D; p.DP = h->DP; p.E = h->E; p.Na = Na;
   p.B = B; p.H = H;
+  p.betaT = h->betaT.as<double>();
+  p.seg = 256;
+  p.seg_bwd = 64;
+  if (uniform) {
+    p.group = 1;
+    p.seg = 128;
+    *smem = 0;
+    *grid = 0;
+    return GPMPC_OK;
+  }
   const int G = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, h->smem_optin);
   if (G < 1) return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
   p.group = G;
-  p.seg = 256;
   *smem = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G, H, Na);
   *grid = B < h->num_sms ? B : h->num_sms;
   cudaError_t ce = h->ws_kk.ensure(sizeof(double) * (size_t)(*grid) * h->E * h->NP);
@@ -311,7 +321,8 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
   RolloutParams p;
   memset(&p, 0, sizeof(p));
   size_t smem; int grid;
-  int rc = fill_common(h, p, E, want_grad, B, H, Na, &smem, &grid);
+  const bool use_uniform = h->uniform && h->path_mode == 0;
+  int rc = fill_common(h, p, E, want_grad, B, H, Na, &smem, &grid, use_uniform);
   if (rc) return rc;
   p.mode = 0;
   p.include_time = include_time; p.iter_ctrl = iter_ctrl; p.per_cand_init = per_candidate_init ? 1 : 0;
@@ -335,8 +346,6 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     CU(h->records.ensure(sizeof(double) * (size_t)B * H * RL.size));
     p.records = h->records.as<double>();
   }
-  p.betaT = h->betaT.as<double>();
-  const bool use_uniform = h->uniform && h->path_mode == 0;
   if (use_uniform) {
     // uniform-kernel fast path: one exp per (i, j) for all output pairs; reverse-mode second sweep for the gradient
     const UniRecLayout UR = uni_rec_layout(E);
@@ -348,16 +357,34 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     }
     const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na);
     const size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na);
-    if (smf > h->smem_optin || smb > h->smem_optin)
+    if (smf > h->smem_optin || (want_grad && smb > h->smem_optin))
       return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
+    // several small CTAs per SM so that one CTA's serial small-matrix phases overlap another's N^2 sweep
+    auto plan = [&](size_t sm, int* thr, int* grd, const char* env_thr, const char* env_ctas) {
+      const size_t per_sm = 227 * 1024;
+      int fit = (int)(per_sm / (sm + 1024));
+      if (fit < 1) fit = 1;
+      int ctas = fit > 4 ? 4 : fit;
+      *thr = ctas >= 4 ? 128 : 256;
+      if (const char* e = getenv(env_thr)) { int v = atoi(e); if (v == 128 || v == 256) *thr = v; }   // tuning aid
+      if (const char* e = getenv(env_ctas)) { int v = atoi(e); if (v >= 1 && v <= fit) ctas = v; }
+      if (ctas * (*thr) > 512) ctas = 512 / (*thr);
+      int g = h->num_sms * ctas;
+      *grd = B < g ? B : g;
+    };
+    int thr_f, grid_f, thr_b, grid_b;
+    plan(smf, &thr_f, &grid_f, "GPMPC_UNI_FWD_THREADS", "GPMPC_UNI_FWD_CTAS");
+    plan(smb, &thr_b, &grid_b, "GPMPC_UNI_BWD_THREADS", "GPMPC_UNI_BWD_CTAS");
+    if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg = v; }
+    if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg_bwd = v; }
     if (h->timing) CU(cudaEventRecord(h->ev[0], st));
-    CU(launch_uniform(E, false, p, nullptr, grid, smf, st));
+    CU(launch_uniform(E, false, p, nullptr, grid_f, thr_f, smf, st));
     h->launches += 1;
     if (h->timing) { CU(cudaEventRecord(h->ev[1], st)); h->ev_fwd = true; }
     h->ev_bwd = false;
     if (want_grad) {
       if (h->timing) CU(cudaEventRecord(h->ev[2], st));
-      CU(launch_uniform(E, true, p, grad, grid, smb, st));
+      CU(launch_uniform(E, true, p, grad, grid_b, thr_b, smb, st));
       h->launches += 1;
       if (h->timing) { CU(cudaEventRecord(h->ev[3], st)); h->ev_bwd = true; }
     }

@@ -3,5 +3,5 @@
 namespace gpmpc {
 template cudaError_t launch_rollout_inst<4>(bool, const RolloutParams&, int, size_t, cudaStream_t);
 template cudaError_t launch_backward_inst<4>(const BackwardParams&, cudaStream_t);
-template cudaError_t launch_uniform_inst<4>(bool, const RolloutParams&, double*, int, size_t, cudaStream_t);
+template cudaError_t launch_uniform_inst<4>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t);
 }  // namespace gpmpc

@@ -37,6 +37,7 @@ struct RolloutParams {
   // ---- launch geometry
   int group;           // pairs per N^2 phase
   int seg;             // columns per work item
+  int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
 };
 
 struct BackwardParams {
@@ -55,12 +56,13 @@ int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, i
 cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
 size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na);
-cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
                            double* iK, double* beta, double* betaT, int* info, cudaStream_t st, long long* launches);
 cudaError_t launch_il2(const double* ls, double* il2, int n, cudaStream_t st);
 
 constexpr int ROLLOUT_THREADS = 512;
+constexpr int UNIFORM_MAX_THREADS = 256;   // uniform kernels: __launch_bounds__(256, 2) -> <= 128 registers
 
 }  // namespace gpmpc

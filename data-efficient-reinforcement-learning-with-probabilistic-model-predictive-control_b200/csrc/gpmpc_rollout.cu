@@ -20,13 +20,13 @@ int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, i
 }
 
 
-template <int EV> cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, size_t smem, cudaStream_t st);
+template <int EV> cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
 template <int EV> cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st);
 template <int E> cudaError_t launch_backward_inst(const BackwardParams& p, cudaStream_t st);
 #define GPMPC_DECL(n)                                                                                             \
   extern template cudaError_t launch_rollout_inst<n>(bool, const RolloutParams&, int, size_t, cudaStream_t);      \
   extern template cudaError_t launch_backward_inst<n>(const BackwardParams&, cudaStream_t);                       \
-  extern template cudaError_t launch_uniform_inst<n>(bool, const RolloutParams&, double*, int, size_t, cudaStream_t);
+  extern template cudaError_t launch_uniform_inst<n>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t);
 GPMPC_DECL(1) GPMPC_DECL(2) GPMPC_DECL(3) GPMPC_DECL(4) GPMPC_DECL(5) GPMPC_DECL(6) GPMPC_DECL(7) GPMPC_DECL(8)
 #undef GPMPC_DECL
 
@@ -44,16 +44,16 @@ cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, 
   }
 }
 
-cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st) {
   switch (EV) {
-    case 1: return launch_uniform_inst<1>(bwd, p, grad, grid, smem, st);
-    case 2: return launch_uniform_inst<2>(bwd, p, grad, grid, smem, st);
-    case 3: return launch_uniform_inst<3>(bwd, p, grad, grid, smem, st);
-    case 4: return launch_uniform_inst<4>(bwd, p, grad, grid, smem, st);
-    case 5: return launch_uniform_inst<5>(bwd, p, grad, grid, smem, st);
-    case 6: return launch_uniform_inst<6>(bwd, p, grad, grid, smem, st);
-    case 7: return launch_uniform_inst<7>(bwd, p, grad, grid, smem, st);
-    case 8: return launch_uniform_inst<8>(bwd, p, grad, grid, smem, st);
+    case 1: return launch_uniform_inst<1>(bwd, p, grad, grid, threads, smem, st);
+    case 2: return launch_uniform_inst<2>(bwd, p, grad, grid, threads, smem, st);
+    case 3: return launch_uniform_inst<3>(bwd, p, grad, grid, threads, smem, st);
+    case 4: return launch_uniform_inst<4>(bwd, p, grad, grid, threads, smem, st);
+    case 5: return launch_uniform_inst<5>(bwd, p, grad, grid, threads, smem, st);
+    case 6: return launch_uniform_inst<6>(bwd, p, grad, grid, threads, smem, st);
+    case 7: return launch_uniform_inst<7>(bwd, p, grad, grid, threads, smem, st);
+    case 8: return launch_uniform_inst<8>(bwd, p, grad, grid, threads, smem, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -22,11 +22,12 @@ HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G
   L.grp = o;
   const int per_pair = grad ? (3 + EV) : 1;
   int grp = G * NP * per_pair;
-  if (grp < E * NP) grp = E * NP;  // the lb[E][NP] array of phases P1/P2 aliases the group arrays
-  L.kap = L.grp; L.gam = L.kap + G * NP; L.rho = L.gam + G * NP; L.xi = L.rho + G * NP;
-  o += grp;
   L.nOut = 1 + D + (grad ? (EV * D + EV * L.PV) : 0);
-  L.out = o; o += E * L.nOut;
+  // the lb[E][NP] array of phases P1/P2 and the moment outputs of P2/P2b alias the group arrays of P3
+  if (grp < E * NP + E * L.nOut) grp = E * NP + E * L.nOut;
+  L.kap = L.grp; L.gam = L.kap + G * NP; L.rho = L.gam + G * NP; L.xi = L.rho + G * NP;
+  L.out = L.grp + E * NP;
+  o += grp;
   L.m = o; o += GPMPC_MAX_D;
   L.s = o; o += EV * EV;
   L.mu = o; o += GPMPC_MAX_EV;

@@ -90,7 +90,7 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 // uniform forward kernel (value + small per-step record when p.records != NULL)
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) uniform_fwd_kernel(const RolloutParams p) {
+__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(const RolloutParams p) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -406,7 +406,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
+__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -596,15 +596,15 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) uniform_bwd_kernel(const R
       // ---- B2: adjoint-weighted N^2 sweep (upper triangle)
       {
         const double wbar = s_scal[3];
-        const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg, nitems = nrb * nseg;
+        const int nrb = NP / 64, nseg = (NP + p.seg_bwd - 1) / p.seg_bwd, nitems = nrb * nseg;
         for (;;) {
           int item = 0;
           if (lane == 0) item = atomicAdd(&s_int[0], 1);
           item = __shfl_sync(0xffffffffu, item, 0);
           if (item >= nitems) break;
           const int I = item / nseg, js = item - I * nseg;
-          int jbeg = js * p.seg;
-          const int jend = min(NP, jbeg + p.seg);
+          int jbeg = js * p.seg_bwd;
+          const int jend = min(NP, jbeg + p.seg_bwd);
           if (jend <= 64 * I) continue;
           jbeg = max(jbeg, 64 * I);
           uni_bwd_item<EV>(p, s_nu, s_kap, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam, s_rho, s_xi, s_tab);
@@ -768,16 +768,17 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) uniform_bwd_kernel(const R
 }
 
 template <int EV>
-cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem,
+                                cudaStream_t st) {
   cudaError_t e;
   if (bwd) {
     e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uniform_bwd_kernel<EV><<<grid, ROLLOUT_THREADS, smem, st>>>(p, grad);
+    uniform_bwd_kernel<EV><<<grid, threads, smem, st>>>(p, grad);
   } else {
     e = cudaFuncSetAttribute(uniform_fwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uniform_fwd_kernel<EV><<<grid, ROLLOUT_THREADS, smem, st>>>(p);
+    uniform_fwd_kernel<EV><<<grid, threads, smem, st>>>(p);
   }
   return cudaGetLastError();
 }
