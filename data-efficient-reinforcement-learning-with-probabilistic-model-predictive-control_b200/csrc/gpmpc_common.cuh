@@ -52,7 +52,7 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   const double INV = 4.61662413084468283841e+01;   // 32 / ln2
   const double SHIFT = 6755399441055744.0;
   double kd = __fma_rn(x, INV, SHIFT);
-  const int n = __double2loint(kd);
+  int n = __double2loint(kd);
   kd -= SHIFT;
   double r = __fma_rn(kd, -2.16608493792591616511e-02, x);   // ln2/32 hi (30 bits)
   r = __fma_rn(kd, -1.32391292681540124659e-11, r);          // ln2/32 lo
@@ -63,12 +63,11 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   p = __fma_rn(p, r, 0.5);
   p = __fma_rn(p, r, 1.0);
   p *= r;
+  n = max(n, -32704);                              // k >= -1022: deep underflow collapses to ~2e-308 (one IMNMX)
   const double t = tab[n & 31];
-  double res = __fma_rn(t, p, t);
-  const int k = n >> 5;
-  const int hi = __double2hiint(res) + (k << 20);
-  res = __hiloint2double(hi, __double2loint(res));
-  return (k < -1021) ? 0.0 : res;
+  const double res = __fma_rn(t, p, t);
+  const int hi = __double2hiint(res) + (int)(((unsigned)n & 0xFFFFFFE0u) << 15);   // += k << 20
+  return __hiloint2double(hi, __double2loint(res));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -81,31 +80,41 @@ HD void spd_inv_det(const double* a, double* inv, double& det) {
   double L[n * n];
   double Li[n * n];
   det = 1.0;
+#pragma unroll
   for (int j = 0; j < n; j++) {
     double d = a[j * n + j];
-    for (int k = 0; k < j; k++) d -= L[j * n + k] * L[j * n + k];
+  #pragma unroll
+  for (int k = 0; k < j; k++) d -= L[j * n + k] * L[j * n + k];
     det *= d;
     d = sqrt(d);
     L[j * n + j] = d;
     double id = 1.0 / d;
-    for (int i = j + 1; i < n; i++) {
+  #pragma unroll
+  for (int i = j + 1; i < n; i++) {
       double v = a[i * n + j];
-      for (int k = 0; k < j; k++) v -= L[i * n + k] * L[j * n + k];
+    #pragma unroll
+  for (int k = 0; k < j; k++) v -= L[i * n + k] * L[j * n + k];
       L[i * n + j] = v * id;
     }
   }
+#pragma unroll
   for (int j = 0; j < n; j++) {
     Li[j * n + j] = 1.0 / L[j * n + j];
-    for (int i = j + 1; i < n; i++) {
+  #pragma unroll
+  for (int i = j + 1; i < n; i++) {
       double v = 0.0;
-      for (int k = j; k < i; k++) v -= L[i * n + k] * Li[k * n + j];
+    #pragma unroll
+  for (int k = j; k < i; k++) v -= L[i * n + k] * Li[k * n + j];
       Li[i * n + j] = v / L[i * n + i];
     }
   }
+#pragma unroll
   for (int i = 0; i < n; i++)
-    for (int j = 0; j <= i; j++) {
+  #pragma unroll
+  for (int j = 0; j <= i; j++) {
       double v = 0.0;
-      for (int k = i; k < n; k++) v += Li[k * n + i] * Li[k * n + j];
+    #pragma unroll
+  for (int k = i; k < n; k++) v += Li[k * n + i] * Li[k * n + j];
       inv[i * n + j] = v;
       inv[j * n + i] = v;
     }
@@ -117,16 +126,24 @@ HD void spd_inv_det(const double* a, double* inv, double& det) {
 template <int n>
 HD void pair_matrices(const double* s, const double* Wd, double* Rinv, double* Q, double& detR) {
   double st[n * n], Ti[n * n], sq[n];
+#pragma unroll
   for (int e = 0; e < n; e++) sq[e] = sqrt(Wd[e]);
+#pragma unroll
   for (int e = 0; e < n; e++)
-    for (int f = 0; f < n; f++) st[e * n + f] = sq[e] * s[e * n + f] * sq[f] + (e == f ? 1.0 : 0.0);
+  #pragma unroll
+  for (int f = 0; f < n; f++) st[e * n + f] = sq[e] * s[e * n + f] * sq[f] + (e == f ? 1.0 : 0.0);
   spd_inv_det<n>(st, Ti, detR);
+#pragma unroll
   for (int e = 0; e < n; e++)
-    for (int f = 0; f < n; f++) Rinv[e * n + f] = Ti[e * n + f] * sq[f] / sq[e];
+  #pragma unroll
+  for (int f = 0; f < n; f++) Rinv[e * n + f] = Ti[e * n + f] * sq[f] / sq[e];
+#pragma unroll
   for (int e = 0; e < n; e++)
-    for (int f = 0; f < n; f++) {
+  #pragma unroll
+  for (int f = 0; f < n; f++) {
       double v = 0.0;
-      for (int k = 0; k < n; k++) v += Rinv[e * n + k] * s[k * n + f];
+    #pragma unroll
+  for (int k = 0; k < n; k++) v += Rinv[e * n + k] * s[k * n + f];
       Q[e * n + f] = 0.5 * v;
     }
 }

@@ -24,42 +24,55 @@ namespace gpmpc {
 //   r_b,i += Eh_ij beta_b,j  (E FMAs),  tr += Eh_ij iK_ij  (1 FMA)   [gp_model.py:169-175 for all (a,b) at once]
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_nu,
-                                             const double* __restrict__ s_kap, const double* __restrict__ Qm,
-                                             const double* __restrict__ il2, int I, int jbeg, int jend, int lane,
-                                             double* s_acc, const double* __restrict__ s_tab) {
-  constexpr int E = EV;
-  const int NP = p.NP, DP = p.DP;
-  const int i0 = 64 * I + lane, i1 = i0 + 32;
-  double u0[EV], u1[EV];
-  {
-    double z0[EV], z1[EV];
+__device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, int j, double (&nu)[EV], double& kap,
+                                             double (&beta)[EV]) {
+  constexpr int RLEN = (EV + 1 + EV + 1) & ~1;
+  const double2* r2 = reinterpret_cast<const double2*>(s_rec) + (size_t)j * (RLEN / 2);
+  double buf[RLEN];
 #pragma unroll
-    for (int e = 0; e < EV; e++) { z0[e] = s_nu[i0 * DP + e] * il2[e]; z1[e] = s_nu[i1 * DP + e] * il2[e]; }
+  for (int q = 0; q < RLEN / 2; q++) { const double2 v = r2[q]; buf[2 * q] = v.x; buf[2 * q + 1] = v.y; }
+#pragma unroll
+  for (int e = 0; e < EV; e++) nu[e] = buf[e];
+  kap = buf[EV];
+#pragma unroll
+  for (int b = 0; b < EV; b++) beta[b] = buf[EV + 1 + b];
+}
+
+template <int EV>
+__device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec,
+                                             const double* __restrict__ Qm, const double* __restrict__ il2, int I,
+                                             int jbeg, int jend, int lane, double* s_acc,
+                                             const double* __restrict__ s_tab) {
+  constexpr int E = EV;
+  const int NP = p.NP;
+  const int i0 = 64 * I + lane, i1 = i0 + 32;
+  double u0[EV], u1[EV], bi0[E], bi1[E], kr0, kr1;
+  {
+    double n0[EV], n1[EV];
+    uni_load_rec<EV>(s_rec, i0, n0, kr0, bi0);
+    uni_load_rec<EV>(s_rec, i1, n1, kr1, bi1);
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-      for (int f = 0; f < EV; f++) { q0 = fma(Qm[e * EV + f], z0[f], q0); q1 = fma(Qm[e * EV + f], z1[f], q1); }
+      for (int f = 0; f < EV; f++) {
+        q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
+        q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
+      }
       u0[e] = 2.0 * q0 * il2[e];
       u1[e] = 2.0 * q1 * il2[e];
     }
   }
-  const double kr0 = s_kap[i0], kr1 = s_kap[i1];
   double r0[E], r1[E], tr = 0.0;
 #pragma unroll
   for (int b = 0; b < E; b++) { r0[b] = 0.0; r1[b] = 0.0; }
-  const double* __restrict__ betaT = p.betaT;   // [j][E]
-  const double* __restrict__ iK = p.iK;
+  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
 #pragma unroll 4
   for (int j = jbeg; j < jend; j++) {
-    double nj[EV], bj[E];
-#pragma unroll
-    for (int e = 0; e < EV; e++) nj[e] = s_nu[j * DP + e];
-#pragma unroll
-    for (int b = 0; b < E; b++) bj[b] = __ldg(betaT + (size_t)j * E + b);
-    const double kj = s_kap[j];
-    const double k0 = __ldg(iK + (size_t)j * NP + i0), k1 = __ldg(iK + (size_t)j * NP + i1);
+    double nj[EV], bj[E], kj;
+    uni_load_rec<EV>(s_rec, j, nj, kj, bj);
+    const double k0 = __ldg(ik0), k1 = __ldg(ik0 + 32);
+    ik0 += NP;
     double t0 = kr0 + kj, t1 = kr1 + kj;
 #pragma unroll
     for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
@@ -70,9 +83,6 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
     tr = fma(e1, k1, tr);
   }
   // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace
-  double bi0[E], bi1[E];
-#pragma unroll
-  for (int b = 0; b < E; b++) { bi0[b] = __ldg(betaT + (size_t)i0 * E + b); bi1[b] = __ldg(betaT + (size_t)i1 * E + b); }
   int pr = 0;
 #pragma unroll
   for (int a = 0; a < E; a++)
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
   constexpr int P = E * (E + 1) / 2;
   const UniLayout L = make_uni_layout(EV, false, NP, DP, D, H, Na);
-  double* s_nu = sm + L.nu; double* s_kap = sm + L.kap; double* s_lb = sm + L.lb; double* s_out = sm + L.out;
+  double* s_rec = sm + L.rec; double* s_out = sm + L.out;
   double* s_m = sm + L.m; double* s_s = sm + L.s; double* s_mu = sm + L.mu; double* s_A = sm + L.A;
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
@@ -171,6 +181,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
         s_misc[1] = detR;
       }
       if (tid < P + 1) s_acc[tid] = 0.0;
+      if (tid < E * nOut) s_out[tid] = 0.0;
       if (tid == 0) s_int[0] = 0;
       __syncthreads();
       if (tid == 100) {
@@ -179,19 +190,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
         for (int e = 0; e < EV * EV; e++) chk += s_s[e];
         s_int[1] = isfinite(chk) ? 0 : 1;
       }
-      // ---- P1: nu, shared exponent terms, kap
+      // ---- P1: nu, shared exponent terms, hot-loop record; mean-part sums h_a, g_a reduced on the fly
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
-        for (int d = 0; d < GPMPC_MAX_D; d++) {
-          if (d < DP) {
-            double v = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
-            nu[d] = v;
-            s_nu[i * DP + d] = v;
-          } else {
-            nu[d] = 0.0;
-          }
-        }
+        for (int d = 0; d < GPMPC_MAX_D; d++) nu[d] = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
         double quad = 0.0, head = 0.0, tail = 0.0, zqz = 0.0;
 #pragma unroll
         for (int e = 0; e < EV; e++) {
@@ -209,24 +212,26 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
         for (int d = EV; d < GPMPC_MAX_D; d++)
           if (d < D) tail = fma(nu[d] * nu[d], il2[d], tail);
         const double ei = (i < N) ? exp_tab(-0.5 * (quad + tail), s_tab) : 0.0;
+        double* rec = s_rec + (size_t)i * L.rlen;
 #pragma unroll
-        for (int a = 0; a < E; a++) s_lb[a * NP + i] = ei * __ldg(p.betaT + (size_t)i * E + a);
-        s_kap[i] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;   // log s2 factored out (s2^2 applied at the end)
+        for (int e = 0; e < EV; e++) rec[e] = nu[e];
+        rec[EV] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;   // log s2 factored out (s2^2 applied at the end)
+#pragma unroll
+        for (int a = 0; a < E; a++) {
+          const double be = __ldg(p.betaT + (size_t)i * E + a);
+          rec[EV + 1 + a] = be;
+          const double lb = ei * be;
+          double v = warp_sum(lb);
+          if (lane == 0) atomicAdd(s_out + a * nOut, v);
+#pragma unroll
+          for (int d = 0; d < GPMPC_MAX_D; d++)
+            if (d < D) {
+              v = warp_sum(lb * nu[d]);
+              if (lane == 0) atomicAdd(s_out + a * nOut + 1 + d, v);
+            }
+        }
       }
       __syncthreads();
-      // ---- P2: h_a, g_a
-      for (int o = tid; o < E * nOut; o += NT) {
-        const int a = o / nOut, q = o - a * nOut;
-        const double* lb = s_lb + a * NP;
-        double acc = 0.0;
-        if (q == 0) {
-          for (int i = 0; i < N; i++) acc += lb[i];
-        } else {
-          const int d1 = q - 1;
-          for (int i = 0; i < N; i++) acc = fma(lb[i], s_nu[i * DP + d1], acc);
-        }
-        s_out[o] = acc;
-      }
       // ---- P3: one N x N sweep for all pairs
       {
         const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg, nitems = nrb * nseg;
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
           if (item >= nitems) break;
           const int I = item / nseg, js = item - I * nseg;
           const int jbeg = js * p.seg, jend = min(NP, jbeg + p.seg);
-          uni_fwd_item<EV>(p, s_nu, s_kap, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab);
+          uni_fwd_item<EV>(p, s_rec, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab);
         }
       }
       __syncthreads();
@@ -322,30 +327,30 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
 //   W_ij = p_i . beta_j - wbar iK_ij ,  w_ij = W_ij Eh_ij ; rows: rho_i, xi_i ; columns: gam_j
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_nu,
-                                             const double* __restrict__ s_kap, const double* __restrict__ Qm,
-                                             const double* __restrict__ il2, const double* __restrict__ Om,
-                                             double wbar, int I, int jbeg, int jend, int lane, double* s_gam,
-                                             double* s_rho, double* s_xi, const double* __restrict__ s_tab) {
+__device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec,
+                                             const double* __restrict__ Qm, const double* __restrict__ il2,
+                                             const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
+                                             int lane, double* s_gam, double* s_rho, double* s_xi,
+                                             const double* __restrict__ s_tab) {
   constexpr int E = EV;
-  const int NP = p.NP, DP = p.DP;
+  const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
-  double u0[EV], u1[EV], p0[E], p1[E];
+  double u0[EV], u1[EV], p0[E], p1[E], kr0, kr1;
   {
-    double z0[EV], z1[EV];
-#pragma unroll
-    for (int e = 0; e < EV; e++) { z0[e] = s_nu[i0 * DP + e] * il2[e]; z1[e] = s_nu[i1 * DP + e] * il2[e]; }
+    double n0[EV], n1[EV], b0[E], b1[E];
+    uni_load_rec<EV>(s_rec, i0, n0, kr0, b0);
+    uni_load_rec<EV>(s_rec, i1, n1, kr1, b1);
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-      for (int f = 0; f < EV; f++) { q0 = fma(Qm[e * EV + f], z0[f], q0); q1 = fma(Qm[e * EV + f], z1[f], q1); }
+      for (int f = 0; f < EV; f++) {
+        q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
+        q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
+      }
       u0[e] = 2.0 * q0 * il2[e];
       u1[e] = 2.0 * q1 * il2[e];
     }
-    double b0[E], b1[E];
-#pragma unroll
-    for (int b = 0; b < E; b++) { b0[b] = __ldg(p.betaT + (size_t)i0 * E + b); b1[b] = __ldg(p.betaT + (size_t)i1 * E + b); }
 #pragma unroll
     for (int a = 0; a < E; a++) {
       double v0 = 0.0, v1 = 0.0;
@@ -355,29 +360,22 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
       p1[a] = v1;
     }
   }
-  const double kr0 = s_kap[i0], kr1 = s_kap[i1];
   double rho0 = 0.0, rho1 = 0.0, xi0[EV], xi1[EV];
 #pragma unroll
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
-  const double* __restrict__ betaT = p.betaT;
-  const double* __restrict__ iK = p.iK;
+  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;
   for (int j0 = jbeg; j0 < jend; j0 += 8) {
     const bool masked = (j0 < 64 * I + 64);
     double v[8];
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
       const int j = j0 + jj;
-      double nj[EV];
+      double nj[EV], bj[E], kj;
+      uni_load_rec<EV>(s_rec, j, nj, kj, bj);
+      double c0 = -wbar * __ldg(ik0), c1 = -wbar * __ldg(ik0 + 32);
+      ik0 += NP;
 #pragma unroll
-      for (int e = 0; e < EV; e++) nj[e] = s_nu[j * DP + e];
-      double c0 = -wbar * __ldg(iK + (size_t)j * NP + i0), c1 = -wbar * __ldg(iK + (size_t)j * NP + i1);
-#pragma unroll
-      for (int b = 0; b < E; b++) {
-        const double bj = __ldg(betaT + (size_t)j * E + b);
-        c0 = fma(p0[b], bj, c0);
-        c1 = fma(p1[b], bj, c1);
-      }
-      const double kj = s_kap[j];
+      for (int b = 0; b < E; b++) { c0 = fma(p0[b], bj[b], c0); c1 = fma(p1[b], bj[b], c1); }
       double t0 = kr0 + kj, t1 = kr1 + kj;
 #pragma unroll
       for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
@@ -412,7 +410,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H, Dc = E + Na;
   const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na);
-  double* s_nu = sm + L.nu; double* s_kap = sm + L.kap; double* s_lb = sm + L.lb;
+  double* s_nu = sm + L.nu; double* s_rec = sm + L.rec;
   double* s_rho = sm + L.rho; double* s_gam = sm + L.gam; double* s_xi = sm + L.xi;
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
@@ -565,7 +563,12 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
           if (d < D) { tail = fma(nu[d] * nu[d], il2[d], tail); an[d] = nu[d] * il2[d]; }
         }
         const double ei = (i < N) ? exp_tab(-0.5 * (quad + tail), s_tab) : 0.0;
-        s_kap[i] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;
+        double* rcd = s_rec + (size_t)i * L.rlen;
+#pragma unroll
+        for (int e = 0; e < EV; e++) rcd[e] = nu[e];
+        rcd[EV] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;
+#pragma unroll
+        for (int a = 0; a < E; a++) rcd[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
         // N pass of the mean part: phi_i = sum_a lb_a,i (h_bar_a + g_bar_a . nu_i^E)
         double phi = 0.0;
 #pragma unroll
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
           const int jend = min(NP, jbeg + p.seg_bwd);
           if (jend <= 64 * I) continue;
           jbeg = max(jbeg, 64 * I);
-          uni_bwd_item<EV>(p, s_nu, s_kap, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam, s_rho, s_xi, s_tab);
+          uni_bwd_item<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam, s_rho, s_xi, s_tab);
         }
       }
       __syncthreads();

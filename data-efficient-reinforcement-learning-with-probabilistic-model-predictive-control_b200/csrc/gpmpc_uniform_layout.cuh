@@ -6,7 +6,7 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int nu, kap, lb, rho, gam, xi, out, nOut;
+  int nu, rec, rlen, rho, gam, xi, out, nOut;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
@@ -15,9 +15,11 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   UniLayout L;
   const int E = EV, P = E * (E + 1) / 2;
   int o = 0;
-  L.nu = o; o += NP * DP;
-  L.kap = o; o += NP;
-  L.lb = o; if (!bwd) o += E * NP; // lb[a][i]: forward P1/P2 only (the reverse sweep recomputes it inline)
+  // hot-loop record per training point j: { nu_j[0..EV), kap_j, beta_j[0..E) } padded to an even length so that
+  // every lane fetches it with (rlen/2) broadcast LDS.128
+  L.rlen = (EV + 1 + E + 1) & ~1;
+  L.rec = o; o += NP * L.rlen;
+  L.nu = o; if (bwd) o += NP * DP;   // full-D nu: only the reverse sweep's reductions need the action/time dims
   L.rho = o; L.gam = o; L.xi = o;
   if (bwd) { L.rho = o; o += NP; L.gam = o; o += NP; L.xi = o; o += NP * EV; }
   L.nOut = 1 + D;

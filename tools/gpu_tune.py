@@ -1,5 +1,4 @@
 """Tuning sweep for the uniform-kernel launch plan (threads / CTAs per SM / item segment sizes)."""
-import itertools
 import os
 import subprocess
 import sys
@@ -18,15 +17,13 @@ for g in (False, True):
     print("grad=%d fwd %.2f bwd %.2f ms -> %.0f preds/s" % (g, f, b, cfg["B"] * cfg["H"] / (f + b) * 1e3), end=" | ")
 print()
 '''
-grid = []
-for ft, fc in ((128, 4), (256, 2), (128, 3), (128, 2)):
-    for seg in (64, 128, 256):
-        grid.append({"GPMPC_UNI_FWD_THREADS": ft, "GPMPC_UNI_FWD_CTAS": fc, "GPMPC_UNI_SEG": seg})
-for bt, bc in ((256, 2), (128, 3), (128, 2), (256, 1)):
-    for seg in (32, 64, 128):
-        grid.append({"GPMPC_UNI_BWD_THREADS": bt, "GPMPC_UNI_BWD_CTAS": bc, "GPMPC_UNI_SEG_BWD": seg})
+grid = [{}]
+for ft, fc in ((128, 4), (256, 2), (128, 3)):
+    grid.append({"GPMPC_UNI_FWD_THREADS": ft, "GPMPC_UNI_FWD_CTAS": fc, "GPMPC_UNI_SEG": 256})
+for bt, bc in ((256, 2), (128, 2), (128, 3), (256, 1)):
+    grid.append({"GPMPC_UNI_BWD_THREADS": bt, "GPMPC_UNI_BWD_CTAS": bc, "GPMPC_UNI_SEG_BWD": 64})
 for cfg in grid:
     env = dict(os.environ)
     env.update({k: str(v) for k, v in cfg.items()})
     out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
-    print(cfg, "->", out.stdout.strip()[-200:], out.stderr.strip()[-200:] if out.returncode else "", flush=True)
+    print(cfg, "->", out.stdout.strip()[-200:], out.stderr.strip()[-300:] if out.returncode else "", flush=True)
