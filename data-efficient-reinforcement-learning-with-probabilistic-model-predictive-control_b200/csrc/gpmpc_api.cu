@@ -368,6 +368,7 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       *thr = ctas >= 4 ? 128 : 256;
       if (const char* e = getenv(env_thr)) { int v = atoi(e); if (v == 128 || v == 256) *thr = v; }   // tuning aid
       if (const char* e = getenv(env_ctas)) { int v = atoi(e); if (v >= 1 && v <= fit) ctas = v; }
+      if (E > 5) { *thr = 256; ctas = 1; }   // large state dims: 255-register kernels, one CTA per SM
       if (ctas * (*thr) > 512) ctas = 512 / (*thr);
       int g = h->num_sms * ctas;
       *grd = B < g ? B : g;

@@ -24,10 +24,10 @@ namespace gpmpc {
 //   r_b,i += Eh_ij beta_b,j  (E FMAs),  tr += Eh_ij iK_ij  (1 FMA)   [gp_model.py:169-175 for all (a,b) at once]
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, int j, double (&nu)[EV], double& kap,
-                                             double (&beta)[EV]) {
-  constexpr int RLEN = (EV + 1 + EV + 1) & ~1;
-  const double2* r2 = reinterpret_cast<const double2*>(s_rec) + (size_t)j * (RLEN / 2);
+__device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, int rlen, int j, double (&nu)[EV],
+                                             double& kap, double (&beta)[EV]) {
+  constexpr int RLEN = (EV + 1 + EV + 1) & ~1;   // hot part; rlen >= RLEN is the record stride (even)
+  const double2* r2 = reinterpret_cast<const double2*>(s_rec + (size_t)j * rlen);
   double buf[RLEN];
 #pragma unroll
   for (int q = 0; q < RLEN / 2; q++) { const double2 v = r2[q]; buf[2 * q] = v.x; buf[2 * q + 1] = v.y; }
@@ -39,7 +39,7 @@ __device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, i
 }
 
 template <int EV>
-__device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec,
+__device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
                                              const double* __restrict__ Qm, const double* __restrict__ il2, int I,
                                              int jbeg, int jend, int lane, double* s_acc,
                                              const double* __restrict__ s_tab) {
@@ -49,8 +49,8 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   double u0[EV], u1[EV], bi0[E], bi1[E], kr0, kr1;
   {
     double n0[EV], n1[EV];
-    uni_load_rec<EV>(s_rec, i0, n0, kr0, bi0);
-    uni_load_rec<EV>(s_rec, i1, n1, kr1, bi1);
+    uni_load_rec<EV>(s_rec, rlen, i0, n0, kr0, bi0);
+    uni_load_rec<EV>(s_rec, rlen, i1, n1, kr1, bi1);
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       double q0 = 0.0, q1 = 0.0;
@@ -70,7 +70,7 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 #pragma unroll 4
   for (int j = jbeg; j < jend; j++) {
     double nj[EV], bj[E], kj;
-    uni_load_rec<EV>(s_rec, j, nj, kj, bj);
+    uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
     const double k0 = __ldg(ik0), k1 = __ldg(ik0 + 32);
     ik0 += NP;
     double t0 = kr0 + kj, t1 = kr1 + kj;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 // uniform forward kernel (value + small per-step record when p.records != NULL)
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(const RolloutParams p) {
+__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) uniform_fwd_kernel(const RolloutParams p) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
           if (item >= nitems) break;
           const int I = item / nseg, js = item - I * nseg;
           const int jbeg = js * p.seg, jend = min(NP, jbeg + p.seg);
-          uni_fwd_item<EV>(p, s_rec, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab);
+          uni_fwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab);
         }
       }
       __syncthreads();
@@ -327,10 +327,10 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_fwd_kernel(con
 //   W_ij = p_i . beta_j - wbar iK_ij ,  w_ij = W_ij Eh_ij ; rows: rho_i, xi_i ; columns: gam_j
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec,
-                                             const double* __restrict__ Qm, const double* __restrict__ il2,
+__device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
+                                             int rhot, const double* __restrict__ Qm, const double* __restrict__ il2,
                                              const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
-                                             int lane, double* s_gam, double* s_rho, double* s_xi,
+                                             int lane, double* s_gam, double* s_accGm, double* s_accGQ,
                                              const double* __restrict__ s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
@@ -338,8 +338,8 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   double u0[EV], u1[EV], p0[E], p1[E], kr0, kr1;
   {
     double n0[EV], n1[EV], b0[E], b1[E];
-    uni_load_rec<EV>(s_rec, i0, n0, kr0, b0);
-    uni_load_rec<EV>(s_rec, i1, n1, kr1, b1);
+    uni_load_rec<EV>(s_rec, rlen, i0, n0, kr0, b0);
+    uni_load_rec<EV>(s_rec, rlen, i1, n1, kr1, b1);
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       double q0 = 0.0, q1 = 0.0;
@@ -371,7 +371,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
     for (int jj = 0; jj < 8; jj++) {
       const int j = j0 + jj;
       double nj[EV], bj[E], kj;
-      uni_load_rec<EV>(s_rec, j, nj, kj, bj);
+      uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
       double c0 = -wbar * __ldg(ik0), c1 = -wbar * __ldg(ik0 + 32);
       ik0 += NP;
 #pragma unroll
@@ -394,24 +394,56 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
     double tot = col_reduce8(v, lane, col);
     if ((lane & 3) == 0) atomicAdd(s_gam + j0 + col, tot);
   }
-  atomicAdd(s_rho + i0, rho0);
-  atomicAdd(s_rho + i1, rho1);
+  // owner lanes turn their row sums (rho_i, xi_i) into contributions to dS/dm (D) and dS/dQ (E x E) right away
+  // (linear in the partial sums, so per-item flushing is exact); no per-row arrays in shared memory
+  const int D = p.D;
+  double gm[GPMPC_MAX_D], gQ[EV * EV];
 #pragma unroll
-  for (int e = 0; e < EV; e++) { atomicAdd(s_xi + i0 * EV + e, xi0[e]); atomicAdd(s_xi + i1 * EV + e, xi1[e]); }
+  for (int e = 0; e < EV * EV; e++) gQ[e] = 0.0;
+  {
+    const double* ra = s_rec + (size_t)i0 * rlen;
+    const double* rb = s_rec + (size_t)i1 * rlen;
+    double za[EV], zb[EV], xa[EV], xb[EV];
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      za[e] = ra[e] * il2[e]; zb[e] = rb[e] * il2[e];
+      xa[e] = xi0[e] * il2[e]; xb[e] = xi1[e] * il2[e];
+      gm[e] = rho0 * za[e] + rho1 * zb[e];
+    }
+#pragma unroll
+    for (int d = EV; d < GPMPC_MAX_D; d++)
+      gm[d] = (d < D) ? (rho0 * ra[rhot + d - EV] + rho1 * rb[rhot + d - EV]) * il2[d] : 0.0;
+#pragma unroll
+    for (int e = 0; e < EV; e++)
+#pragma unroll
+      for (int f = 0; f < EV; f++)
+        gQ[e * EV + f] = rho0 * za[e] * za[f] + za[e] * xa[f] + za[f] * xa[e] +
+                         rho1 * zb[e] * zb[f] + zb[e] * xb[f] + zb[f] * xb[e];
+  }
+#pragma unroll
+  for (int d = 0; d < GPMPC_MAX_D; d++)
+    if (d < D) {
+      const double v = warp_sum(gm[d]);
+      if (lane == 0) atomicAdd(s_accGm + d, v);
+    }
+#pragma unroll
+  for (int e = 0; e < EV * EV; e++) {
+    const double v = warp_sum(gQ[e]);
+    if (lane == 0) atomicAdd(s_accGQ + e, v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
+__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H, Dc = E + Na;
   const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na);
-  double* s_nu = sm + L.nu; double* s_rec = sm + L.rec;
-  double* s_rho = sm + L.rho; double* s_gam = sm + L.gam; double* s_xi = sm + L.xi;
+  double* s_rec = sm + L.rec; double* s_gam = sm + L.gam;
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
   double* s2p = sm + L.small2;
@@ -465,8 +497,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
       // ---- B0: model input, shared matrices, adjoint coefficients (thread 0: O(E^3))
       if (tid < D) s_m[tid] = (tid < E) ? mup[tid] : (tid < E + Na ? am[tid - E] : (double)(p.iter_ctrl + t - 1));
       for (int o = tid; o < L.accN + 1; o += NT) s_acc[o] = 0.0;
-      for (int o = tid; o < NP; o += NT) { s_rho[o] = 0.0; s_gam[o] = 0.0; }
-      for (int o = tid; o < NP * EV; o += NT) s_xi[o] = 0.0;
+      for (int o = tid; o < NP; o += NT) s_gam[o] = 0.0;
       if (tid == 0) {
         s_int[0] = 0;
         double Ca[EV * EV], Ai[EV * EV], det, pl = 1.0, Wd[EV], Rinv[EV * EV], Qm[EV * EV], detR;
@@ -530,19 +561,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
         for (int e = 0; e < EV * EV; e++) s_scal[8 + e] = A_bar[e];   // needs 8 + E2 <= 72 doubles
       }
       __syncthreads();
-      // ---- B1: nu, exponent terms, lb (as in the forward)
+      // ---- B1: nu, exponent terms, hot-loop record (as in the forward) + N pass of the mean part
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
-        for (int d = 0; d < GPMPC_MAX_D; d++) {
-          if (d < DP) {
-            double v = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
-            nu[d] = v;
-            s_nu[i * DP + d] = v;
-          } else {
-            nu[d] = 0.0;
-          }
-        }
+        for (int d = 0; d < GPMPC_MAX_D; d++) nu[d] = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
         double quad = 0.0, head = 0.0, tail = 0.0, zqz = 0.0, an[GPMPC_MAX_D];
 #pragma unroll
         for (int e = 0; e < EV; e++) {
@@ -569,6 +592,9 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
         rcd[EV] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;
 #pragma unroll
         for (int a = 0; a < E; a++) rcd[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
+#pragma unroll
+        for (int d = EV; d < GPMPC_MAX_D; d++)
+          if (d < D) rcd[L.rhot + d - EV] = nu[d];
         // N pass of the mean part: phi_i = sum_a lb_a,i (h_bar_a + g_bar_a . nu_i^E)
         double phi = 0.0;
 #pragma unroll
@@ -610,11 +636,12 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
           const int jend = min(NP, jbeg + p.seg_bwd);
           if (jend <= 64 * I) continue;
           jbeg = max(jbeg, 64 * I);
-          uni_bwd_item<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam, s_rho, s_xi, s_tab);
+          uni_bwd_item<EV>(p, s_rec, L.rlen, L.rhot, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam, s_acc + accGm,
+                           s_acc + accGQ, s_tab);
         }
       }
       __syncthreads();
-      // ---- B3: reduce (rho, gam, xi) -> G_m (D), G_Q (E x E)   [same formulas as a diagonal pair]
+      // ---- B3: column sums gam_j -> their share of G_m (D), G_Q (E x E)   [row sums were folded in per item]
       {
         double gm[GPMPC_MAX_D], gQ[EV * EV];
 #pragma unroll
@@ -622,17 +649,18 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, 2) uniform_bwd_kernel(con
 #pragma unroll
         for (int e = 0; e < EV * EV; e++) gQ[e] = 0.0;
         for (int i = tid; i < N; i += NT) {
-          const double rg = s_rho[i] + s_gam[i];
-          double z[EV], xs[EV];
+          const double g = s_gam[i];
+          const double* rc = s_rec + (size_t)i * L.rlen;
+          double z[EV];
 #pragma unroll
-          for (int d = 0; d < GPMPC_MAX_D; d++)
-            if (d < D) gm[d] = fma(rg * il2[d], s_nu[i * DP + d], gm[d]);
+          for (int e = 0; e < EV; e++) { z[e] = rc[e] * il2[e]; gm[e] = fma(g, z[e], gm[e]); }
 #pragma unroll
-          for (int e = 0; e < EV; e++) { z[e] = s_nu[i * DP + e] * il2[e]; xs[e] = s_xi[(size_t)i * EV + e] * il2[e]; }
+          for (int d = EV; d < GPMPC_MAX_D; d++)
+            if (d < D) gm[d] = fma(g * il2[d], rc[L.rhot + d - EV], gm[d]);
 #pragma unroll
           for (int e = 0; e < EV; e++)
 #pragma unroll
-            for (int f = 0; f < EV; f++) gQ[e * EV + f] += rg * z[e] * z[f] + z[e] * xs[f] + z[f] * xs[e];
+            for (int f = 0; f < EV; f++) gQ[e * EV + f] = fma(g * z[e], z[f], gQ[e * EV + f]);
         }
         for (int d = 0; d < D; d++) {
           double v = warp_sum(gm[d]);

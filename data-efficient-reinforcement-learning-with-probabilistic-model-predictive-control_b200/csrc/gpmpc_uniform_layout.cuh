@@ -6,7 +6,7 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int nu, rec, rlen, rho, gam, xi, out, nOut;
+  int rec, rlen, rhot, gam, out, nOut;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
@@ -17,11 +17,11 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   int o = 0;
   // hot-loop record per training point j: { nu_j[0..EV), kap_j, beta_j[0..E) } padded to an even length so that
   // every lane fetches it with (rlen/2) broadcast LDS.128
-  L.rlen = (EV + 1 + E + 1) & ~1;
+  // (the reverse sweep appends the action/time dims of nu, needed by its dS/dm reductions)
+  L.rhot = (EV + 1 + E + 1) & ~1;
+  L.rlen = L.rhot + (bwd ? ((D - EV + 1) & ~1) : 0);
   L.rec = o; o += NP * L.rlen;
-  L.nu = o; if (bwd) o += NP * DP;   // full-D nu: only the reverse sweep's reductions need the action/time dims
-  L.rho = o; L.gam = o; L.xi = o;
-  if (bwd) { L.rho = o; o += NP; L.gam = o; o += NP; L.xi = o; o += NP * EV; }
+  L.gam = o; if (bwd) o += NP;       // column sums of the triangular sweep
   L.nOut = 1 + D;
   L.out = o; o += E * L.nOut;
   L.m = o; o += GPMPC_MAX_D;
