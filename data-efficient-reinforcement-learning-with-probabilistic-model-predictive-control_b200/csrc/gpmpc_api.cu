@@ -355,8 +355,10 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     } else {
       p.records = nullptr;
     }
-    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na);
-    const size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na);
+    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false);
+    size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true);
+    p.rowarr = smb <= 112 * 1024 ? 1 : 0;      // per-row arrays only while two CTAs still fit on an SM
+    if (!p.rowarr) smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false);
     if (smf > h->smem_optin || (want_grad && smb > h->smem_optin))
       return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
     // several small CTAs per SM so that one CTA's serial small-matrix phases overlap another's N^2 sweep

@@ -326,12 +326,12 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) unifor
 // reverse sweep hot loop: upper-triangle sweep with the adjoint-weighted coefficient
 //   W_ij = p_i . beta_j - wbar iK_ij ,  w_ij = W_ij Eh_ij ; rows: rho_i, xi_i ; columns: gam_j
 // ---------------------------------------------------------------------------------------------
-template <int EV>
+template <int EV, bool ROWARR>
 __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
                                              int rhot, const double* __restrict__ Qm, const double* __restrict__ il2,
                                              const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
                                              int lane, double* s_gam, double* s_accGm, double* s_accGQ,
-                                             const double* __restrict__ s_tab) {
+                                             double* s_rho, double* s_xi, const double* __restrict__ s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
@@ -394,8 +394,15 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
     double tot = col_reduce8(v, lane, col);
     if ((lane & 3) == 0) atomicAdd(s_gam + j0 + col, tot);
   }
-  // owner lanes turn their row sums (rho_i, xi_i) into contributions to dS/dm (D) and dS/dQ (E x E) right away
-  // (linear in the partial sums, so per-item flushing is exact); no per-row arrays in shared memory
+  if (ROWARR) {   // shared memory has room for per-row partial sums: 2 (1 + EV) conflict-free atomics per lane
+    atomicAdd(s_rho + i0, rho0);
+    atomicAdd(s_rho + i1, rho1);
+#pragma unroll
+    for (int e = 0; e < EV; e++) { atomicAdd(s_xi + i0 * EV + e, xi0[e]); atomicAdd(s_xi + i1 * EV + e, xi1[e]); }
+    return;
+  }
+  // otherwise the owner lanes turn their row sums (rho_i, xi_i) into contributions to dS/dm (D) and dS/dQ (E x E)
+  // right away (linear in the partial sums, so per-item flushing is exact); no per-row arrays in shared memory
   const int D = p.D;
   double gm[GPMPC_MAX_D], gQ[EV * EV];
 #pragma unroll
@@ -436,14 +443,14 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
 // ---------------------------------------------------------------------------------------------
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
-template <int EV>
+template <int EV, bool ROWARR>
 __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H, Dc = E + Na;
-  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na);
-  double* s_rec = sm + L.rec; double* s_gam = sm + L.gam;
+  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, ROWARR);
+  double* s_rec = sm + L.rec; double* s_gam = sm + L.gam; double* s_rho = sm + L.rho; double* s_xi = sm + L.xi;
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
   double* s2p = sm + L.small2;
@@ -498,6 +505,10 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) unifor
       if (tid < D) s_m[tid] = (tid < E) ? mup[tid] : (tid < E + Na ? am[tid - E] : (double)(p.iter_ctrl + t - 1));
       for (int o = tid; o < L.accN + 1; o += NT) s_acc[o] = 0.0;
       for (int o = tid; o < NP; o += NT) s_gam[o] = 0.0;
+      if (ROWARR) {
+        for (int o = tid; o < NP; o += NT) s_rho[o] = 0.0;
+        for (int o = tid; o < NP * EV; o += NT) s_xi[o] = 0.0;
+      }
       if (tid == 0) {
         s_int[0] = 0;
         double Ca[EV * EV], Ai[EV * EV], det, pl = 1.0, Wd[EV], Rinv[EV * EV], Qm[EV * EV], detR;
@@ -636,8 +647,8 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) unifor
           const int jend = min(NP, jbeg + p.seg_bwd);
           if (jend <= 64 * I) continue;
           jbeg = max(jbeg, 64 * I);
-          uni_bwd_item<EV>(p, s_rec, L.rlen, L.rhot, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam, s_acc + accGm,
-                           s_acc + accGQ, s_tab);
+          uni_bwd_item<EV, ROWARR>(p, s_rec, L.rlen, L.rhot, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam,
+                                   s_acc + accGm, s_acc + accGQ, s_rho, s_xi, s_tab);
         }
       }
       __syncthreads();
@@ -649,11 +660,19 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) unifor
 #pragma unroll
         for (int e = 0; e < EV * EV; e++) gQ[e] = 0.0;
         for (int i = tid; i < N; i += NT) {
-          const double g = s_gam[i];
+          const double g = s_gam[i] + (ROWARR ? s_rho[i] : 0.0);
           const double* rc = s_rec + (size_t)i * L.rlen;
           double z[EV];
 #pragma unroll
           for (int e = 0; e < EV; e++) { z[e] = rc[e] * il2[e]; gm[e] = fma(g, z[e], gm[e]); }
+          if (ROWARR) {
+#pragma unroll
+            for (int e = 0; e < EV; e++) {
+              const double xe = s_xi[(size_t)i * EV + e] * il2[e];
+#pragma unroll
+              for (int f = 0; f < EV; f++) { gQ[f * EV + e] = fma(z[f], xe, gQ[f * EV + e]); gQ[e * EV + f] = fma(z[f], xe, gQ[e * EV + f]); }
+            }
+          }
 #pragma unroll
           for (int d = EV; d < GPMPC_MAX_D; d++)
             if (d < D) gm[d] = fma(g * il2[d], rc[L.rhot + d - EV], gm[d]);
@@ -802,10 +821,14 @@ template <int EV>
 cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem,
                                 cudaStream_t st) {
   cudaError_t e;
-  if (bwd) {
-    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (bwd && p.rowarr) {
+    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uniform_bwd_kernel<EV><<<grid, threads, smem, st>>>(p, grad);
+    uniform_bwd_kernel<EV, true><<<grid, threads, smem, st>>>(p, grad);
+  } else if (bwd) {
+    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    uniform_bwd_kernel<EV, false><<<grid, threads, smem, st>>>(p, grad);
   } else {
     e = cudaFuncSetAttribute(uniform_fwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -6,12 +6,13 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, rlen, rhot, gam, out, nOut;
+  int rec, rlen, rhot, gam, rho, xi, out, nOut;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
 // bwd=false: forward kernel; bwd=true: reverse-sweep kernel (needs rho/gam/xi arrays)
-HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int Na) {
+// rowarr (reverse sweep only): keep per-row partial sums rho_i, xi_i in shared memory (fast path when it fits)
+HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool rowarr = false) {
   UniLayout L;
   const int E = EV, P = E * (E + 1) / 2;
   int o = 0;
@@ -22,6 +23,8 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.rlen = L.rhot + (bwd ? ((D - EV + 1) & ~1) : 0);
   L.rec = o; o += NP * L.rlen;
   L.gam = o; if (bwd) o += NP;       // column sums of the triangular sweep
+  L.rho = o; L.xi = o;
+  if (bwd && rowarr) { L.rho = o; o += NP; L.xi = o; o += NP * EV; }
   L.nOut = 1 + D;
   L.out = o; o += E * L.nOut;
   L.m = o; o += GPMPC_MAX_D;
