@@ -46,11 +46,11 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   constexpr int E = EV;
   const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
-  double u0[EV], u1[EV], kr0, kr1;
+  double u0[EV], u1[EV], bi0[E], bi1[E], kr0, kr1;
   {
-    double n0[EV], n1[EV], bt0[E], bt1[E];   // row betas are re-read after the sweep (keeps 16 registers free)
-    uni_load_rec<EV>(s_rec, rlen, i0, n0, kr0, bt0);
-    uni_load_rec<EV>(s_rec, rlen, i1, n1, kr1, bt1);
+    double n0[EV], n1[EV];
+    uni_load_rec<EV>(s_rec, rlen, i0, n0, kr0, bi0);
+    uni_load_rec<EV>(s_rec, rlen, i1, n1, kr1, bi1);
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       double q0 = 0.0, q1 = 0.0;
@@ -66,43 +66,21 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   double r0[E], r1[E], tr = 0.0;
 #pragma unroll
   for (int b = 0; b < E; b++) { r0[b] = 0.0; r1[b] = 0.0; }
-  // iK row j, lane = column i (symmetric matrix): L2-resident, ~500 cycles away -> the loads of the NEXT group of
-  // four columns are issued before the current group is computed (register double buffer)
-  const double* __restrict__ ik = p.iK + (size_t)jbeg * NP + i0;
-  double ka[4], kb[4];
+  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
+#pragma unroll 4
+  for (int j = jbeg; j < jend; j++) {
+    double nj[EV], bj[E], kj;
+    uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
+    const double k0 = __ldg(ik0), k1 = __ldg(ik0 + 32);
+    ik0 += NP;
+    double t0 = kr0 + kj, t1 = kr1 + kj;
 #pragma unroll
-  for (int q = 0; q < 4; q++) { ka[q] = __ldg(ik + (size_t)q * NP); kb[q] = __ldg(ik + (size_t)q * NP + 32); }
-  for (int j = jbeg; j < jend; j += 4) {
-    double na[4], nb[4];
-    ik += (size_t)4 * NP;
-    if (j + 4 < jend) {
+    for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
+    const double e0 = exp_tab(t0, s_tab), e1 = exp_tab(t1, s_tab);
 #pragma unroll
-      for (int q = 0; q < 4; q++) { na[q] = __ldg(ik + (size_t)q * NP); nb[q] = __ldg(ik + (size_t)q * NP + 32); }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; q++) { na[q] = 0.0; nb[q] = 0.0; }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      double nj[EV], bj[E], kj;
-      uni_load_rec<EV>(s_rec, rlen, j + q, nj, kj, bj);
-      double t0 = kr0 + kj, t1 = kr1 + kj;
-#pragma unroll
-      for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
-      const double e0 = exp_tab(t0, s_tab), e1 = exp_tab(t1, s_tab);
-#pragma unroll
-      for (int b = 0; b < E; b++) { r0[b] = fma(e0, bj[b], r0[b]); r1[b] = fma(e1, bj[b], r1[b]); }
-      tr = fma(e0, ka[q], tr);
-      tr = fma(e1, kb[q], tr);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) { ka[q] = na[q]; kb[q] = nb[q]; }
-  }
-  double bi0[E], bi1[E];
-  {
-    double nn[EV], kk;
-    uni_load_rec<EV>(s_rec, rlen, i0, nn, kk, bi0);
-    uni_load_rec<EV>(s_rec, rlen, i1, nn, kk, bi1);
+    for (int b = 0; b < E; b++) { r0[b] = fma(e0, bj[b], r0[b]); r1[b] = fma(e1, bj[b], r1[b]); }
+    tr = fma(e0, k0, tr);
+    tr = fma(e1, k1, tr);
   }
   // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace
   int pr = 0;
@@ -385,48 +363,32 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   double rho0 = 0.0, rho1 = 0.0, xi0[EV], xi1[EV];
 #pragma unroll
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
-  const double* __restrict__ ik = p.iK + (size_t)jbeg * NP + i0;
-  double ka[4], kb[4];   // register double buffer of the iK loads (see uni_fwd_item)
-#pragma unroll
-  for (int q = 0; q < 4; q++) { ka[q] = __ldg(ik + (size_t)q * NP); kb[q] = __ldg(ik + (size_t)q * NP + 32); }
+  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;
   for (int j0 = jbeg; j0 < jend; j0 += 8) {
     const bool masked = (j0 < 64 * I + 64);
     double v[8];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-      double na[4], nb[4];
-      ik += (size_t)4 * NP;
-      if (j0 + 4 * half + 4 < jend) {
+    for (int jj = 0; jj < 8; jj++) {
+      const int j = j0 + jj;
+      double nj[EV], bj[E], kj;
+      uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
+      double c0 = -wbar * __ldg(ik0), c1 = -wbar * __ldg(ik0 + 32);
+      ik0 += NP;
 #pragma unroll
-        for (int q = 0; q < 4; q++) { na[q] = __ldg(ik + (size_t)q * NP); nb[q] = __ldg(ik + (size_t)q * NP + 32); }
-      } else {
+      for (int b = 0; b < E; b++) { c0 = fma(p0[b], bj[b], c0); c1 = fma(p1[b], bj[b], c1); }
+      double t0 = kr0 + kj, t1 = kr1 + kj;
 #pragma unroll
-        for (int q = 0; q < 4; q++) { na[q] = 0.0; nb[q] = 0.0; }
+      for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
+      double w0 = c0 * exp_tab(t0, s_tab), w1 = c1 * exp_tab(t1, s_tab);
+      if (masked) {
+        w0 = (j > i0) ? w0 : ((j == i0) ? 0.5 * w0 : 0.0);
+        w1 = (j > i1) ? w1 : ((j == i1) ? 0.5 * w1 : 0.0);
       }
+      rho0 += w0;
+      rho1 += w1;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int jj = 4 * half + q, j = j0 + jj;
-        double nj[EV], bj[E], kj;
-        uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
-        double c0 = -wbar * ka[q], c1 = -wbar * kb[q];
-#pragma unroll
-        for (int b = 0; b < E; b++) { c0 = fma(p0[b], bj[b], c0); c1 = fma(p1[b], bj[b], c1); }
-        double t0 = kr0 + kj, t1 = kr1 + kj;
-#pragma unroll
-        for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
-        double w0 = c0 * exp_tab(t0, s_tab), w1 = c1 * exp_tab(t1, s_tab);
-        if (masked) {
-          w0 = (j > i0) ? w0 : ((j == i0) ? 0.5 * w0 : 0.0);
-          w1 = (j > i1) ? w1 : ((j == i1) ? 0.5 * w1 : 0.0);
-        }
-        rho0 += w0;
-        rho1 += w1;
-#pragma unroll
-        for (int e = 0; e < EV; e++) { xi0[e] = fma(w0, nj[e], xi0[e]); xi1[e] = fma(w1, nj[e], xi1[e]); }
-        v[jj] = w0 + w1;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++) { ka[q] = na[q]; kb[q] = nb[q]; }
+      for (int e = 0; e < EV; e++) { xi0[e] = fma(w0, nj[e], xi0[e]); xi1[e] = fma(w1, nj[e], xi1[e]); }
+      v[jj] = w0 + w1;
     }
     int col;
     double tot = col_reduce8(v, lane, col);
