@@ -379,8 +379,6 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     plan(smf, &thr_f, &grid_f, "GPMPC_UNI_FWD_THREADS", "GPMPC_UNI_FWD_CTAS");
     plan(smb, &thr_b, &grid_b, "GPMPC_UNI_BWD_THREADS", "GPMPC_UNI_BWD_CTAS");
     if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg = v; }
-    p.prefetch = 8;
-    if (const char* e = getenv("GPMPC_UNI_PREFETCH")) { int v = atoi(e); if (v >= 0 && v <= 64) p.prefetch = v; }
     if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg_bwd = v; }
     if (h->timing) CU(cudaEventRecord(h->ev[0], st));
     CU(launch_uniform(E, false, p, nullptr, grid_f, thr_f, smf, st));

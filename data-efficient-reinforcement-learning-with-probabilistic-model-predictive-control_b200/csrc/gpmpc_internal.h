@@ -38,7 +38,6 @@ struct RolloutParams {
   int group;           // pairs per N^2 phase
   int seg;             // columns per work item
   int rowarr;          // uniform reverse sweep: per-row partial sums in shared memory (when they fit)
-  int prefetch;        // uniform hot loops: L1 prefetch distance (columns) for the iK rows, 0 = off
   int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
 };
 

@@ -67,16 +67,11 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 #pragma unroll
   for (int b = 0; b < E; b++) { r0[b] = 0.0; r1[b] = 0.0; }
   const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
-  const int pd = p.prefetch;
 #pragma unroll 4
   for (int j = jbeg; j < jend; j++) {
     double nj[EV], bj[E], kj;
     uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
     const double k0 = __ldg(ik0), k1 = __ldg(ik0 + 32);
-    if (pd > 0 && j + pd < jend) {   // pull the row needed UNI_PREFETCH columns later from L2 into L1
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(ik0 + (size_t)pd * NP));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(ik0 + (size_t)pd * NP + 32));
-    }
     ik0 += NP;
     double t0 = kr0 + kj, t1 = kr1 + kj;
 #pragma unroll
@@ -369,7 +364,6 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
 #pragma unroll
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
   const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;
-  const int pd = p.prefetch;
   for (int j0 = jbeg; j0 < jend; j0 += 8) {
     const bool masked = (j0 < 64 * I + 64);
     double v[8];
@@ -379,10 +373,6 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
       double nj[EV], bj[E], kj;
       uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
       double c0 = -wbar * __ldg(ik0), c1 = -wbar * __ldg(ik0 + 32);
-      if (pd > 0 && j + pd < jend) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ik0 + (size_t)pd * NP));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ik0 + (size_t)pd * NP + 32));
-      }
       ik0 += NP;
 #pragma unroll
       for (int b = 0; b < E; b++) { c0 = fma(p0[b], bj[b], c0); c1 = fma(p1[b], bj[b], c1); }

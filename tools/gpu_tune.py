@@ -1,4 +1,4 @@
-"""Tuning sweep for the uniform-kernel launch plan / prefetch distance (env overrides read by libgpmpc)."""
+"""Tuning sweep for the uniform-kernel launch plan (threads / CTAs per SM / item segment sizes)."""
 import os
 import subprocess
 import sys
@@ -17,7 +17,11 @@ for g in (False, True):
     print("grad=%d fwd %.2f bwd %.2f ms -> %.0f preds/s" % (g, f, b, cfg["B"] * cfg["H"] / (f + b) * 1e3), end=" | ")
 print()
 '''
-grid = [{"GPMPC_UNI_PREFETCH": v} for v in (0, 2, 4, 8, 16, 32)]
+grid = [{}]
+for ft, fc in ((128, 4), (256, 2), (128, 3)):
+    grid.append({"GPMPC_UNI_FWD_THREADS": ft, "GPMPC_UNI_FWD_CTAS": fc, "GPMPC_UNI_SEG": 256})
+for bt, bc in ((256, 2), (128, 2), (128, 3), (256, 1)):
+    grid.append({"GPMPC_UNI_BWD_THREADS": bt, "GPMPC_UNI_BWD_CTAS": bc, "GPMPC_UNI_SEG_BWD": 64})
 for cfg in grid:
     env = dict(os.environ)
     env.update({k: str(v) for k, v in cfg.items()})
