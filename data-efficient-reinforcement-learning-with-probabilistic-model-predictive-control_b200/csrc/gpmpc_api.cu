@@ -355,14 +355,10 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     } else {
       p.records = nullptr;
     }
-    // forward: stage iK through shared memory (cp.async, 8 KB per warp) when two 256-thread CTAs still fit
-    size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false, 8);
-    p.ikstage = (smf <= 112 * 1024 && E <= 5) ? 1 : 0;
-    if (const char* e = getenv("GPMPC_UNI_IKSTAGE")) p.ikstage = (atoi(e) != 0 && smf <= 112 * 1024) ? 1 : 0;
-    if (!p.ikstage) smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false, 0);
-    size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true, 0);
+    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false);
+    size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true);
     p.rowarr = smb <= 112 * 1024 ? 1 : 0;      // per-row arrays only while two CTAs still fit on an SM
-    if (!p.rowarr) smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false, 0);
+    if (!p.rowarr) smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false);
     if (smf > h->smem_optin || (want_grad && smb > h->smem_optin))
       return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
     // several small CTAs per SM so that one CTA's serial small-matrix phases overlap another's N^2 sweep
@@ -381,7 +377,6 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     };
     int thr_f, grid_f, thr_b, grid_b;
     plan(smf, &thr_f, &grid_f, "GPMPC_UNI_FWD_THREADS", "GPMPC_UNI_FWD_CTAS");
-    if (p.ikstage) { thr_f = 256; grid_f = B < 2 * h->num_sms ? B : 2 * h->num_sms; }   // layout sized for 8 warps
     plan(smb, &thr_b, &grid_b, "GPMPC_UNI_BWD_THREADS", "GPMPC_UNI_BWD_CTAS");
     if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg = v; }
     if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg_bwd = v; }

@@ -71,17 +71,6 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
 }
 
 // ---------------------------------------------------------------------------------------------
-// cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass the register file
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-// ---------------------------------------------------------------------------------------------
 // Small dense SPD helpers (n <= 8), used once per step per GP / pair.
 // ---------------------------------------------------------------------------------------------
 // inv = a^-1, det = det(a) for symmetric positive definite a (n x n, row-major).  A non-positive

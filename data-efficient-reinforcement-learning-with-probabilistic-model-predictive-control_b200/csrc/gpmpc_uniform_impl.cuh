@@ -38,11 +38,11 @@ __device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, i
   for (int b = 0; b < EV; b++) beta[b] = buf[EV + 1 + b];
 }
 
-template <int EV, bool STAGE>
+template <int EV>
 __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
                                              const double* __restrict__ Qm, const double* __restrict__ il2, int I,
                                              int jbeg, int jend, int lane, double* s_acc,
-                                             const double* __restrict__ s_tab, double* __restrict__ ikbuf) {
+                                             const double* __restrict__ s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
@@ -66,44 +66,6 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   double r0[E], r1[E], tr = 0.0;
 #pragma unroll
   for (int b = 0; b < E; b++) { r0[b] = 0.0; r1[b] = 0.0; }
-  if (STAGE) {
-    // iK rows j (symmetric: row j = column j), columns 64 I .. 64 I + 63 = one 512 B segment per j.  Each lane
-    // copies 16 B of it with cp.async into this warp's double buffer, 8 rows per stage, one stage ahead of the
-    // arithmetic: the ~500-cycle L2 latency never reaches the scoreboard of the FMA that consumes iK.
-    const double* __restrict__ src = p.iK + (size_t)jbeg * NP + 64 * I + 2 * lane;
-#pragma unroll
-    for (int q = 0; q < 8; q++) cp_async16(ikbuf + q * 64 + 2 * lane, src + (size_t)q * NP);
-    cp_async_commit();
-    int stage = 0;
-    for (int j0 = jbeg; j0 < jend; j0 += 8) {
-      if (j0 + 8 < jend) {
-        const double* __restrict__ nxt = src + (size_t)(j0 - jbeg + 8) * NP;
-#pragma unroll
-        for (int q = 0; q < 8; q++) cp_async16(ikbuf + (stage ^ 1) * 512 + q * 64 + 2 * lane, nxt + (size_t)q * NP);
-      }
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
-      const double* __restrict__ kb = ikbuf + stage * 512 + lane;
-#pragma unroll 4
-      for (int q = 0; q < 8; q++) {
-        double nj[EV], bj[E], kj;
-        uni_load_rec<EV>(s_rec, rlen, j0 + q, nj, kj, bj);
-        const double k0 = kb[q * 64], k1 = kb[q * 64 + 32];
-        double t0 = kr0 + kj, t1 = kr1 + kj;
-#pragma unroll
-        for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
-        const double e0 = exp_tab(t0, s_tab), e1 = exp_tab(t1, s_tab);
-#pragma unroll
-        for (int b = 0; b < E; b++) { r0[b] = fma(e0, bj[b], r0[b]); r1[b] = fma(e1, bj[b], r1[b]); }
-        tr = fma(e0, k0, tr);
-        tr = fma(e1, k1, tr);
-      }
-      __syncwarp();
-      stage ^= 1;
-    }
-    cp_async_wait<0>();
-  } else {
   const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
 #pragma unroll 4
   for (int j = jbeg; j < jend; j++) {
@@ -119,7 +81,6 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
     for (int b = 0; b < E; b++) { r0[b] = fma(e0, bj[b], r0[b]); r1[b] = fma(e1, bj[b], r1[b]); }
     tr = fma(e0, k0, tr);
     tr = fma(e1, k1, tr);
-  }
   }
   // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace
   int pr = 0;
@@ -138,16 +99,15 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 // ---------------------------------------------------------------------------------------------
 // uniform forward kernel (value + small per-step record when p.records != NULL)
 // ---------------------------------------------------------------------------------------------
-template <int EV, bool STAGE>
+template <int EV>
 __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) uniform_fwd_kernel(const RolloutParams p) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
   constexpr int P = E * (E + 1) / 2;
-  const UniLayout L = make_uni_layout(EV, false, NP, DP, D, H, Na, false, STAGE ? (int)(blockDim.x >> 5) : 0);
+  const UniLayout L = make_uni_layout(EV, false, NP, DP, D, H, Na);
   double* s_rec = sm + L.rec; double* s_out = sm + L.out;
-  double* s_ikbuf = sm + L.ikbuf + (threadIdx.x >> 5) * 1024;
   double* s_m = sm + L.m; double* s_s = sm + L.s; double* s_mu = sm + L.mu; double* s_A = sm + L.A;
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
@@ -282,7 +242,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) unifor
           if (item >= nitems) break;
           const int I = item / nseg, js = item - I * nseg;
           const int jbeg = js * p.seg, jend = min(NP, jbeg + p.seg);
-          uni_fwd_item<EV, STAGE>(p, s_rec, L.rlen, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab, s_ikbuf);
+          uni_fwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab);
         }
       }
       __syncthreads();
@@ -869,14 +829,10 @@ cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, 
     e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     uniform_bwd_kernel<EV, false><<<grid, threads, smem, st>>>(p, grad);
-  } else if (p.ikstage) {
-    e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    uniform_fwd_kernel<EV, true><<<grid, threads, smem, st>>>(p);
   } else {
-    e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(uniform_fwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uniform_fwd_kernel<EV, false><<<grid, threads, smem, st>>>(p);
+    uniform_fwd_kernel<EV><<<grid, threads, smem, st>>>(p);
   }
   return cudaGetLastError();
 }

@@ -6,15 +6,13 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, rlen, rhot, gam, rho, xi, ikbuf, out, nOut;
+  int rec, rlen, rhot, gam, rho, xi, out, nOut;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
 // bwd=false: forward kernel; bwd=true: reverse-sweep kernel (needs rho/gam/xi arrays)
 // rowarr (reverse sweep only): keep per-row partial sums rho_i, xi_i in shared memory (fast path when it fits)
-// ikwarps > 0: per-warp double buffer (2 x 8 rows x 64 columns) for the cp.async staging of iK tiles
-HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool rowarr = false,
-                             int ikwarps = 0) {
+HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool rowarr = false) {
   UniLayout L;
   const int E = EV, P = E * (E + 1) / 2;
   int o = 0;
@@ -27,7 +25,6 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.gam = o; if (bwd) o += NP;       // column sums of the triangular sweep
   L.rho = o; L.xi = o;
   if (bwd && rowarr) { L.rho = o; o += NP; L.xi = o; o += NP * EV; }
-  L.ikbuf = o; o += ikwarps * 1024;
   L.nOut = 1 + D;
   L.out = o; o += E * L.nOut;
   L.m = o; o += GPMPC_MAX_D;
