@@ -299,10 +299,15 @@ def main():
         preds_rank0 = Bl * H
         achieved = preds_rank0 * b_alg / (fwd_ms * 1e-3) / 1e9
         fp64_peak = _cabi.measure_fp64_peak(local_rank)
+        uniform = eng.uses_uniform_path()
+        kname = ("gpmpc::uniform_fwd_kernel<%d> (one exp per (i,j) for all output pairs)" % E) if uniform else \
+            ("gpmpc::rollout_kernel<%d,true> (per-pair sweep + forward-mode Jacobian records)" % E)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                    "kernel": "gpmpc::rollout_kernel<%d,true> (fwd+Jacobian records), %.2f ms/launch for %d predictions"
-                              % (E, fwd_ms, preds_rank0),
+                    "kernel": "%s, %.2f ms/launch for %d predictions" % (kname, fwd_ms, preds_rank0),
+                    "reverse_sweep_kernel": ("gpmpc::uniform_bwd_kernel<%d> (adjoint-weighted upper-triangle N^2 sweep), "
+                                             "%.2f ms/launch" % (E, bwd_ms)) if uniform else
+                    ("gpmpc::backward_kernel<%d> (small-matrix algebra on records), %.2f ms/launch" % (E, bwd_ms)),
                     "algorithmic_bytes_per_prediction": b_alg,
                     "note": "algorithmic bytes (SURVEY 8(d): 8*(E N^2 + E N + N D) per prediction) are served from L2/L1/"
                             "shared memory -- the training block is shared by all candidates -- so frac>1 is expected; "
@@ -317,6 +322,7 @@ def main():
                 "config": workload_config(cfg, args),
                 "forward_only": {"value": preds * args.steps / (ms_fwd * 1e-3), "unit": UNIT,
                                  "ms_per_step": ms_fwd / args.steps},
+                "kernel_path": "uniform (all GPs share their hyper-parameters)" if uniform else "general (per-pair)",
                 "kernel_ms": {"rollout_fwd": fwd_ms, "reverse_sweep": bwd_ms},
                 "prepare_ms": {"first_call": prepare_ms_first, "steady": prepare_ms,
                                "what": "Gram + Cholesky + iK + beta for %d GPs, N=%d (once per control step)" % (E, N)},
