@@ -70,6 +70,43 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   return __hiloint2double(hi, __double2loint(res));
 }
 
+// Four exponentials evaluated stage by stage (4 independent FMAs per stage).  Measured on B200: the FP64 pipe
+// needs ~4 independent dependent-chains PER WARP to saturate (DFMA latency 8.3 clk; 4 warps x 1 chain reach only
+// 65 % of peak, 4 warps x 4 chains 92 % -- tools/micro/dfma_latency.cu), so the hot loops feed it 4 elements at once.
+__device__ __forceinline__ void exp_tab_x4(const double (&x)[4], double (&res)[4], const double* __restrict__ tab) {
+  const double INV = 4.61662413084468283841e+01, SHIFT = 6755399441055744.0;
+  double kd[4], r[4], p[4], t[4];
+  int n[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) kd[c] = __fma_rn(x[c], INV, SHIFT);
+#pragma unroll
+  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }
+#pragma unroll
+  for (int c = 0; c < 4; c++) r[c] = __fma_rn(kd[c], -2.16608493792591616511e-02, x[c]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) r[c] = __fma_rn(kd[c], -1.32391292681540124659e-11, r[c]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) { n[c] = max(n[c], -32704); t[c] = tab[n[c] & 31]; }
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = __fma_rn(1.38888888888888888889e-03, r[c], 8.33333333333333333333e-03);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 4.16666666666666666667e-02);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 1.66666666666666666667e-01);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 0.5);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 1.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] *= r[c];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const double v = __fma_rn(t[c], p[c], t[c]);
+    const int hi = __double2hiint(v) + (int)(((unsigned)n[c] & 0xFFFFFFE0u) << 15);
+    res[c] = __hiloint2double(hi, __double2loint(v));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Small dense SPD helpers (n <= 8), used once per step per GP / pair.
 // ---------------------------------------------------------------------------------------------

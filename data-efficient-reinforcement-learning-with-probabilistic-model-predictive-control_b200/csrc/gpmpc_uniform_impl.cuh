@@ -19,6 +19,10 @@
 
 namespace gpmpc {
 
+#ifndef UNI_MINB
+#define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // forward hot loop: full sweep, rows {64 I + lane, +32}, columns [jbeg, jend)
 //   r_b,i += Eh_ij beta_b,j  (E FMAs),  tr += Eh_ij iK_ij  (1 FMA)   [gp_model.py:169-175 for all (a,b) at once]
@@ -67,21 +71,33 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 #pragma unroll
   for (int b = 0; b < E; b++) { r0[b] = 0.0; r1[b] = 0.0; }
   const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
-#pragma unroll 4
-  for (int j = jbeg; j < jend; j++) {
-    double nj[EV], bj[E], kj;
-    uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
-    const double k0 = __ldg(ik0), k1 = __ldg(ik0 + 32);
-    ik0 += NP;
-    double t0 = kr0 + kj, t1 = kr1 + kj;
+  double tr2 = 0.0;
+#pragma unroll 2
+  for (int j = jbeg; j < jend; j += 2) {   // 2 columns x 2 rows = 4 independent chains per warp
+    double na[EV], nb[EV], ba[E], bb[E], ka, kb;
+    uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
+    uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
+    const double k0a = __ldg(ik0), k1a = __ldg(ik0 + 32), k0b = __ldg(ik0 + NP), k1b = __ldg(ik0 + NP + 32);
+    ik0 += 2 * (size_t)NP;
+    double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, ex[4];
 #pragma unroll
-    for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
-    const double e0 = exp_tab(t0, s_tab), e1 = exp_tab(t1, s_tab);
+    for (int e = 0; e < EV; e++) {
+      t[0] = fma(u0[e], na[e], t[0]);
+      t[1] = fma(u1[e], na[e], t[1]);
+      t[2] = fma(u0[e], nb[e], t[2]);
+      t[3] = fma(u1[e], nb[e], t[3]);
+    }
+    exp_tab_x4(t, ex, s_tab);
 #pragma unroll
-    for (int b = 0; b < E; b++) { r0[b] = fma(e0, bj[b], r0[b]); r1[b] = fma(e1, bj[b], r1[b]); }
-    tr = fma(e0, k0, tr);
-    tr = fma(e1, k1, tr);
+    for (int b = 0; b < E; b++) { r0[b] = fma(ex[0], ba[b], r0[b]); r1[b] = fma(ex[1], ba[b], r1[b]); }
+#pragma unroll
+    for (int b = 0; b < E; b++) { r0[b] = fma(ex[2], bb[b], r0[b]); r1[b] = fma(ex[3], bb[b], r1[b]); }
+    tr = fma(ex[0], k0a, tr);
+    tr2 = fma(ex[1], k1a, tr2);
+    tr = fma(ex[2], k0b, tr);
+    tr2 = fma(ex[3], k1b, tr2);
   }
+  tr += tr2;
   // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace
   int pr = 0;
 #pragma unroll
@@ -100,7 +116,7 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 // uniform forward kernel (value + small per-step record when p.records != NULL)
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) uniform_fwd_kernel(const RolloutParams p) {
+__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd_kernel(const RolloutParams p) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -368,27 +384,51 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
     const bool masked = (j0 < 64 * I + 64);
     double v[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int j = j0 + jj;
-      double nj[EV], bj[E], kj;
-      uni_load_rec<EV>(s_rec, rlen, j, nj, kj, bj);
-      double c0 = -wbar * __ldg(ik0), c1 = -wbar * __ldg(ik0 + 32);
-      ik0 += NP;
+    for (int jp = 0; jp < 4; jp++) {   // pairs of columns: 2 columns x 2 rows = 4 independent chains per warp
+      const int j = j0 + 2 * jp;
+      double na[EV], nb[EV], ba[E], bb[E], ka, kb;
+      uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
+      uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
+      double c[4] = {-wbar * __ldg(ik0), -wbar * __ldg(ik0 + 32), -wbar * __ldg(ik0 + NP), -wbar * __ldg(ik0 + NP + 32)};
+      ik0 += 2 * (size_t)NP;
 #pragma unroll
-      for (int b = 0; b < E; b++) { c0 = fma(p0[b], bj[b], c0); c1 = fma(p1[b], bj[b], c1); }
-      double t0 = kr0 + kj, t1 = kr1 + kj;
-#pragma unroll
-      for (int e = 0; e < EV; e++) { t0 = fma(u0[e], nj[e], t0); t1 = fma(u1[e], nj[e], t1); }
-      double w0 = c0 * exp_tab(t0, s_tab), w1 = c1 * exp_tab(t1, s_tab);
-      if (masked) {
-        w0 = (j > i0) ? w0 : ((j == i0) ? 0.5 * w0 : 0.0);
-        w1 = (j > i1) ? w1 : ((j == i1) ? 0.5 * w1 : 0.0);
+      for (int b = 0; b < E; b++) {
+        c[0] = fma(p0[b], ba[b], c[0]);
+        c[1] = fma(p1[b], ba[b], c[1]);
+        c[2] = fma(p0[b], bb[b], c[2]);
+        c[3] = fma(p1[b], bb[b], c[3]);
       }
-      rho0 += w0;
-      rho1 += w1;
+      double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, w[4];
 #pragma unroll
-      for (int e = 0; e < EV; e++) { xi0[e] = fma(w0, nj[e], xi0[e]); xi1[e] = fma(w1, nj[e], xi1[e]); }
-      v[jj] = w0 + w1;
+      for (int e = 0; e < EV; e++) {
+        t[0] = fma(u0[e], na[e], t[0]);
+        t[1] = fma(u1[e], na[e], t[1]);
+        t[2] = fma(u0[e], nb[e], t[2]);
+        t[3] = fma(u1[e], nb[e], t[3]);
+      }
+      exp_tab_x4(t, w, s_tab);
+#pragma unroll
+      for (int q = 0; q < 4; q++) w[q] *= c[q];
+      if (masked) {
+        w[0] = (j > i0) ? w[0] : ((j == i0) ? 0.5 * w[0] : 0.0);
+        w[1] = (j > i1) ? w[1] : ((j == i1) ? 0.5 * w[1] : 0.0);
+        w[2] = (j + 1 > i0) ? w[2] : ((j + 1 == i0) ? 0.5 * w[2] : 0.0);
+        w[3] = (j + 1 > i1) ? w[3] : ((j + 1 == i1) ? 0.5 * w[3] : 0.0);
+      }
+      rho0 += w[0] + w[2];
+      rho1 += w[1] + w[3];
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+        xi0[e] = fma(w[0], na[e], xi0[e]);
+        xi1[e] = fma(w[1], na[e], xi1[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+        xi0[e] = fma(w[2], nb[e], xi0[e]);
+        xi1[e] = fma(w[3], nb[e], xi1[e]);
+      }
+      v[2 * jp] = w[0] + w[1];
+      v[2 * jp + 1] = w[2] + w[3];
     }
     int col;
     double tot = col_reduce8(v, lane, col);
@@ -444,7 +484,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
 template <int EV, bool ROWARR>
-__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, (EV <= 5 ? 2 : 1)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
+__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;

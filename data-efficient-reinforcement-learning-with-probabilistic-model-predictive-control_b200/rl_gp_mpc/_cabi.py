@@ -8,7 +8,7 @@ import os
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libgpmpc.so")
+_LIB_PATH = os.environ.get("GPMPC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libgpmpc.so")
 _lib = None
 
 GPMPC_OK = 0

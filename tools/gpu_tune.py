@@ -17,11 +17,7 @@ for g in (False, True):
     print("grad=%d fwd %.2f bwd %.2f ms -> %.0f preds/s" % (g, f, b, cfg["B"] * cfg["H"] / (f + b) * 1e3), end=" | ")
 print()
 '''
-grid = [{}]
-for ft, fc in ((128, 4), (256, 2), (128, 3)):
-    grid.append({"GPMPC_UNI_FWD_THREADS": ft, "GPMPC_UNI_FWD_CTAS": fc, "GPMPC_UNI_SEG": 256})
-for bt, bc in ((256, 2), (128, 2), (128, 3), (256, 1)):
-    grid.append({"GPMPC_UNI_BWD_THREADS": bt, "GPMPC_UNI_BWD_CTAS": bc, "GPMPC_UNI_SEG_BWD": 64})
+grid = [{}, {"GPMPC_UNI_FWD_THREADS": 256, "GPMPC_UNI_FWD_CTAS": 2, "GPMPC_UNI_SEG": 256}]
 for cfg in grid:
     env = dict(os.environ)
     env.update({k: str(v) for k, v in cfg.items()})
