@@ -9,10 +9,14 @@ _DEFAULT_OPTIMIZER_PARAMS = {
 class ControllerConfig:
     def __init__(self, len_horizon: int = 15, actions_optimizer_params: dict = None,
                  init_from_previous_actions: bool = True, restarts_optim: int = 1, optimize: bool = True,
-                 num_repeat_actions: int = 1):
+                 num_repeat_actions: int = 1, batched_candidates: int = 0, batched_iters: int = 30,
+                 batched_lr: float = 0.05):
         """len_horizon: MPC steps; actions_optimizer_params: scipy L-BFGS-B options; init_from_previous_actions:
         warm start from the shifted previous solution; restarts_optim: optimiser restarts; optimize: False =
-        random actions (debug); num_repeat_actions: each action is held this many env steps."""
+        random actions (debug); num_repeat_actions: each action is held this many env steps.
+        NEW (additive, default off): batched_candidates > 0 replaces the serial scipy restarts by that many candidate
+        sequences optimised simultaneously on the device (projected Adam, batched_iters steps of size batched_lr),
+        every objective/gradient evaluation being ONE batched rollout."""
         self.len_horizon = len_horizon
         self.actions_optimizer_params = dict(_DEFAULT_OPTIMIZER_PARAMS) if actions_optimizer_params is None \
             else actions_optimizer_params
@@ -20,3 +24,6 @@ class ControllerConfig:
         self.restarts_optim = restarts_optim
         self.optimize = optimize
         self.num_repeat_actions = num_repeat_actions
+        self.batched_candidates = batched_candidates
+        self.batched_iters = batched_iters
+        self.batched_lr = batched_lr

@@ -89,9 +89,55 @@ class GpMpcController(BaseControllerObject):
         x_mem, y_mem = self.memory.get()
         self.transition_model.prepare_inference(x_mem, y_mem)
 
+    def _get_optimal_actions_batched(self, state_mu, state_var):
+        """B candidate action sequences optimised at once on the device (box-projected Adam on the LCB objective).
+
+        Replaces the serial restart loop of the reference (gp_mpc_controller.py:125-148): candidate 0 is the shifted
+        previous solution (when init_from_previous_actions), the others are uniform random restarts; each iteration
+        costs one batched rollout (value + gradient for all candidates).  Returns the model actions of the best one."""
+        ctl = self.config.controller
+        h, na = ctl.len_horizon, self.actions_mapper.dim_action
+        nb = int(ctl.batched_candidates)
+        dev = self.transition_model.engine.device
+        x = torch.rand((nb, h * na), dtype=torch.float64, device=dev)
+        if ctl.init_from_previous_actions and self.actions_mpc_previous_iter is not None:
+            warm = generate_mpc_action_init_frompreviousiter(self.actions_mpc_previous_iter, dim_action=na)
+            x[0] = torch.as_tensor(warm, dtype=torch.float64, device=dev)
+        m = torch.zeros_like(x)
+        v = torch.zeros_like(x)
+        best_cost = torch.full((nb,), float("inf"), dtype=torch.float64, device=dev)
+        best_x = x.clone()
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        for k in range(1, int(ctl.batched_iters) + 1):
+            out = self._rollout(x, state_mu, state_var, need_grad=True)
+            cost, grad = out["cost"], out["grad"]
+            ok = torch.isfinite(cost)
+            better = ok & (cost < best_cost)
+            best_cost = torch.where(better, cost, best_cost)
+            best_x[better] = x[better]
+            grad = torch.nan_to_num(grad, nan=0.0, posinf=0.0, neginf=0.0)
+            m.mul_(b1).add_(grad, alpha=1 - b1)
+            v.mul_(b2).addcmul_(grad, grad, value=1 - b2)
+            step = (m / (1 - b1 ** k)) / ((v / (1 - b2 ** k)).sqrt() + eps)
+            x = (x - ctl.batched_lr * step).clamp_(0.0, 1.0)
+        out = self._rollout(x, state_mu, state_var, need_grad=False)
+        cost = out["cost"]
+        better = torch.isfinite(cost) & (cost < best_cost)
+        best_cost = torch.where(better, cost, best_cost)
+        best_x[better] = x[better]
+        idx = int(torch.argmin(best_cost).item())
+        final = self._rollout(best_x[idx:idx + 1], state_mu, state_var, need_grad=False)   # side effects of the winner
+        self._store_side_effects(final, 0)
+        self.batched_costs = best_cost
+        self.last_optim_cost = float(best_cost[idx].item())
+        self.actions_mpc_previous_iter = best_x[idx].cpu().numpy().copy()
+        return self.actions_mapper.transform_action_mpc_to_action_model(best_x[idx].cpu())
+
     def _get_optimal_actions(self, state_mu, state_var):
         self._prepare()
         ctl = self.config.controller
+        if getattr(ctl, "batched_candidates", 0) and ctl.optimize:
+            return self._get_optimal_actions_batched(state_mu, state_var)
         h, na = ctl.len_horizon, self.actions_mapper.dim_action
         best_val, best_actions = np.inf, None
         for idx_restart in range(ctl.restarts_optim):
@@ -109,6 +155,7 @@ class GpMpcController(BaseControllerObject):
             if val < best_val or (best_actions is None and np.isnan(val)):
                 best_val, best_actions = val, cand
         self.actions_mpc_previous_iter = best_actions.copy()
+        self.last_optim_cost = float(best_val)   # additive: objective value of the returned action sequence
         return self.actions_mapper.transform_action_mpc_to_action_model(torch.as_tensor(best_actions))
 
     def _get_random_actions(self, state_mu, state_var):
