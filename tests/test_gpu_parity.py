@@ -277,3 +277,35 @@ def test_batched_on_device_optimizer_beats_serial_restarts():
     assert a_batched.shape == a_serial.shape and -1.0 <= a_batched[0] <= 1.0
     assert np.isfinite(cost_batched) and cost_batched <= cost_serial + 1e-6
     assert batched.batched_costs.shape == (256,) and batched.get_iter_info().predicted_states.shape == (9, 3)
+
+
+def test_kernel_path_selection_follows_the_hyperparameters():
+    """prepare() re-detects whether all GPs share their hyper-parameters; both paths give the same answer."""
+    cfg = make_workload("C3", B=4, H=3, seed=41, N=100)
+    eng = make_engine(cfg)
+    assert eng.uses_uniform_path()
+    uni = rollout(eng, cfg)
+    eng.set_path(1)
+    assert not eng.uses_uniform_path()
+    gen = rollout(eng, cfg)
+    np.testing.assert_allclose(uni["cost"], gen["cost"], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(uni["grad"], gen["grad"], rtol=0, atol=ATOL_GRAD)
+    eng.set_path(0)
+    ls = full_lengthscale(cfg).copy()
+    ls[1, 0] *= 1.0000001                                   # one GP differs in one lengthscale -> general path
+    eng.prepare(cfg["x"], cfg["y"], ls, cfg["outputscale"], cfg["noise"])
+    assert not eng.uses_uniform_path()
+    eng.prepare(cfg["x"], cfg["y"], full_lengthscale(cfg), cfg["outputscale"], cfg["noise"])
+    assert eng.uses_uniform_path()
+
+
+def test_uniform_path_large_state_dimension():
+    """C5 dims (E=8, Na=3, D=11) on the uniform path (255-register kernels, owner-lane reductions)."""
+    cfg = make_workload(E=8, Na=3, N=200, H=2, B=2, ls=0.7, seed=42)
+    eng = make_engine(cfg)
+    assert eng.uses_uniform_path()
+    want = orc.evaluate_workload(cfg)
+    got = rollout(eng, cfg)
+    np.testing.assert_allclose(got["cost"], want["cost"], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(got["grad"], want["grad"], rtol=0, atol=ATOL_GRAD)
+    np.testing.assert_allclose(got["states_var_pred"], want["states_var_pred"], rtol=0, atol=ATOL)
