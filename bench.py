@@ -189,6 +189,8 @@ def fp64_report(uniform, E, N, preds, fwd_ms, bwd_ms, f_alg, peak):
 # ------------------------------------------------------------------------------------------ CUDA arm
 def main():
     args = parse_args()
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
