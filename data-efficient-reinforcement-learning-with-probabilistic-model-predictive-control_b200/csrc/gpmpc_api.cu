@@ -263,7 +263,7 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
   p.seg_bwd = 64;
   if (uniform) {
     p.group = 1;
-    p.seg = 128;
+    p.seg = 256;
     *smem = 0;
     *grid = 0;
     return GPMPC_OK;
@@ -355,10 +355,17 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     } else {
       p.records = nullptr;
     }
-    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false);
-    size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true);
+    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false, false);
+    size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true, false);
     p.rowarr = smb <= 112 * 1024 ? 1 : 0;      // per-row arrays only while two CTAs still fit on an SM
-    if (!p.rowarr) smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false);
+    if (!p.rowarr) smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false, false);
+    {  // precomputed per-step matrices: only if they do not cost a resident CTA (or the launch itself)
+      const size_t with = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, p.rowarr != 0, true);
+      const size_t lim = smb <= 112 * 1024 ? 112 * 1024 : h->smem_optin;
+      p.premat = with <= lim ? 1 : 0;
+      if (const char* e = getenv("GPMPC_UNI_PREMAT")) p.premat = (atoi(e) != 0 && with <= lim) ? 1 : 0;
+      if (p.premat) smb = with;
+    }
     if (smf > h->smem_optin || (want_grad && smb > h->smem_optin))
       return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
     // several small CTAs per SM so that one CTA's serial small-matrix phases overlap another's N^2 sweep
@@ -366,8 +373,8 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       const size_t per_sm = 227 * 1024;
       int fit = (int)(per_sm / (sm + 1024));
       if (fit < 1) fit = 1;
-      int ctas = fit > 4 ? 4 : fit;
-      *thr = ctas >= 4 ? 128 : 256;
+      int ctas = fit > 2 ? 2 : fit;      // tuned on B200: 2 CTAs x 256 threads per SM (16 warps, <= 128 registers)
+      *thr = 256;
       if (const char* e = getenv(env_thr)) { int v = atoi(e); if (v == 128 || v == 256) *thr = v; }   // tuning aid
       if (const char* e = getenv(env_ctas)) { int v = atoi(e); if (v >= 1 && v <= fit) ctas = v; }
       if (E > 5) { *thr = 256; ctas = 1; }   // large state dims: 255-register kernels, one CTA per SM

@@ -481,6 +481,62 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Step quantities of the reverse sweep that depend only on the FORWARD trajectory (not on the adjoints flowing
+// back): the shared small matrices and the stage-cost adjoint.  With `premat` they are computed for all H steps in
+// parallel (one thread per step) before the serial sweep, which shortens its single-thread critical path.
+// ---------------------------------------------------------------------------------------------
+template <int EV>
+__device__ inline void uni_step_matrices(const double* sp, const double* il2, double s2, double* A, double* Q,
+                                         double* Rinv, double& c, double& detR) {
+  double Ca[EV * EV], det, pl = 1.0, Wd[EV];
+  for (int e = 0; e < EV; e++)
+    for (int f = 0; f < EV; f++) Ca[e * EV + f] = sp[e * EV + f] + (e == f ? 1.0 / il2[e] : 0.0);
+  spd_inv_det<EV>(Ca, A, det);
+  for (int e = 0; e < EV; e++) { pl *= il2[e]; Wd[e] = 2.0 * il2[e]; }
+  c = s2 / sqrt(det * pl);
+  pair_matrices<EV>(sp, Wd, Rinv, Q, detR);
+}
+
+// adjoint of the stage cost at (mup, sp, am) (setpoint_distance_reward_mapper.py:12-68): ADDS into dmu (E), da (Na),
+// dS (E x E, symmetrised)
+template <int EV>
+__device__ inline void uni_stage_adjoint(const RolloutParams& p, int Na, double wmu, double wv, const double* mup,
+                                         const double* sp, const double* am, double* dmu, double* da, double* dS) {
+  constexpr int E = EV;
+  const int Dc = E + Na;
+  double e[GPMPC_MAX_D], We[GPMPC_MAX_D], sWe[EV], t1[EV * EV];
+  for (int d = 0; d < Dc; d++) e[d] = (d < E ? mup[d] : am[d - E]) - p.c_target[d];
+  for (int d = 0; d < Dc; d++) { double v = 0.0; for (int k = 0; k < Dc; k++) v += p.c_W[d * Dc + k] * e[k]; We[d] = v; }
+  for (int i = 0; i < E; i++) { double v = 0.0; for (int k = 0; k < E; k++) v += sp[i * E + k] * We[k]; sWe[i] = v; }
+  for (int d = 0; d < Dc; d++) {
+    double v = 0.0;
+    for (int i = 0; i < E; i++) v += p.c_W[i * Dc + d] * sWe[i];
+    const double gd = wmu * 2.0 * We[d] + wv * 8.0 * v;
+    if (d < E) dmu[d] += gd; else da[d - E] += gd;
+  }
+  for (int i = 0; i < E; i++)
+    for (int k = 0; k < E; k++) { double v = 0.0; for (int l = 0; l < E; l++) v += p.c_W[l * Dc + i] * sp[k * E + l]; t1[i * E + k] = v; }
+  for (int i = 0; i < E; i++)
+    for (int k = 0; k < E; k++) {
+      double v = 0.0;
+      for (int l = 0; l < E; l++) v += t1[i * E + l] * p.c_W[k * Dc + l];
+      const double full_ik = wmu * p.c_W[k * Dc + i] + wv * (4.0 * v + 4.0 * We[i] * We[k]);
+      dS[i * E + k] += 0.5 * full_ik;
+      dS[k * E + i] += 0.5 * full_ik;
+    }
+  if (p.use_constraints) {
+    const double rt2 = 1.4142135623730951, ispi = 0.5641895835477563;
+    for (int d = 0; d < E; d++) {
+      double sig = sp[d * E + d];
+      double zmin = (p.c_smin[d] - mup[d]) / (sig * rt2), zmax = (p.c_smax[d] - mup[d]) / (sig * rt2);
+      double pmin = exp(-zmin * zmin) * ispi, pmax = exp(-zmax * zmax) * ispi;
+      dmu[d] += wmu * (pmin - pmax) * (-1.0 / (sig * rt2));
+      dS[d * E + d] += wmu * (pmin * (-zmin / sig) - pmax * (-zmax / sig));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
 template <int EV, bool ROWARR>
@@ -489,7 +545,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H, Dc = E + Na;
-  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, ROWARR);
+  const bool premat = p.premat != 0;
+  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, ROWARR, premat);
+  double* s_pre = sm + L.pre;
+  const int oA = 0, oQ = EV * EV, oRi = 2 * EV * EV, odS = 3 * EV * EV, oc = 4 * EV * EV, odet = oc + 1, odmu = oc + 2,
+            oda = odmu + EV;
   double* s_rec = sm + L.rec; double* s_gam = sm + L.gam; double* s_rho = sm + L.rho; double* s_xi = sm + L.xi;
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
@@ -535,6 +595,22 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           s_sbar[i * E + k] = wmu * p.c_WT[k * E + i] + wv * (4.0 * v + 4.0 * We[i] * We[k]);
         }
     }
+    if (premat) {
+      for (int tt = tid; tt < H; tt += NT) {   // step t = tt + 1 of the sweep uses the state at index tt
+        double* pr = s_pre + (size_t)tt * L.prelen;
+        double A[EV * EV], Q[EV * EV], Ri[EV * EV], c, detR, dmu[EV], da[GPMPC_MAX_D], dS[EV * EV];
+        uni_step_matrices<EV>(vars + (size_t)tt * E * E, il2, s2, A, Q, Ri, c, detR);
+        for (int e = 0; e < EV; e++) dmu[e] = 0.0;
+        for (int k = 0; k < Na; k++) da[k] = 0.0;
+        for (int e = 0; e < EV * EV; e++) dS[e] = 0.0;
+        uni_stage_adjoint<EV>(p, Na, wmu, -p.kappa * wmu * 0.5 / sqrt(rvs[tt]), mus + (size_t)tt * E,
+                              vars + (size_t)tt * E * E, ams + (size_t)tt * Na, dmu, da, dS);
+        for (int e = 0; e < EV * EV; e++) { pr[oA + e] = A[e]; pr[oQ + e] = Q[e]; pr[oRi + e] = Ri[e]; pr[odS + e] = dS[e]; }
+        pr[oc] = c; pr[odet] = detR;
+        for (int e = 0; e < EV; e++) pr[odmu + e] = dmu[e];
+        for (int k = 0; k < Na; k++) pr[oda + k] = da[k];
+      }
+    }
     __syncthreads();
     for (int t = H; t >= 1; t--) {
       const double* rec = p.records + ((size_t)cand * H + (t - 1)) * RL.size;
@@ -551,13 +627,14 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       }
       if (tid == 0) {
         s_int[0] = 0;
-        double Ca[EV * EV], Ai[EV * EV], det, pl = 1.0, Wd[EV], Rinv[EV * EV], Qm[EV * EV], detR;
-        for (int e = 0; e < EV; e++)
-          for (int f = 0; f < EV; f++) Ca[e * EV + f] = sp[e * EV + f] + (e == f ? 1.0 / il2[e] : 0.0);
-        spd_inv_det<EV>(Ca, Ai, det);
-        for (int e = 0; e < EV; e++) { pl *= il2[e]; Wd[e] = 2.0 * il2[e]; }
-        const double c = s2 / sqrt(det * pl);
-        pair_matrices<EV>(sp, Wd, Rinv, Qm, detR);
+        double Ai[EV * EV], Rinv[EV * EV], Qm[EV * EV], c, detR;
+        if (premat) {
+          const double* pr = s_pre + (size_t)(t - 1) * L.prelen;
+          for (int e = 0; e < EV * EV; e++) { Ai[e] = pr[oA + e]; Qm[e] = pr[oQ + e]; Rinv[e] = pr[oRi + e]; }
+          c = pr[oc]; detR = pr[odet];
+        } else {
+          uni_step_matrices<EV>(sp, il2, s2, Ai, Qm, Rinv, c, detR);
+        }
         for (int e = 0; e < EV * EV; e++) { s_A[e] = Ai[e]; s_Q[e] = Qm[e]; s_Rinv[e] = Rinv[e]; }
         const double rs = 1.0 / sqrt(detR);
         const double* Mrec = rec + RL.offM;
@@ -807,38 +884,13 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
                              0.5 * (X[i * E + k] + X[k * E + i]);
         for (int e = 0; e < E; e++) nmu[e] = s_mubar[e] + m_bar[e];
         for (int k = 0; k < Na; k++) a_bar[k] = m_bar[E + k];
-        {  // stage cost at t-1
-          const double wv = -p.kappa * wmu * 0.5 / sqrt(rvs[t - 1]);
-          double e[GPMPC_MAX_D], We[GPMPC_MAX_D], sWe[EV];
-          for (int d = 0; d < Dc; d++) e[d] = (d < E ? mup[d] : am[d - E]) - p.c_target[d];
-          for (int d = 0; d < Dc; d++) { double v = 0.0; for (int k = 0; k < Dc; k++) v += p.c_W[d * Dc + k] * e[k]; We[d] = v; }
-          for (int i = 0; i < E; i++) { double v = 0.0; for (int k = 0; k < E; k++) v += sp[i * E + k] * We[k]; sWe[i] = v; }
-          for (int d = 0; d < Dc; d++) {
-            double v = 0.0;
-            for (int i = 0; i < E; i++) v += p.c_W[i * Dc + d] * sWe[i];
-            const double gd = wmu * 2.0 * We[d] + wv * 8.0 * v;
-            if (d < E) nmu[d] += gd; else a_bar[d - E] += gd;
-          }
-          for (int i = 0; i < E; i++)
-            for (int k = 0; k < E; k++) { double v = 0.0; for (int l = 0; l < E; l++) v += p.c_W[l * Dc + i] * sp[k * E + l]; t1[i * E + k] = v; }
-          for (int i = 0; i < E; i++)
-            for (int k = 0; k < E; k++) {
-              double v = 0.0;
-              for (int l = 0; l < E; l++) v += t1[i * E + l] * p.c_W[k * Dc + l];
-              const double full_ik = wmu * p.c_W[k * Dc + i] + wv * (4.0 * v + 4.0 * We[i] * We[k]);
-              nsb[i * E + k] += 0.5 * full_ik;
-              nsb[k * E + i] += 0.5 * full_ik;
-            }
-          if (p.use_constraints) {
-            const double rt2 = 1.4142135623730951, ispi = 0.5641895835477563;
-            for (int d = 0; d < E; d++) {
-              double sig = sp[d * E + d];
-              double zmin = (p.c_smin[d] - mup[d]) / (sig * rt2), zmax = (p.c_smax[d] - mup[d]) / (sig * rt2);
-              double pmin = exp(-zmin * zmin) * ispi, pmax = exp(-zmax * zmax) * ispi;
-              nmu[d] += wmu * (pmin - pmax) * (-1.0 / (sig * rt2));
-              nsb[d * E + d] += wmu * (pmin * (-zmin / sig) - pmax * (-zmax / sig));
-            }
-          }
+        if (premat) {   // stage-cost adjoint at t-1, precomputed
+          const double* pr = s_pre + (size_t)(t - 1) * L.prelen;
+          for (int e = 0; e < E; e++) nmu[e] += pr[odmu + e];
+          for (int k = 0; k < Na; k++) a_bar[k] += pr[oda + k];
+          for (int e = 0; e < E * E; e++) nsb[e] += pr[odS + e];
+        } else {
+          uni_stage_adjoint<EV>(p, Na, wmu, -p.kappa * wmu * 0.5 / sqrt(rvs[t - 1]), mup, sp, am, nmu, a_bar, nsb);
         }
         for (int k = 0; k < Na; k++) gout[(size_t)(t - 1) * Na + k] = a_bar[k];
         for (int e = 0; e < E; e++) s_mubar[e] = nmu[e];

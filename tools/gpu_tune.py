@@ -17,7 +17,7 @@ for g in (False, True):
     print("grad=%d fwd %.2f bwd %.2f ms -> %.0f preds/s" % (g, f, b, cfg["B"] * cfg["H"] / (f + b) * 1e3), end=" | ")
 print()
 '''
-grid = [{}, {"GPMPC_UNI_FWD_THREADS": 256, "GPMPC_UNI_FWD_CTAS": 2, "GPMPC_UNI_SEG": 256}]
+grid = [{}, {"GPMPC_UNI_PREMAT": 0}]
 for cfg in grid:
     env = dict(os.environ)
     env.update({k: str(v) for k, v in cfg.items()})
