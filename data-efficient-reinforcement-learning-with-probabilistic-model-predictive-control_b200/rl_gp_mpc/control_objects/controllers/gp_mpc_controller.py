@@ -44,7 +44,7 @@ class GpMpcController(BaseControllerObject):
                              include_time_model=self.transition_model.config.include_time_model,
                              step_model=config.controller.num_repeat_actions)
         self.actions_mpc_previous_iter = None
-        self.clamp_lcb_class = Clamp()
+        self.clamp_lcb_class = Clamp
         self.iter_ctrl = 0
         self.num_cores_main = multiprocessing.cpu_count()
         self.ctx = multiprocessing.get_context("spawn")

@@ -1,13 +1,21 @@
-"""Straight-through clamp and normal CDF with the reference's semantics
-(control_objects/utils/pytorch_utils.py:4-17).  Host-side helpers only: inside the fused CUDA rollout
-the same two rules are applied in the forward and reverse kernels."""
+"""Two small numerical helpers with the reference's semantics (control_objects/utils/pytorch_utils.py:4-17).
+
+Host-side only: inside the fused CUDA rollout the same two rules are applied by the forward and reverse kernels."""
 import math
 
 import torch
 
+_SQRT2 = math.sqrt(2.0)
+
+
+def normal_cdf(x, mu, sigma):
+    """Phi((x - mu) / sigma) written with erf, as the reference does."""
+    return 0.5 * (1.0 + torch.erf((x - mu) / (sigma * _SQRT2)))
+
 
 class Clamp(torch.autograd.Function):
-    """clamp in the forward pass, identity in the backward pass (gradient flows at the bounds)."""
+    """Straight-through clamp: the value is clamped, the gradient passes unchanged, so that an optimiser variable
+    sitting on a bound can still move (torch.clamp would zero its gradient)."""
 
     @staticmethod
     def forward(ctx, input, min, max):
@@ -16,8 +24,3 @@ class Clamp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         return grad_output.clone(), None, None
-
-
-def normal_cdf(x, mu, sigma):
-    z = (x - mu) / (sigma * math.sqrt(2.0))
-    return 0.5 * (1.0 + torch.erf(z))
