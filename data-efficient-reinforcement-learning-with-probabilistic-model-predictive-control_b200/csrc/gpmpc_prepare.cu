@@ -5,7 +5,7 @@
 // Layout: every N x N matrix lives in an NP x NP buffer (NP = N rounded up to 64, zero padded) so
 // that the rollout kernel needs no bounds checks; iK is stored symmetrised.
 //
-// One CTA per GP.  At the reference's sizes (N <= ~1500, gp_memory.py points_batch_memory) the
+// Multi-CTA blocked algorithms (all E matrices in the same launches); float64 throughout.  At the reference
 // factorisation is ~1 % of a control step, so the design goal here is
 // float64 correctness; the N^2 rollout loop is where the time goes.
 #include "gpmpc_common.cuh"
@@ -34,170 +34,218 @@ __global__ void gram_kernel(const double* __restrict__ x, const double* __restri
   K[((size_t)a * NP + i) * NP + j] = v;
 }
 
-// ------------------------------------------------------------------ blocked Cholesky, in place
-// Lower factor written into the lower triangle of A (ld = NP); one CTA (1024 threads) per GP.
+// ------------------------------------------------------------------ blocked right-looking Cholesky, in place
+// Lower factor written into the lower triangle of A (ld = NP).  Per 32-column panel: (1) factor the diagonal block
+// (one warp per GP), (2) panel solve, one thread per row below, (3) trailing symmetric update in 64 x 64 tiles spread
+// over the whole GPU (this is ~all of the N^3/3 flops).  All E matrices are processed by the same launches.
 constexpr int CH_NB = 32;
-constexpr int CH_T = 128;  // trailing-update macro tile
 
-__global__ void __launch_bounds__(1024, 1)
-cholesky_kernel(double* __restrict__ Aall, int N, int NP, int* __restrict__ info) {
+__global__ void __launch_bounds__(32) chol_diag_kernel(double* __restrict__ Aall, int k0, int N, int NP,
+                                                       int* __restrict__ info) {
   double* A = Aall + (size_t)blockIdx.x * NP * NP;
   __shared__ double Ld[CH_NB][CH_NB + 1];
-  extern __shared__ double dyn[];  // two CH_T x CH_NB panels
-  double* PI = dyn;
-  double* PJ = dyn + CH_T * (CH_NB + 1);
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int k0 = 0; k0 < N; k0 += CH_NB) {
-    const int kb = min(CH_NB, N - k0);
-    // (a) diagonal block -> smem, factor with one warp (lane = row)
-    for (int e = tid; e < CH_NB * CH_NB; e += blockDim.x) {
-      int r = e / CH_NB, c = e % CH_NB;
-      Ld[r][c] = (r < kb && c < kb) ? A[(size_t)(k0 + r) * NP + k0 + c] : (r == c ? 1.0 : 0.0);
+  const int lane = threadIdx.x;
+  const int kb = min(CH_NB, N - k0);
+  for (int c = 0; c < CH_NB; c++)
+    Ld[lane][c] = (lane < kb && c < kb) ? A[(size_t)(k0 + lane) * NP + k0 + c] : (lane == c ? 1.0 : 0.0);
+  __syncwarp();
+  for (int c = 0; c < kb; c++) {
+    const double piv = Ld[c][c];
+    if (!(piv > 0.0) && lane == 0) atomicExch(info + blockIdx.x, k0 + c + 1);
+    const double d = sqrt(piv);
+    __syncwarp();
+    if (lane == c) Ld[c][c] = d;
+    if (lane > c && lane < kb) Ld[lane][c] /= d;
+    __syncwarp();
+    if (lane > c && lane < kb) {
+      const double lrc = Ld[lane][c];
+      for (int c2 = c + 1; c2 <= lane; c2++) Ld[lane][c2] -= lrc * Ld[c2][c];
     }
-    __syncthreads();
-    if (warp == 0) {
-      for (int c = 0; c < kb; c++) {
-        double piv = Ld[c][c];
-        if (!(piv > 0.0) && lane == 0) atomicExch(info + blockIdx.x, k0 + c + 1);
-        double d = sqrt(piv);
-        __syncwarp();
-        if (lane == c) Ld[c][c] = d;
-        if (lane > c && lane < kb) Ld[lane][c] /= d;
-        __syncwarp();
-        // rank-1 update of the remaining columns: lane = row r, loop over columns c2 in (c, r]
-        if (lane > c && lane < kb) {
-          double lrc = Ld[lane][c];
-          for (int c2 = c + 1; c2 <= lane; c2++) Ld[lane][c2] -= lrc * Ld[c2][c];
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int e = tid; e < kb * kb; e += blockDim.x) {
-      int r = e / kb, c = e % kb;
-      if (c <= r) A[(size_t)(k0 + r) * NP + k0 + c] = Ld[r][c];
-    }
-    // (b) panel: rows below the block, one thread per row: solve x Ld^T = a
-    const int r0 = k0 + kb;
-    for (int r = r0 + tid; r < N; r += blockDim.x) {
-      double xr[CH_NB];
-      double* row = A + (size_t)r * NP + k0;
-#pragma unroll
-      for (int c = 0; c < CH_NB; c++) xr[c] = (c < kb) ? row[c] : 0.0;
-#pragma unroll
-      for (int c = 0; c < CH_NB; c++) {
-        if (c < kb) {
-          double v = xr[c];
-#pragma unroll
-          for (int c2 = 0; c2 < c; c2++) v -= xr[c2] * Ld[c][c2];
-          xr[c] = v / Ld[c][c];
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < CH_NB; c++)
-        if (c < kb) row[c] = xr[c];
-    }
-    __syncthreads();
-    // (c) trailing update A[i][j] -= sum_c P[i][c] P[j][c], i >= j >= r0, in CH_T x CH_T macro tiles
-    const int nrem = N - r0;
-    if (nrem <= 0) break;
-    const int nt = (nrem + CH_T - 1) / CH_T;
-    for (int ti = 0; ti < nt; ti++) {
-      for (int tj = 0; tj <= ti; tj++) {
-        __syncthreads();
-        for (int e = tid; e < CH_T * CH_NB; e += blockDim.x) {
-          int r = e / CH_NB, c = e % CH_NB;
-          int gi = r0 + ti * CH_T + r, gj = r0 + tj * CH_T + r;
-          PI[r * (CH_NB + 1) + c] = (gi < N && c < kb) ? A[(size_t)gi * NP + k0 + c] : 0.0;
-          PJ[r * (CH_NB + 1) + c] = (gj < N && c < kb) ? A[(size_t)gj * NP + k0 + c] : 0.0;
-        }
-        __syncthreads();
-        // 1024 threads -> 32 x 32 grid of 4 x 4 register tiles
-        const int ty = tid >> 5, tx = tid & 31;
-        double acc[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-        for (int c = 0; c < CH_NB; c++) {
-          double pi[4], pj[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) pi[u] = PI[(ty + 32 * u) * (CH_NB + 1) + c];
-#pragma unroll
-          for (int v = 0; v < 4; v++) pj[v] = PJ[(tx + 32 * v) * (CH_NB + 1) + c];
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int v = 0; v < 4; v++) acc[u][v] = fma(pi[u], pj[v], acc[u][v]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int v = 0; v < 4; v++) {
-            int gi = r0 + ti * CH_T + ty + 32 * u, gj = r0 + tj * CH_T + tx + 32 * v;
-            if (gi < N && gj <= gi) A[(size_t)gi * NP + gj] -= acc[u][v];
-          }
-      }
-    }
-    __syncthreads();
+    __syncwarp();
   }
+  if (lane < kb)
+    for (int c = 0; c <= lane; c++) A[(size_t)(k0 + lane) * NP + k0 + c] = Ld[lane][c];
 }
 
-// ------------------------------------------------------------------ solves: iK = (L L^T)^-1, beta
-// One thread per right-hand-side column c of [ I | y_a ] (N + 1 columns).  Z (ld = NC) holds the
-// columns; forward substitution L Z = RHS then backward L^T X = Z, rows of L broadcast from smem.
-__global__ void __launch_bounds__(1024, 1)
-chol_solve_kernel(const double* __restrict__ Lall, const double* __restrict__ y, double* __restrict__ Zall,
-                  int N, int NP, int E) {
-  const int a = blockIdx.x;
+__global__ void __launch_bounds__(128) chol_trsm_kernel(double* __restrict__ Aall, int k0, int N, int NP) {
+  double* A = Aall + (size_t)blockIdx.y * NP * NP;
+  __shared__ double Ld[CH_NB][CH_NB + 1];
+  const int kb = min(CH_NB, N - k0);
+  for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
+    const int r = e / CH_NB, c = e % CH_NB;
+    Ld[r][c] = (r < kb && c <= r) ? A[(size_t)(k0 + r) * NP + k0 + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const int r = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  double xr[CH_NB];
+  double* row = A + (size_t)r * NP + k0;
+#pragma unroll
+  for (int c = 0; c < CH_NB; c++) xr[c] = (c < kb) ? row[c] : 0.0;
+#pragma unroll
+  for (int c = 0; c < CH_NB; c++) {
+    double v = xr[c];
+#pragma unroll
+    for (int c2 = 0; c2 < c; c2++) v -= xr[c2] * Ld[c][c2];
+    xr[c] = v / Ld[c][c];
+  }
+#pragma unroll
+  for (int c = 0; c < CH_NB; c++)
+    if (c < kb) row[c] = xr[c];
+}
+
+// A[i][j] -= sum_c P[i][c] P[j][c] for i >= j >= r0, P = panel columns [k0, k0+kb); one 64 x 64 tile per CTA
+__global__ void __launch_bounds__(256) chol_syrk_kernel(double* __restrict__ Aall, int k0, int N, int NP) {
+  double* A = Aall + (size_t)blockIdx.y * NP * NP;
+  __shared__ double PI[64][CH_NB + 1], PJ[64][CH_NB + 1];
+  const int kb = min(CH_NB, N - k0), r0 = k0 + kb;
+  int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ti++;
+  while (ti * (ti + 1) / 2 > (int)blockIdx.x) ti--;
+  const int tj = blockIdx.x - ti * (ti + 1) / 2;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * CH_NB; e += blockDim.x) {
+    const int r = e / CH_NB, c = e % CH_NB;
+    const int gi = r0 + ti * 64 + r, gj = r0 + tj * 64 + r;
+    PI[r][c] = (gi < N && c < kb) ? A[(size_t)gi * NP + k0 + c] : 0.0;
+    PJ[r][c] = (gj < N && c < kb) ? A[(size_t)gj * NP + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  double acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+  for (int c = 0; c < CH_NB; c++) {
+    double pi[4], pj[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) pi[u] = PI[ty + 16 * u][c];
+#pragma unroll
+    for (int v = 0; v < 4; v++) pj[v] = PJ[tx + 16 * v][c];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int v = 0; v < 4; v++) acc[u][v] = fma(pi[u], pj[v], acc[u][v]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int gi = r0 + ti * 64 + ty + 16 * u, gj = r0 + tj * 64 + tx + 16 * v;
+      if (gi < N && gj <= gi) A[(size_t)gi * NP + gj] -= acc[u][v];
+    }
+}
+
+// ------------------------------------------------------------------ iK = (L L^T)^-1 and beta = iK y
+// One CTA per block of 32 right-hand-side columns of [ I | y_a ]: forward substitution L Y = RHS then backward
+// L^T X = Y, block row by block row (32 x 32 tile products through shared memory + a 32-step triangular solve by one
+// warp).  Identity columns are zero above their diagonal block, so the forward sweep starts there.  Z (ld = NC) holds
+// the columns; X overwrites Y in place.
+__global__ void __launch_bounds__(256) chol_inverse_kernel(const double* __restrict__ Lall, const double* __restrict__ y,
+                                                           double* __restrict__ Zall, int N, int NP, int E) {
+  const int a = blockIdx.y, cb = blockIdx.x;
   const double* L = Lall + (size_t)a * NP * NP;
   const int NC = NP + 64;
   double* Z = Zall + (size_t)a * NP * NC;
-  extern __shared__ double rowbuf[];  // NP doubles
-  const int tid = threadIdx.x;
-  // init RHS
-  for (int c = tid; c <= N; c += blockDim.x)
-    for (int r = 0; r < N; r++) Z[(size_t)r * NC + c] = (c < N) ? (r == c ? 1.0 : 0.0) : y[r * E + a];
-  __syncthreads();
-  // forward: for r: z[r] = (rhs[r] - sum_{k<r} L[r][k] z[k]) / L[r][r]
-  for (int r = 0; r < N; r++) {
-    for (int k = tid; k <= r; k += blockDim.x) rowbuf[k] = L[(size_t)r * NP + k];
-    __syncthreads();
-    for (int c = tid; c <= N; c += blockDim.x) {
-      int kstart = (c < N) ? c : 0;  // identity columns are zero above their diagonal
-      if (kstart <= r) {
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        int k = kstart;
-        for (; k + 3 < r; k += 4) {
-          v0 = fma(rowbuf[k], Z[(size_t)k * NC + c], v0);
-          v1 = fma(rowbuf[k + 1], Z[(size_t)(k + 1) * NC + c], v1);
-          v2 = fma(rowbuf[k + 2], Z[(size_t)(k + 2) * NC + c], v2);
-          v3 = fma(rowbuf[k + 3], Z[(size_t)(k + 3) * NC + c], v3);
-        }
-        for (; k < r; k++) v0 = fma(rowbuf[k], Z[(size_t)k * NC + c], v0);
-        double v = (v0 + v1) + (v2 + v3);
-        Z[(size_t)r * NC + c] = (Z[(size_t)r * NC + c] - v) / rowbuf[r];
+  __shared__ double Lt[32][33], Yt[32][33], Acc[32][33];
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;   // rows ty, ty+8, ty+16, ty+24 ; column tx
+  const int c0 = 32 * cb, c = c0 + tx;
+  const int nrb = (N + 31) / 32;
+  const int rb0 = (c0 + 31 < N) ? cb : 0;                        // the block holding the y column starts at the top
+  // ---- forward
+  for (int rb = rb0; rb < nrb; rb++) {
+    const int r0 = 32 * rb;
+    double acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = r0 + ty + 8 * u;
+      acc[u] = (r < N) ? ((c < N) ? (r == c ? 1.0 : 0.0) : (c == N ? y[(size_t)r * E + a] : 0.0)) : 0.0;
+    }
+    for (int kb = rb0; kb < rb; kb++) {
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int rr = ty + 8 * u;
+        Lt[rr][tx] = (r0 + rr < N) ? L[(size_t)(r0 + rr) * NP + 32 * kb + tx] : 0.0;
+        Yt[rr][tx] = Z[(size_t)(32 * kb + rr) * NC + c];
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 32; k++) {
+        const double yv = Yt[k][tx];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] = fma(-Lt[ty + 8 * u][k], yv, acc[u]);
       }
     }
     __syncthreads();
-  }
-  // backward: L^T X = Z : x[r] = (z[r] - sum_{k>r} L[k][r] x[k]) / L[r][r]
-  for (int r = N - 1; r >= 0; r--) {
-    for (int k = r + tid; k < N; k += blockDim.x) rowbuf[k] = L[(size_t)k * NP + r];  // column r of L
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int rr = ty + 8 * u;
+      Acc[rr][tx] = acc[u];
+      Lt[rr][tx] = (r0 + rr < N && tx <= rr) ? L[(size_t)(r0 + rr) * NP + r0 + tx] : (rr == tx ? 1.0 : 0.0);
+    }
     __syncthreads();
-    for (int c = tid; c <= N; c += blockDim.x) {
-      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-      int k = r + 1;
-      for (; k + 3 < N; k += 4) {
-        v0 = fma(rowbuf[k], Z[(size_t)k * NC + c], v0);
-        v1 = fma(rowbuf[k + 1], Z[(size_t)(k + 1) * NC + c], v1);
-        v2 = fma(rowbuf[k + 2], Z[(size_t)(k + 2) * NC + c], v2);
-        v3 = fma(rowbuf[k + 3], Z[(size_t)(k + 3) * NC + c], v3);
+    if (ty == 0) {   // one warp: column tx, 32 sequential rows
+      double yv[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        double v = Acc[i][tx];
+#pragma unroll
+        for (int k = 0; k < i; k++) v = fma(-Lt[i][k], yv[k], v);
+        yv[i] = v / Lt[i][i];
       }
-      for (; k < N; k++) v0 = fma(rowbuf[k], Z[(size_t)k * NC + c], v0);
-      double v = (v0 + v1) + (v2 + v3);
-      Z[(size_t)r * NC + c] = (Z[(size_t)r * NC + c] - v) / rowbuf[r];
+#pragma unroll
+      for (int i = 0; i < 32; i++) Z[(size_t)(r0 + i) * NC + c] = (r0 + i < N) ? yv[i] : 0.0;
+    }
+    __syncthreads();
+  }
+  // rows above the first processed block of an identity column block are zero
+  for (int rb = 0; rb < rb0; rb++)
+#pragma unroll
+    for (int u = 0; u < 4; u++) Z[(size_t)(32 * rb + ty + 8 * u) * NC + c] = 0.0;
+  __syncthreads();
+  // ---- backward: X[rb] = Lrr^-T (Y[rb] - sum_{kb > rb} L[kb, rb]^T X[kb])
+  for (int rb = nrb - 1; rb >= 0; rb--) {
+    const int r0 = 32 * rb;
+    double acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[u] = Z[(size_t)(r0 + ty + 8 * u) * NC + c];
+    for (int kb = rb + 1; kb < nrb; kb++) {
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int rr = ty + 8 * u;    // Lt[k][i] = L[32 kb + k][r0 + i]
+        Lt[rr][tx] = (32 * kb + rr < N) ? L[(size_t)(32 * kb + rr) * NP + r0 + tx] : 0.0;
+        Yt[rr][tx] = Z[(size_t)(32 * kb + rr) * NC + c];
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 32; k++) {
+        const double xv = Yt[k][tx];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] = fma(-Lt[k][ty + 8 * u], xv, acc[u]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int rr = ty + 8 * u;
+      Acc[rr][tx] = acc[u];
+      Lt[rr][tx] = (r0 + rr < N && tx <= rr) ? L[(size_t)(r0 + rr) * NP + r0 + tx] : (rr == tx ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (ty == 0) {
+      double xv[32];
+#pragma unroll
+      for (int i = 31; i >= 0; i--) {
+        double v = Acc[i][tx];
+#pragma unroll
+        for (int k = i + 1; k < 32; k++) v = fma(-Lt[k][i], xv[k], v);
+        xv[i] = v / Lt[i][i];
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i++) Z[(size_t)(r0 + i) * NC + c] = (r0 + i < N) ? xv[i] : 0.0;
     }
     __syncthreads();
   }
@@ -229,13 +277,21 @@ cudaError_t launch_prepare(const double* x, const double* y, const double* ls, c
   dim3 grd((NP + 31) / 32, (NP + 7) / 8, E);
   cudaMemsetAsync(info, 0, sizeof(int) * E, st);
   gram_kernel<<<grd, blk, 0, st>>>(x, ls, s2, noise, Kbuf, N, NP, D);
-  size_t sm1 = 2 * CH_T * (CH_NB + 1) * sizeof(double);
-  cudaFuncSetAttribute(cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-  cholesky_kernel<<<E, 1024, sm1, st>>>(Kbuf, N, NP, info);
-  size_t sm2 = NP * sizeof(double);
-  chol_solve_kernel<<<E, 1024, sm2, st>>>(Kbuf, y, Zbuf, N, NP, E);
+  long long n = 1;
+  for (int k0 = 0; k0 < N; k0 += CH_NB) {
+    chol_diag_kernel<<<E, 32, 0, st>>>(Kbuf, k0, N, NP, info);
+    n++;
+    const int rem = N - k0 - CH_NB;
+    if (rem > 0) {
+      chol_trsm_kernel<<<dim3((rem + 127) / 128, E), 128, 0, st>>>(Kbuf, k0, N, NP);
+      const int nt = (rem + 63) / 64;
+      chol_syrk_kernel<<<dim3(nt * (nt + 1) / 2, E), 256, 0, st>>>(Kbuf, k0, N, NP);
+      n += 2;
+    }
+  }
+  chol_inverse_kernel<<<dim3(N / 32 + 1, E), 256, 0, st>>>(Kbuf, y, Zbuf, N, NP, E);
   finalize_kernel<<<grd, blk, 0, st>>>(Zbuf, iK, beta, betaT, N, NP, E);
-  *launches += 4;
+  *launches += n + 2;
   return cudaGetLastError();
 }
 
