@@ -422,6 +422,17 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
   return GPMPC_OK;
 }
 
+int gpmpc_mll(gpmpc_handle* h, const double* y, double* out, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!h->prepared) return fail(h, GPMPC_ERR_NOT_PREPARED, "mll: call gpmpc_prepare first (same x, y, hyper-parameters)");
+  if (!y || !out) return fail(h, GPMPC_ERR_BAD_ARG, "mll: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  CU(launch_mll(h->x.as<double>(), y, h->ls.as<double>(), h->s2.as<double>(), h->Kbuf.as<double>(), h->iK.as<double>(),
+                h->beta.as<double>(), out, h->N, h->NP, h->D, h->E, 3 + h->D, st, &h->launches));
+  return GPMPC_OK;
+}
+
 int gpmpc_set_path(gpmpc_handle* h, int mode) {
   if (!h || mode < 0 || mode > 1) return GPMPC_ERR_BAD_ARG;
   h->path_mode = mode;

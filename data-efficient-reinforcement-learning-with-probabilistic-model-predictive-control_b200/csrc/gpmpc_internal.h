@@ -62,6 +62,9 @@ cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* gra
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
                            double* iK, double* beta, double* betaT, int* info, cudaStream_t st, long long* launches);
+cudaError_t launch_mll(const double* x, const double* y, const double* ls, const double* s2, const double* Lbuf,
+                       const double* iK, const double* beta, double* out, int N, int NP, int D, int E, int stride,
+                       cudaStream_t st, long long* launches);
 cudaError_t launch_il2(const double* ls, double* il2, int n, cudaStream_t st);
 
 constexpr int ROLLOUT_THREADS = 512;

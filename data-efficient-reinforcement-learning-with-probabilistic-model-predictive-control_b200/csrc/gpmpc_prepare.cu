@@ -270,6 +270,75 @@ __global__ void finalize_kernel(const double* __restrict__ Zall, double* __restr
   }
 }
 
+// ------------------------------------------------------------------ exact-GP log marginal likelihood + gradient
+// (reference: gpytorch ExactMarginalLogLikelihood inside GpStateTransitionModel.train, gp_model.py:193-306)
+//   LML_a = -1/2 y^T alpha - sum_i log L_ii - N/2 log(2 pi),   alpha = K^-1 y,
+//   dLML/dtheta = 1/2 sum_ij (alpha_i alpha_j - iK_ij) dK_ij/dtheta      for theta in {lengthscale_d, s2, noise}.
+// out[a] = { LML, dLML/ds2, dLML/dnoise, dLML/dl_0 .. dLML/dl_{D-1} }  (MLL_STRIDE doubles per GP, zeroed first)
+__global__ void mll_logdet_kernel(const double* __restrict__ Lall, const double* __restrict__ beta,
+                                  const double* __restrict__ y, double* __restrict__ out, int N, int NP, int E, int stride) {
+  const int a = blockIdx.x;
+  const double* L = Lall + (size_t)a * NP * NP;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    acc += -0.5 * y[(size_t)i * E + a] * beta[(size_t)a * NP + i] - log(L[(size_t)i * NP + i]);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out + (size_t)a * stride, acc);
+  if (threadIdx.x == 0) atomicAdd(out + (size_t)a * stride, -0.5 * N * 1.8378770664093453);   // log(2 pi)
+}
+
+__global__ void __launch_bounds__(256) mll_grad_kernel(const double* __restrict__ x, const double* __restrict__ ls,
+                                                       const double* __restrict__ s2, const double* __restrict__ iK,
+                                                       const double* __restrict__ beta, double* __restrict__ out,
+                                                       int N, int NP, int D, int stride) {
+  const int a = blockIdx.z;
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+  double g[2 + GPMPC_MAX_D];
+#pragma unroll
+  for (int q = 0; q < 2 + GPMPC_MAX_D; q++) g[q] = 0.0;
+  if (j < N) {
+    const double bj = beta[(size_t)a * NP + j];
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u;
+      if (i >= N) break;
+      const double w = 0.5 * (beta[(size_t)a * NP + i] * bj - iK[((size_t)a * NP + i) * NP + j]);
+      double d2 = 0.0, dd[GPMPC_MAX_D];
+#pragma unroll
+      for (int d = 0; d < GPMPC_MAX_D; d++) {
+        dd[d] = 0.0;
+        if (d < D) {
+          const double l = ls[a * D + d], t = (x[(size_t)i * D + d] - x[(size_t)j * D + d]) / l;
+          d2 = fma(t, t, d2);
+          dd[d] = t * t / l;               // (x_i - x_j)^2 / l^3 * l^0 ... times k below
+        }
+      }
+      const double k = exp(-0.5 * d2);     // dK/ds2
+      g[0] = fma(w, k, g[0]);
+      if (i == j) g[1] += w;               // dK/dnoise = I
+      const double wk = w * s2[a] * k;
+#pragma unroll
+      for (int d = 0; d < GPMPC_MAX_D; d++)
+        if (d < D) g[2 + d] = fma(wk, dd[d], g[2 + d]);
+    }
+  }
+  for (int q = 0; q < 2 + D; q++) {
+    double v = g[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + (size_t)a * stride + 1 + q, v);
+  }
+}
+
+cudaError_t launch_mll(const double* x, const double* y, const double* ls, const double* s2, const double* Lbuf,
+                       const double* iK, const double* beta, double* out, int N, int NP, int D, int E, int stride,
+                       cudaStream_t st, long long* launches) {
+  cudaMemsetAsync(out, 0, sizeof(double) * E * stride, st);
+  mll_logdet_kernel<<<E, 256, 0, st>>>(Lbuf, beta, y, out, N, NP, E, stride);
+  mll_grad_kernel<<<dim3((N + 31) / 32, (N + 31) / 32, E), 256, 0, st>>>(x, ls, s2, iK, beta, out, N, NP, D, stride);
+  *launches += 2;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
                            double* iK, double* beta, double* betaT, int* info, cudaStream_t st, long long* launches) {

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "gpmpc_predict_step": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 4),
     "gpmpc_rollout": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
                       + [ctypes.c_void_p] * 7 + [ctypes.c_void_p]),
+    "gpmpc_mll": (ctypes.c_int, [ctypes.c_void_p] * 4),
     "gpmpc_set_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gpmpc_uses_uniform_path": (ctypes.c_int, [ctypes.c_void_p]),
     "gpmpc_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -199,6 +200,15 @@ class Engine:
                                                 _ptr(grad), _ptr(smu), _ptr(svar), _ptr(rew), _ptr(rewv), _ptr(am),
                                                 self._stream()))
         return o
+
+    def mll(self, y):
+        """Log marginal likelihood and gradient of the GPs of the last prepare(); returns a (E, 3+D) CUDA tensor
+        { LML, dLML/d outputscale, dLML/d noise, dLML/d lengthscale[0..D) }."""
+        y = _f64(y, self.device, (self.N, self.E))
+        out = torch.empty((self.E, 3 + self.D), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.gpmpc_mll(self._h, _ptr(y), _ptr(out), self._stream()))
+        return out
 
     def set_path(self, mode):
         """0: automatic (uniform-kernel fast path when all GPs share their hyper-parameters), 1: general path."""

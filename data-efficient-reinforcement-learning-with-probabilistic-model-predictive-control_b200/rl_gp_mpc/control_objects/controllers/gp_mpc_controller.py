@@ -6,6 +6,7 @@ its objective evaluated by the B200 CUDA engine.
   get_action / _get_optimal_actions  gp_mpc_controller.py:52-153  same orchestration (scipy L-BFGS-B, restarts)
 The five side-effect tensors (:279-283) are kept; for a batch they describe the best candidate."""
 import multiprocessing
+import threading
 
 import numpy as np
 import torch
@@ -25,6 +26,27 @@ from rl_gp_mpc.control_objects.utils.pytorch_utils import Clamp
 
 from .abstract_controller import BaseControllerObject
 from .iteration_info_class import IterationInformation
+
+
+class _TrainingThread(threading.Thread):
+    """threading.Thread with the few multiprocessing.Process members the controller logic relies on
+    (`_closed`, `close()`), so that check_and_close_processes reads like the reference's (:216-227)."""
+
+    def __init__(self, target, args):
+        super().__init__(target=self._guarded, daemon=True)
+        self._fn, self._fn_args, self._closed = target, args, False
+
+    def _guarded(self):
+        queue, saved_state = self._fn_args[0], self._fn_args[1]
+        try:
+            self._fn(*self._fn_args)
+        except Exception as exc:        # never leave the controller waiting on an empty queue
+            print("training failed:", exc)
+            saved_state.to_arrays()
+            queue.put(saved_state.parameters)
+
+    def close(self):
+        self._closed = True
 
 
 class GpMpcController(BaseControllerObject):
@@ -178,9 +200,17 @@ class GpMpcController(BaseControllerObject):
             self.start_training_process()
 
     def start_training_process(self):
-        """Reference :201-214 spawns the hyper-parameter trainer; fitting is outside the accelerated path
-        (GpStateTransitionModel.train keeps the current hyper-parameters), so nothing is spawned here."""
-        return None
+        """Launch the hyper-parameter fit without blocking the control loop (reference :201-214 spawns a process;
+        here a thread drives the device-side objective through its own engine handle).  The result is collected by
+        check_and_close_processes exactly like in the reference."""
+        saved_state = self.transition_model.save_state()
+        saved_state.to_arrays()
+        tr = self.config.training
+        self.p_train = _TrainingThread(target=self.transition_model.train,
+                                       args=(self.queue_train, saved_state, tr.lr_train, tr.iter_train,
+                                             tr.clip_grad_value, tr.print_train, tr.step_print_train,
+                                             self.transition_model._device))
+        self.p_train.start()
 
     def check_and_close_processes(self):
         if "p_train" in self.__dict__ and not self.p_train._closed and not self.p_train.is_alive():

@@ -185,11 +185,91 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
         return out["states_mu_pred"], out["states_var_pred"]
 
     @staticmethod
-    def train(queue, saved_state, lr_train, num_iter_train, clip_grad_value, print_train=False, step_print_train=25):
-        """Hyper-parameter fitting (reference gp_model.py:193-306) is outside the accelerated hot path
-        (SURVEY.md section 8(f) N2); the prior hyper-parameters are returned unchanged."""
+    def train(queue, saved_state, lr_train, num_iter_train, clip_grad_value, print_train=False, step_print_train=25,
+              device=None):
+        """Hyper-parameter fitting with the reference's procedure (gp_model.py:193-306): for every GP, uniform random
+        re-initialisation inside the Interval bounds, torch LBFGS (strong Wolfe) on the unconstrained parameters,
+        keep the best negative marginal log-likelihood (per data point, as gpytorch's ExactMarginalLogLikelihood
+        reports it) and fall back to the previous hyper-parameters when nothing better is found.  The objective and
+        its gradient come from the device (gpmpc_prepare + gpmpc_mll: Gram, Cholesky, K^-1, 1/2 tr((aa^T-K^-1) dK));
+        only the O(D) optimiser state lives on the host.  The result goes to `queue` as a list of
+        {'covar_module.base_kernel.lengthscale', 'covar_module.outputscale', 'likelihood.noise'} dicts."""
+        import time
+        t0 = time.time()
         saved_state.to_tensors()
-        queue.put([{k: np.asarray(v) for k, v in p.items()} for p in saved_state.parameters])
+        x = torch.as_tensor(saved_state.inputs, dtype=torch.float64)
+        y_all = torch.as_tensor(saved_state.states_change, dtype=torch.float64)
+        cons = saved_state.constraints_hyperparams
+        params_out = []
+        try:
+            engine = _cabi.Engine(device)
+        except Exception as exc:                       # no device / no library: keep the current hyper-parameters
+            print("training skipped:", exc)
+            queue.put([{k: np.asarray(v) for k, v in p.items()} for p in saved_state.parameters])
+            return
+        n, d = x.shape
+
+        def bounds(idx):
+            lo = torch.cat([torch.as_tensor(cons["min_lengthscale"], dtype=torch.float64)[idx].reshape(-1),
+                            torch.as_tensor(cons["min_outputscale"], dtype=torch.float64)[idx].reshape(1),
+                            torch.as_tensor(cons["min_std_noise"], dtype=torch.float64)[idx].reshape(1) ** 2])
+            hi = torch.cat([torch.as_tensor(cons["max_lengthscale"], dtype=torch.float64)[idx].reshape(-1),
+                            torch.as_tensor(cons["max_outputscale"], dtype=torch.float64)[idx].reshape(1),
+                            torch.as_tensor(cons["max_std_noise"], dtype=torch.float64)[idx].reshape(1) ** 2])
+            return lo, hi
+
+        class _NegMll(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, theta, y_col):            # theta = [lengthscale (D), outputscale, noise] constrained
+                engine.prepare(x, y_col, theta[:d].reshape(1, d), theta[d:d + 1], theta[d + 1:d + 2])
+                out = engine.mll(y_col)[0].cpu()
+                grad = torch.cat([out[3:3 + d], out[1:3]])
+                ctx.save_for_backward(-grad / n)
+                return -out[0] / n
+
+            @staticmethod
+            def backward(ctx, g):
+                return g * ctx.saved_tensors[0], None
+
+        for idx, prev in enumerate(saved_state.parameters):
+            y_col = y_all[:, idx:idx + 1].contiguous()
+            lo, hi = bounds(idx)
+            prev_theta = torch.cat([torch.as_tensor(prev["covar_module.base_kernel.lengthscale"], dtype=torch.float64).reshape(-1),
+                                    torch.as_tensor(prev["covar_module.outputscale"], dtype=torch.float64).reshape(1),
+                                    torch.as_tensor(prev["likelihood.noise"], dtype=torch.float64).reshape(1)])
+            best_theta = prev_theta.clone()
+            try:
+                best_loss = float(_NegMll.apply(prev_theta, y_col))
+            except Exception:
+                best_loss = float("inf")
+            prev_loss = best_loss
+            start = lo + torch.rand(d + 2, dtype=torch.float64) * (hi - lo)          # random restart (:229-247)
+            p0 = ((start - lo) / (hi - lo)).clamp(1e-6, 1 - 1e-6)
+            raw = (torch.log(p0) - torch.log1p(-p0)).requires_grad_(True)
+            opt = torch.optim.LBFGS([raw], lr=lr_train, line_search_fn="strong_wolfe")
+            try:
+                for it in range(num_iter_train):
+                    def closure():
+                        opt.zero_grad()
+                        theta = lo + (hi - lo) * torch.sigmoid(raw)
+                        loss = _NegMll.apply(theta, y_col)
+                        loss.backward()
+                        if print_train and it % step_print_train == 0:
+                            print("Iter %d/%d - Loss: %.5f" % (it + 1, num_iter_train, loss.item()))
+                        return loss
+                    loss = float(opt.step(closure))
+                    if loss < best_loss:
+                        best_loss = loss
+                        best_theta = (lo + (hi - lo) * torch.sigmoid(raw)).detach().clone()
+            except Exception as exc:                   # e.g. a trial point with a non positive definite kernel matrix
+                print(exc)
+            print("training - model %d - time %.2f s - loss %.5f -> %.5f - outputscale %s - lengthscales %s - noise %s" % (
+                idx, time.time() - t0, prev_loss, best_loss, best_theta[d].numpy(), best_theta[:d].numpy(),
+                best_theta[d + 1].numpy()))
+            params_out.append({"covar_module.base_kernel.lengthscale": best_theta[:d].reshape(1, d).numpy(),
+                               "covar_module.outputscale": best_theta[d].reshape(()).numpy(),
+                               "likelihood.noise": best_theta[d + 1].reshape(1).numpy()})
+        queue.put(params_out)
 
     def save_state(self):
         return SavedState(inputs=self.x_mem, states_change=self.y_mem,

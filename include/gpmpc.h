@@ -101,6 +101,14 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
                   double* cost, double* grad, double* states_mu, double* states_var,
                   double* rewards, double* rewards_var, double* actions_model, void* stream);
 
+/*
+ * Exact-GP log marginal likelihood and its gradient w.r.t. the hyper-parameters, for the E GPs factorised by the
+ * last gpmpc_prepare (same x, y, hyper-parameters) -- the objective GpStateTransitionModel.train minimises through
+ * gpytorch's ExactMarginalLogLikelihood (control_objects/models/gp_model.py:193-306).  y (N,E) as given to prepare.
+ * out (E, 3+D): { LML, dLML/d outputscale, dLML/d noise, dLML/d lengthscale[0..D) } (not divided by N).
+ */
+int gpmpc_mll(gpmpc_handle* h, const double* y, double* out, void* stream);
+
 /* Kernel-path selection.  When every GP has bitwise-identical hyper-parameters (the reference's state before
  * hyper-parameter training, examples/<env>/config_<env>.py:41-45) gpmpc_rollout uses the "uniform-kernel" path
  * (one exp per (i,j) for all output pairs).  mode 0: automatic (default); mode 1: always the general path.

@@ -1,0 +1,106 @@
+"""GPU: hyper-parameter objective on the device: exact-GP log marginal likelihood + gradient,
+and the reference-style training procedure that drives it (gp_model.py:193-306)."""
+import queue as queue_mod
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpmpc_oracle as orc
+from oracle.workloads import full_lengthscale, make_workload
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu_lml(x, y, ls, s2, noise):
+    """float64 torch reference: sum over GPs is NOT taken; returns (E,) LML and autograd gradients."""
+    x = torch.as_tensor(x); y = torch.as_tensor(y)
+    ls = torch.as_tensor(ls).clone().requires_grad_(True)
+    s2 = torch.as_tensor(s2).clone().requires_grad_(True)
+    noise = torch.as_tensor(noise).clone().requires_grad_(True)
+    K = orc.gram_matrix(x, ls, s2) + noise[:, None, None] * torch.eye(x.shape[0], dtype=torch.float64)
+    L = torch.linalg.cholesky(K)
+    alpha = torch.cholesky_solve(y.t()[:, :, None], L)[:, :, 0]
+    lml = -0.5 * (y.t() * alpha).sum(1) - torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(1) \
+        - 0.5 * x.shape[0] * np.log(2 * np.pi)
+    grads = []
+    for a in range(lml.shape[0]):
+        g = torch.autograd.grad(lml[a], (ls, s2, noise), retain_graph=True)
+        grads.append((g[0][a].numpy(), g[1][a].item(), g[2][a].item()))
+    return lml.detach().numpy(), grads
+
+
+@pytest.mark.parametrize("kw", [dict(E=2, Na=1, N=70, ls=0.5, seed=51, noise=1e-3),
+                                dict(E=3, Na=2, N=150, ls=0.4, seed=52, noise=1e-4, distinct_lengthscales=True)])
+def test_marginal_likelihood_and_gradient_match_autograd(kw):
+    from rl_gp_mpc import _cabi
+    cfg = make_workload(H=2, B=1, **kw)
+    ls = full_lengthscale(cfg)
+    eng = _cabi.Engine()
+    eng.prepare(cfg["x"], cfg["y"], ls, cfg["outputscale"], cfg["noise"])
+    out = eng.mll(cfg["y"]).cpu().numpy()
+    lml, grads = cpu_lml(cfg["x"], cfg["y"], ls, cfg["outputscale"], cfg["noise"])
+    D = cfg["D"]
+    for a in range(cfg["E"]):
+        assert abs(out[a, 0] - lml[a]) <= 1e-8 * max(1.0, abs(lml[a]))
+        scale = max(1.0, np.abs(grads[a][0]).max(), abs(grads[a][1]), abs(grads[a][2]))
+        np.testing.assert_allclose(out[a, 3:3 + D], grads[a][0], rtol=0, atol=1e-7 * scale)
+        assert abs(out[a, 1] - grads[a][1]) <= 1e-7 * scale
+        assert abs(out[a, 2] - grads[a][2]) <= 1e-7 * scale
+
+
+def test_training_procedure_improves_the_marginal_likelihood_and_feeds_the_controller():
+    from rl_gp_mpc import GpMpcController
+    from rl_gp_mpc.config_classes.controller_config import ControllerConfig
+    from rl_gp_mpc.config_classes.model_config import ModelConfig
+    from rl_gp_mpc.config_classes.observation_config import ObservationConfig
+    from rl_gp_mpc.config_classes.reward_config import RewardConfig
+    from rl_gp_mpc.config_classes.total_config import Config
+    from rl_gp_mpc.config_classes.training_config import TrainingConfig
+    from rl_gp_mpc.control_objects.models.gp_model import GpStateTransitionModel
+    cfg = make_workload(E=2, Na=1, N=80, H=4, B=1, ls=0.5, seed=53, preset="mountaincar")
+    r = cfg["reward"]
+    config = Config(
+        observation_config=ObservationConfig(obs_var_norm=[1e-6] * 2),
+        reward_config=RewardConfig(target_state_norm=list(r["target_state"]), weight_state=list(r["weight_state"]),
+                                   weight_state_terminal=list(r["weight_state_terminal"]),
+                                   target_action_norm=list(r["target_action"]), weight_action=list(r["weight_action"])),
+        controller_config=ControllerConfig(len_horizon=4),
+        training_config=TrainingConfig(lr_train=0.5, iter_train=8, training_frequency=1000),
+        model_config=ModelConfig(gp_init={"noise_covar.noise": [1e-3, 1e-3], "base_kernel.lengthscale": [2.0, 2.0],
+                                          "outputscale": [0.5, 0.5]},
+                                 min_std_noise=1e-3, max_std_noise=1e-1, min_outputscale=1e-4, max_outputscale=1.0,
+                                 min_lengthscale=5e-2, max_lengthscale=10.0))
+    ctrl = GpMpcController(-np.ones(2), np.ones(2), -np.ones(1), np.ones(1), config)
+    ctrl.memory.model_inputs[:cfg["N"]] = torch.as_tensor(cfg["x"])
+    ctrl.memory.model_targets[:cfg["N"]] = torch.as_tensor(cfg["y"])
+    ctrl.memory.len_mem_model = cfg["N"]
+    ctrl.get_action(np.zeros(2))
+    tm = ctrl.transition_model
+    assert tm.engine.uses_uniform_path()
+    # direct call of the reference-signature static method
+    torch.manual_seed(3)
+    q = queue_mod.Queue()
+    st = tm.save_state(); st.to_arrays()
+    GpStateTransitionModel.train(q, st, 0.5, 8, 1e-3)
+    new = q.get(timeout=5)
+    assert len(new) == 2 and set(new[0]) == {"covar_module.base_kernel.lengthscale", "covar_module.outputscale", "likelihood.noise"}
+    old_ls = np.full((2, 3), 2.0)
+    eng = tm.engine
+    def neg_mll(ls, s2, nz):
+        eng.prepare(cfg["x"], cfg["y"], ls, s2, nz)
+        return -eng.mll(cfg["y"])[:, 0].cpu().numpy() / cfg["N"]
+    before = neg_mll(old_ls, [0.5, 0.5], [1e-3, 1e-3])
+    after = neg_mll(np.stack([p["covar_module.base_kernel.lengthscale"][0] for p in new]),
+                    [float(p["covar_module.outputscale"]) for p in new], [float(p["likelihood.noise"][0]) for p in new])
+    assert np.all(after <= before + 1e-12) and np.any(after < before - 1e-3)
+    for p in new:
+        assert np.all(p["covar_module.base_kernel.lengthscale"] >= 5e-2) and 1e-6 <= p["likelihood.noise"][0] <= 1e-2
+    # asynchronous flow through the controller (gp_mpc_controller.py:201-227)
+    ctrl.start_training_process()
+    ctrl.p_train.join(timeout=120)
+    assert not ctrl.p_train.is_alive()
+    ctrl.check_and_close_processes()
+    assert ctrl.p_train._closed
+    act = ctrl.get_action(np.zeros(2))                       # per-GP hyper-parameters now -> general kernel path
+    assert act.shape == (1,) and np.isfinite(ctrl.last_optim_cost)
