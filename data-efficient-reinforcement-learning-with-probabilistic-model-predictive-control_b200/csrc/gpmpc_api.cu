@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #include <string>
 
@@ -39,7 +40,7 @@ struct gpmpc_handle {
   std::string err;
   bool prepared = false, cost_set = false;
   int N = 0, NP = 0, D = 0, DP = 0, E = 0, Na = 0;
-  DevBuf x, il2, s2, ls, noise, beta, betaT, iK, Kbuf, Zbuf, info;
+  DevBuf x, il2, s2, ls, noise, beta, betaT, iK, Kbuf, Zbuf, info, exp2tab;
   bool uniform = false;      // all GPs share one hyper-parameter set -> uniform-kernel fast path
   int path_mode = 0;         // 0 auto, 1 force the general path
   DevBuf c_target, c_W, c_WT, c_smin, c_smax;
@@ -132,6 +133,17 @@ int gpmpc_create(gpmpc_handle** out, int device) {
   h->num_sms = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
   for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+  {  // 2^(j/2048), rounded once from extended precision (exp2s table of the uniform-kernel path)
+    static double tab[EXP2S_N];
+    for (int j = 0; j < EXP2S_N; j++) tab[j] = (double)exp2l((long double)j / (long double)EXP2S_N);
+    if (h->exp2tab.ensure(sizeof(tab)) != cudaSuccess ||
+        cudaMemcpy(h->exp2tab.ptr, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      h->exp2tab.release();
+      delete h;
+      return GPMPC_ERR_CUDA;
+    }
+  }
   *out = h;
   return GPMPC_OK;
 }
@@ -142,7 +154,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
-                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in};
+                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -255,7 +267,7 @@ int gpmpc_set_cost(gpmpc_handle* h, const double* target, const double* W, const
 static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int B, int H, int Na, size_t* smem,
                        int* grid, bool uniform = false) {
   p.x = h->x.as<double>(); p.beta = h->beta.as<double>(); p.iK = h->iK.as<double>();
-  p.il2 = h->il2.as<double>(); p.s2 = h->s2.as<double>();
+  p.il2 = h->il2.as<double>(); p.s2 = h->s2.as<double>(); p.exp2tab = h->exp2tab.as<double>();
   p.N = h->N; p.NP = h->NP; p.D = h->D; p.DP = h->DP; p.E = h->E; p.Na = Na;
   p.B = B; p.H = H;
   p.betaT = h->betaT.as<double>();

@@ -172,9 +172,11 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
       }
       kr0 = fma(z0[e], q0, kr0);
       kr1 = fma(z1[e], q1, kr1);
-      u0[e] = 2.0 * q0 * il2b[e];
-      u1[e] = 2.0 * q1 * il2b[e];
+      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2b[e];   // exponent in table units (exp2s; s_kapj is scaled too)
+      u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2b[e];
     }
+    kr0 *= GPMPC_EXP2S_SCALE;
+    kr1 *= GPMPC_EXP2S_SCALE;
   }
   const double bi0 = __ldg(beta_a + i0), bi1 = __ldg(beta_a + i1);
   double rho0 = 0.0, rho1 = 0.0;
@@ -207,8 +209,8 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
         t0 = fma(u0[e], nj[e], t0);
         t1 = fma(u1[e], nj[e], t1);
       }
-      double w0 = c0 * exp_tab(t0, s_tab);
-      double w1 = c1 * exp_tab(t1, s_tab);
+      double w0 = c0 * exp2s(t0, s_tab);
+      double w1 = c1 * exp2s(t1, s_tab);
       if (masked) {
         w0 = (j > i0) ? w0 : ((j == i0) ? 0.5 * w0 : 0.0);
         w1 = (j > i1) ? w1 : ((j == i1) ? 0.5 * w1 : 0.0);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   // ---- candidate-independent constants
   for (int o = tid; o < E * D; o += NT) s_il2[o] = p.il2[o];
   if (tid < E) { s_s2[tid] = p.s2[tid]; s_logs2[tid] = log(p.s2[tid]); }
-  if (tid >= 64 && tid < 96) s_tab[tid - 64] = exp2((double)(tid - 64) * 0.03125);
+  for (int i = tid; i < EXP2S_N; i += NT) s_tab[i] = p.exp2tab[i];
   if (tid == 0) {
     int pr = 0;
     for (int a = 0; a < E; a++)
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
             if (d < D) tail = fma(nu[d] * nu[d], la[d], tail);
           double lb = 0.0, kv = 0.0;
           if (i < N) {
-            lb = __ldg(p.beta + (size_t)a * NP + i) * exp_tab(-0.5 * (quad + tail), s_tab);
+            lb = __ldg(p.beta + (size_t)a * NP + i) * exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab);
             kv = s_logs2[a] - 0.5 * (head + tail);
           }
           s_lb[a * NP + i] = lb;
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
               kap = fma(z[e], r, kap);
             }
           }
-          s_kap[o] = kap;
+          s_kap[o] = GPMPC_EXP2S_SCALE * kap;
           if (GRAD) {
             s_gam[o] = 0.0;
             s_rho[o] = 0.0;

@@ -49,7 +49,7 @@ HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G
   L.rv = o; o += H + 1;
   L.ints = o; o += 2 + P;  // counter, bad flag, pair table (packed a*16+b)
   o = (o + 1) & ~1;
-  L.tab = o; o += 32;      // 2^(j/32) for exp_tab
+  L.tab = o; o += EXP2S_N;   // 2^(j/2048) for exp2s
   L.total = (o + 1) & ~1;
   return L;
 }

@@ -63,8 +63,8 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
         q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
         q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
       }
-      u0[e] = 2.0 * q0 * il2[e];
-      u1[e] = 2.0 * q1 * il2[e];
+      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2[e];   // exponent in table units (exp2s)
+      u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2[e];
     }
   }
   double r0[E], r1[E], tr = 0.0;
@@ -87,7 +87,7 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
       t[2] = fma(u0[e], nb[e], t[2]);
       t[3] = fma(u1[e], nb[e], t[3]);
     }
-    exp_tab_x4(t, ex, s_tab);
+    exp2s_x4(t, ex, s_tab);
 #pragma unroll
     for (int b = 0; b < E; b++) { r0[b] = fma(ex[0], ba[b], r0[b]); r1[b] = fma(ex[1], ba[b], r1[b]); }
 #pragma unroll
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
   const double* il2 = p.il2;            // row 0 (all rows equal)
   const double s2 = p.s2[0];
-  if (tid >= 64 && tid < 96) s_tab[tid - 64] = exp2((double)(tid - 64) * 0.03125);
+  for (int i = tid; i < EXP2S_N; i += NT) s_tab[i] = p.exp2tab[i];
   __syncthreads();
 
   for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
@@ -227,11 +227,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
           if (d < D) tail = fma(nu[d] * nu[d], il2[d], tail);
-        const double ei = (i < N) ? exp_tab(-0.5 * (quad + tail), s_tab) : 0.0;
+        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
         double* rec = s_rec + (size_t)i * L.rlen;
 #pragma unroll
         for (int e = 0; e < EV; e++) rec[e] = nu[e];
-        rec[EV] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;   // log s2 factored out (s2^2 applied at the end)
+        rec[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;   // table units; log s2 factored out (s2^2 applied at the end)
 #pragma unroll
         for (int a = 0; a < E; a++) {
           const double be = __ldg(p.betaT + (size_t)i * E + a);
@@ -364,8 +364,8 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
         q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
         q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
       }
-      u0[e] = 2.0 * q0 * il2[e];
-      u1[e] = 2.0 * q1 * il2[e];
+      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2[e];   // exponent in table units (exp2s)
+      u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2[e];
     }
 #pragma unroll
     for (int a = 0; a < E; a++) {
@@ -406,7 +406,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
         t[2] = fma(u0[e], nb[e], t[2]);
         t[3] = fma(u1[e], nb[e], t[3]);
       }
-      exp_tab_x4(t, w, s_tab);
+      exp2s_x4(t, w, s_tab);
 #pragma unroll
       for (int q = 0; q < 4; q++) w[q] *= c[q];
       if (masked) {
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const double* il2 = p.il2;
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
-  if (tid >= 64 && tid < 96) s_tab[tid - 64] = exp2((double)(tid - 64) * 0.03125);
+  for (int i = tid; i < EXP2S_N; i += NT) s_tab[i] = p.exp2tab[i];
   __syncthreads();
   // accumulator layout: [0] unused, [1 .. D] G_m, [1+D .. 1+D+E2) G_Q, then N-pass: Phi_m[D], Phi_A[P]
   const int accGm = 1, accGQ = 1 + D, accPm = 1 + D + EV * EV, accPA = accPm + D;
@@ -713,11 +713,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           an[d] = 0.0;
           if (d < D) { tail = fma(nu[d] * nu[d], il2[d], tail); an[d] = nu[d] * il2[d]; }
         }
-        const double ei = (i < N) ? exp_tab(-0.5 * (quad + tail), s_tab) : 0.0;
+        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
         double* rcd = s_rec + (size_t)i * L.rlen;
 #pragma unroll
         for (int e = 0; e < EV; e++) rcd[e] = nu[e];
-        rcd[EV] = (i < N) ? (-0.5 * (head + tail) + zqz) : 0.0;
+        rcd[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;
 #pragma unroll
         for (int a = 0; a < E; a++) rcd[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
 #pragma unroll

@@ -17,6 +17,9 @@ __global__ void __launch_bounds__(512) k(double* out, const double* in, int iter
         if (MODE == 2) v[c] = fma(v[c], w[c], z[c]);           // 3 register operands, same "column"
         if (MODE == 3) v[c] = fma(v[c], w[(c + 1) & 7], z[(c + 3) & 7]);   // 3 register operands, mixed
         if (MODE == 4) v[c] = fma(w[c], z[(c + 1) & 7], v[c]);  // accumulate form: acc += w*z
+        if (MODE == 5) v[c] = fma(w[c & 1], z[c >> 1], v[c]);   // outer product 2 x 4: pairs share z (operand reuse cache)
+        if (MODE == 6) v[c] = fma(w[(c ^ (c >> 1)) & 1], z[c >> 1], v[c]);   // serpentine: every instruction shares one operand with its predecessor
+        if (MODE == 7) v[c] = fma(w[u & 7], z[c], v[c]);        // one operand fixed over 8 instructions
       }
   }
   double s = 0;
@@ -44,5 +47,8 @@ int main() {
   run<2>("v = fma(v, w, z)", sms, buf, in);
   run<3>("v = fma(v, w', z'')  (mixed registers)", sms, buf, in);
   run<4>("v = fma(w, z', v)    (accumulate)", sms, buf, in);
+  run<5>("v[c] = fma(w[c&1], z[c>>1], v[c])  (pairs share z)", sms, buf, in);
+  run<6>("v[c] = fma(w[serp], z[c>>1], v[c]) (serpentine)", sms, buf, in);
+  run<7>("v[c] = fma(w[u], z[c], v[c])  (w fixed x8)", sms, buf, in);
   return 0;
 }
