@@ -107,64 +107,71 @@ __device__ __forceinline__ void exp_tab_x4(const double (&x)[4], double (&res)[4
   }
 }
 
-// Hot-loop exponential of the uniform-kernel path, 7 float64 operations.  The caller passes the exponent already
+// Hot-loop exponential, 7 float64 operations + 7 integer/LDS instructions.  The caller passes the exponent already
 // in table units, t2 = x * 2048 / ln 2 (the scale is folded into the per-row / per-column terms when they are built,
 // so it costs nothing per element):
 //   n = rint(t2) (magic-number add), f = t2 - n in [-1/2, 1/2]  (exact: no Cody-Waite constants needed),
 //   exp(x) = 2^(n >> 11) * T[n & 2047] * (1 + f (c1 + f (c2 + f c3))),   T[j] = 2^(j/2048) in shared memory (16 KB,
 //   correctly rounded on the host).  c2 carries the minimax correction of the even quartic remainder
 //   (tools/gen/exp2_coeffs.py: truncation error 5.9e-18; total error <= ~1.1 ulp from the table and final roundings).
-// Exponents below the normal range collapse to ~2e-308 like exp_tab; t2 < -2^31 (x < -7e5) is detected through the
-// words of the shifted value (integer pipe) and treated as deep underflow.  t2 > 0 is limited by the caller's
-// bound x <= log(s2^2) as before.
+// Deep underflow: t2 is clamped to >= -1022 * 2048 - 1 by ONE unsigned integer min on its high word (negative doubles
+// order like unsigned integers), so n always fits and the result collapses to <= ~2e-308 (possibly a tiny denormal
+// pattern, never NaN/negative) for x < -708.  A NaN exponent also collapses to ~0: NaN inputs are screened per step
+// by the callers (s_int[1]), as before.  t2 > 0 is limited by the callers' bound x <= log(s2^2).
 constexpr int EXP2S_LOG = 11;
 constexpr int EXP2S_N = 1 << EXP2S_LOG;
 #define GPMPC_EXP2S_SCALE 2.95463944374059701659e+03   /* 2048 / ln 2 */
 #define GPMPC_EXP2S_C1 3.38450771757785784290e-04
 #define GPMPC_EXP2S_C2 5.72744625649513507015e-08
 #define GPMPC_EXP2S_C3 6.46152867293236580665e-12
-#define GPMPC_EXP2S_NMIN (-1022 * EXP2S_N)
+#define GPMPC_EXP2S_HI_MIN 0xC13FF000u                 /* high word of -(1022 * 2048).0 */
 
-// low / high word of t2 + 1.5 * 2^52  ->  clamped integer exponent.  The low word is rint(t2) only while
-// -2^31 <= t2 < 2^31: high word 0x43380000 (t2 >= 0) or 0x4337FFFF with a negative low word.
-__device__ __forceinline__ int exp2s_index(int n, int hw) {
-  const bool deep = (hw < 0x4337FFFF) || (hw == 0x4337FFFF && n >= 0);
-  return deep ? GPMPC_EXP2S_NMIN : max(n, GPMPC_EXP2S_NMIN);
+__device__ __forceinline__ unsigned exp2s_table_addr(const double* tab) {   // 32-bit shared-window address
+  return (unsigned)__cvta_generic_to_shared(tab);
 }
-
-__device__ __forceinline__ double exp2s(double t2, const double* __restrict__ tab) {
-  const double SHIFT = 6755399441055744.0;
-  double kd = t2 + SHIFT;
-  int n = __double2loint(kd);
-  const int hw = __double2hiint(kd);
-  kd -= SHIFT;
-  const double f = t2 - kd;
-  n = exp2s_index(n, hw);
-  double p = __fma_rn(GPMPC_EXP2S_C3, f, GPMPC_EXP2S_C2);
-  p = __fma_rn(p, f, GPMPC_EXP2S_C1);
-  p *= f;
-  const double t = tab[n & (EXP2S_N - 1)];
-  const double v = __fma_rn(t, p, t);
-  const int hi = __double2hiint(v) + (int)(((unsigned)n & ~(unsigned)(EXP2S_N - 1)) << (20 - EXP2S_LOG));
+__device__ __forceinline__ double exp2s_lds(unsigned addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double exp2s_clamp(double t2) {
+  const unsigned h = min((unsigned)__double2hiint(t2), GPMPC_EXP2S_HI_MIN);
+  return __hiloint2double((int)h, __double2loint(t2));
+}
+// integer side: m = n << 3 serves both the table byte offset (m & 0x3ff8) and the exponent ((m & ~0x3fff) << 6)
+__device__ __forceinline__ double exp2s_scale(double v, int m) {   // v * 2^(n >> 11) through the exponent field
+  const int hi = __double2hiint(v) + ((m & ~(8 * EXP2S_N - 1)) << (17 - EXP2S_LOG));
   return __hiloint2double(hi, __double2loint(v));
 }
 
-// Four at once, stage by stage (4 independent float64 operations per stage, see exp_tab_x4).
-__device__ __forceinline__ void exp2s_x4(const double (&x)[4], double (&res)[4], const double* __restrict__ tab) {
+__device__ __forceinline__ double exp2s(double t2, unsigned tab_s) {
   const double SHIFT = 6755399441055744.0;
-  double kd[4], f[4], p[4], t[4];
-  int n[4], hw[4];
+  t2 = exp2s_clamp(t2);
+  double kd = t2 + SHIFT;
+  const int n = __double2loint(kd);
+  kd -= SHIFT;
+  const double f = t2 - kd;
+  const int m = n << 3;
+  const double t = exp2s_lds(tab_s + (m & (8 * EXP2S_N - 8)));
+  double p = __fma_rn(GPMPC_EXP2S_C3, f, GPMPC_EXP2S_C2);
+  p = __fma_rn(p, f, GPMPC_EXP2S_C1);
+  p *= f;
+  return exp2s_scale(__fma_rn(t, p, t), m);
+}
+
+// Four at once, stage by stage (4 independent float64 operations per stage, see exp_tab_x4).
+__device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4], unsigned tab_s) {
+  const double SHIFT = 6755399441055744.0;
+  double x[4], kd[4], f[4], p[4], t[4];
+  int n[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) x[c] = exp2s_clamp(xin[c]);
 #pragma unroll
   for (int c = 0; c < 4; c++) kd[c] = x[c] + SHIFT;
 #pragma unroll
-  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); hw[c] = __double2hiint(kd[c]); kd[c] -= SHIFT; }
+  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]) << 3; kd[c] -= SHIFT; }
 #pragma unroll
-  for (int c = 0; c < 4; c++) f[c] = x[c] - kd[c];
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    n[c] = exp2s_index(n[c], hw[c]);
-    t[c] = tab[n[c] & (EXP2S_N - 1)];
-  }
+  for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_lds(tab_s + (n[c] & (8 * EXP2S_N - 8))); }
 #pragma unroll
   for (int c = 0; c < 4; c++) p[c] = __fma_rn(GPMPC_EXP2S_C3, f[c], GPMPC_EXP2S_C2);
 #pragma unroll
@@ -172,11 +179,7 @@ __device__ __forceinline__ void exp2s_x4(const double (&x)[4], double (&res)[4],
 #pragma unroll
   for (int c = 0; c < 4; c++) p[c] *= f[c];
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    const double v = __fma_rn(t[c], p[c], t[c]);
-    const int hi = __double2hiint(v) + (int)(((unsigned)n[c] & ~(unsigned)(EXP2S_N - 1)) << (20 - EXP2S_LOG));
-    res[c] = __hiloint2double(hi, __double2loint(v));
-  }
+  for (int c = 0; c < 4; c++) res[c] = exp2s_scale(__fma_rn(t[c], p[c], t[c]), n[c]);
 }
 
 // ---------------------------------------------------------------------------------------------

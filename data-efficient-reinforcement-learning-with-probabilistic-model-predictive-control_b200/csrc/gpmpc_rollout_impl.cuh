@@ -149,7 +149,7 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
                                           const double* __restrict__ kka, const double* __restrict__ beta_a,
                                           const double* __restrict__ beta_b, const double* __restrict__ iKa,
                                           int I, int jbeg, int jend, int lane, double* s_gam, double* s_rho,
-                                          double* s_xi, double* s_acc, const double* __restrict__ s_tab) {
+                                          double* s_xi, double* s_acc, unsigned s_tab) {
   const int NP = p.NP, DP = p.DP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
   double u0[EV], u1[EV], kr0, kr1;
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   double* s_r = sm + L.r;
   double* s_rv = sm + L.rv;
   int* s_int = reinterpret_cast<int*>(sm + L.ints);  // [0] counter, [1] bad flag, [2..] pair table
-  double* s_tab = sm + L.tab;
+  double* s_tabp = sm + L.tab;
+  const unsigned s_tab = exp2s_table_addr(s_tabp);
   const int nOut = L.nOut, PV = L.PV;
   const RecLayout RL = rec_layout(E, D);
   const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   // ---- candidate-independent constants
   for (int o = tid; o < E * D; o += NT) s_il2[o] = p.il2[o];
   if (tid < E) { s_s2[tid] = p.s2[tid]; s_logs2[tid] = log(p.s2[tid]); }
-  for (int i = tid; i < EXP2S_N; i += NT) s_tab[i] = p.exp2tab[i];
+  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
   if (tid == 0) {
     int pr = 0;
     for (int a = 0; a < E; a++)

@@ -46,7 +46,7 @@ template <int EV>
 __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
                                              const double* __restrict__ Qm, const double* __restrict__ il2, int I,
                                              int jbeg, int jend, int lane, double* s_acc,
-                                             const double* __restrict__ s_tab) {
+                                             unsigned s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
@@ -127,13 +127,13 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   double* s_m = sm + L.m; double* s_s = sm + L.s; double* s_mu = sm + L.mu; double* s_A = sm + L.A;
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
-  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
+  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   const int nOut = L.nOut;
   const UniRecLayout RL = uni_rec_layout(E);
   const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
   const double* il2 = p.il2;            // row 0 (all rows equal)
   const double s2 = p.s2[0];
-  for (int i = tid; i < EXP2S_N; i += NT) s_tab[i] = p.exp2tab[i];
+  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
   __syncthreads();
 
   for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
@@ -347,7 +347,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
                                              int rhot, const double* __restrict__ Qm, const double* __restrict__ il2,
                                              const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
                                              int lane, double* s_gam, double* s_accGm, double* s_accGQ,
-                                             double* s_rho, double* s_xi, const double* __restrict__ s_tab) {
+                                             double* s_rho, double* s_xi, unsigned s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
             oda = odmu + EV;
   double* s_rec = sm + L.rec; double* s_gam = sm + L.gam; double* s_rho = sm + L.rho; double* s_xi = sm + L.xi;
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
-  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tab = sm + L.tab;
+  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   double* s2p = sm + L.small2;
   // small2 carve: mu_bar[E], s_bar[E2], Om[E2], Rinv[E2], Ub[E2], Vb[E2], hg[E + E2] (h_bar, g_bar), scal[16]
   double* s_mubar = s2p; double* s_sbar = s_mubar + GPMPC_MAX_EV; double* s_Om = s_sbar + EV * EV;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const double* il2 = p.il2;
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
-  for (int i = tid; i < EXP2S_N; i += NT) s_tab[i] = p.exp2tab[i];
+  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
   __syncthreads();
   // accumulator layout: [0] unused, [1 .. D] G_m, [1+D .. 1+D+E2) G_Q, then N-pass: Phi_m[D], Phi_A[P]
   const int accGm = 1, accGQ = 1 + D, accPm = 1 + D + EV * EV, accPA = accPm + D;
