@@ -46,6 +46,7 @@ struct gpmpc_handle {
   DevBuf c_target, c_W, c_WT, c_smin, c_smax;
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
+  DevBuf dbg_clk;
   DevBuf ws_kk, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
   long long launches = 0;
   bool timing = false;
@@ -154,7 +155,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
-                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab};
+                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -399,6 +400,12 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     plan(smb, &thr_b, &grid_b, "GPMPC_UNI_BWD_THREADS", "GPMPC_UNI_BWD_CTAS");
     if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg = v; }
     if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg_bwd = v; }
+    const bool dbg = getenv("GPMPC_DEBUG_CLOCKS") != nullptr;   // tuning aid: per-phase cycles of CTA 0 on stderr
+    if (dbg) {
+      CU(h->dbg_clk.ensure(sizeof(long long) * 16));
+      CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * 16, st));
+      p.dbg_clk = h->dbg_clk.as<long long>();
+    }
     if (h->timing) CU(cudaEventRecord(h->ev[0], st));
     CU(launch_uniform(E, false, p, nullptr, grid_f, thr_f, smf, st));
     h->launches += 1;
@@ -409,6 +416,15 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       CU(launch_uniform(E, true, p, grad, grid_b, thr_b, smb, st));
       h->launches += 1;
       if (h->timing) { CU(cudaEventRecord(h->ev[3], st)); h->ev_bwd = true; }
+    }
+    if (dbg) {
+      long long c[16];
+      CU(cudaMemcpyAsync(c, h->dbg_clk.ptr, sizeof(c), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      const long long nf = (long long)((B + grid_f - 1) / grid_f) * H, nb = (long long)((B + grid_b - 1) / grid_b) * H;
+      fprintf(stderr, "[gpmpc clocks/step, CTA 0] fwd: P0 %lld  P1 %lld  P3 sweep %lld  P4 %lld | bwd: pre %lld  B0 %lld  B1 %lld  B2 sweep %lld  B3 %lld  B4 %lld\n",
+              c[0] / nf, c[1] / nf, c[2] / nf, c[3] / nf, want_grad ? c[8] / nb : 0, want_grad ? c[9] / nb : 0,
+              want_grad ? c[10] / nb : 0, want_grad ? c[11] / nb : 0, want_grad ? c[12] / nb : 0, want_grad ? c[13] / nb : 0);
     }
     return GPMPC_OK;
   }

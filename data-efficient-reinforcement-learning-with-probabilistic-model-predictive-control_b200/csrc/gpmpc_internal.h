@@ -41,6 +41,7 @@ struct RolloutParams {
   int premat;          // uniform reverse sweep: per-step matrices / stage-cost adjoints precomputed for all steps
   int rowarr;          // uniform reverse sweep: per-row partial sums in shared memory (when they fit)
   int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
+  long long* dbg_clk;  // tuning aid (GPMPC_DEBUG_CLOCKS): CTA 0 accumulates clock64() deltas per phase here, else NULL
 };
 
 struct BackwardParams {

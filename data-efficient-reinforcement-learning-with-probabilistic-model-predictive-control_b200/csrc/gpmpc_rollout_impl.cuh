@@ -136,6 +136,32 @@ __device__ __forceinline__ double col_reduce8(const double (&v)[8], int lane, in
   return c;
 }
 
+// Sums of K2 (power of two, <= 32) per-lane values over the 32 lanes with K2 - 1 + log2(32 / K2) shuffles instead
+// of 5 K2 (halving exchange: at offset 16, 8, ... every lane keeps one half of its values and sends the other half).
+// On return value number `idx` is complete in every lane that shares `idx`; lanes with (lane & (32 / K2 - 1)) == 0
+// are the designated writers (idx = lane / (32 / K2)).
+template <int K2>
+__device__ __forceinline__ double warp_reduce_multi(double (&v)[K2], int lane, int& idx) {
+  static_assert(K2 >= 1 && K2 <= 32 && (K2 & (K2 - 1)) == 0, "K2 must be a power of two <= 32");
+  int off = 16;
+  idx = 0;
+#pragma unroll
+  for (int n = K2; n > 1; n >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < n / 2; k++) {
+      const double send = up ? v[k] : v[k + n / 2];
+      const double keep = up ? v[k + n / 2] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    idx += up ? n / 2 : 0;
+  }
+  double r = v[0];
+#pragma unroll
+  for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // The hot loop: one warp, rows {64 I + lane, 64 I + 32 + lane}, columns [jbeg, jend).
 //   t_ij = kap_i + kap_j + u_i . nu_j ;  w_ij = (beta_a,i beta_b,j - [a==b] iK_a,ij) exp(t_ij)

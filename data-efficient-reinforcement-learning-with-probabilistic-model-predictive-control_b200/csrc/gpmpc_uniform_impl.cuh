@@ -19,6 +19,9 @@
 
 namespace gpmpc {
 
+// tuning aid: thread 0 of CTA 0 adds the cycles since the previous mark to slot k (after a __syncthreads)
+#define UNI_CLK(k) do { if (p.dbg_clk && blockIdx.x == 0 && tid == 0) { const long long c_ = clock64(); p.dbg_clk[k] += c_ - clk_; clk_ = c_; } } while (0)
+
 #ifndef UNI_MINB
 #define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
 #endif
@@ -45,7 +48,7 @@ __device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, i
 template <int EV>
 __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
                                              const double* __restrict__ Qm, const double* __restrict__ il2, int I,
-                                             int jbeg, int jend, int lane, double* s_acc,
+                                             int jbeg, int jend, int lane, double* s_part,
                                              unsigned s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
@@ -80,36 +83,85 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
     const double k0a = __ldg(ik0), k1a = __ldg(ik0 + 32), k0b = __ldg(ik0 + NP), k1b = __ldg(ik0 + NP + 32);
     ik0 += 2 * (size_t)NP;
     double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, ex[4];
+    // serpentine order: every FMA shares one register operand with its predecessor (operand-reuse cache; a DFMA
+    // with three fresh register operands issues at 2/3 rate on B200, tools/micro/dfma_operands.cu)
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       t[0] = fma(u0[e], na[e], t[0]);
       t[1] = fma(u1[e], na[e], t[1]);
-      t[2] = fma(u0[e], nb[e], t[2]);
       t[3] = fma(u1[e], nb[e], t[3]);
+      t[2] = fma(u0[e], nb[e], t[2]);
     }
     exp2s_x4(t, ex, s_tab);
 #pragma unroll
-    for (int b = 0; b < E; b++) { r0[b] = fma(ex[0], ba[b], r0[b]); r1[b] = fma(ex[1], ba[b], r1[b]); }
+    for (int b = 0; b < E; b++) {
+      if (b & 1) { r1[b] = fma(ex[1], ba[b], r1[b]); r0[b] = fma(ex[0], ba[b], r0[b]); }
+      else       { r0[b] = fma(ex[0], ba[b], r0[b]); r1[b] = fma(ex[1], ba[b], r1[b]); }
+    }
 #pragma unroll
-    for (int b = 0; b < E; b++) { r0[b] = fma(ex[2], bb[b], r0[b]); r1[b] = fma(ex[3], bb[b], r1[b]); }
+    for (int b = 0; b < E; b++) {
+      if (b & 1) { r1[b] = fma(ex[3], bb[b], r1[b]); r0[b] = fma(ex[2], bb[b], r0[b]); }
+      else       { r0[b] = fma(ex[2], bb[b], r0[b]); r1[b] = fma(ex[3], bb[b], r1[b]); }
+    }
     tr = fma(ex[0], k0a, tr);
     tr2 = fma(ex[1], k1a, tr2);
     tr = fma(ex[2], k0b, tr);
     tr2 = fma(ex[3], k1b, tr2);
   }
   tr += tr2;
-  // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace
-  int pr = 0;
+  // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace: halving reduction of the P + 1 lane partials, 16 at a time, into
+  // this warp's private accumulator row (no shared-memory float64 atomics: those are CAS spin loops)
+  constexpr int P1 = E * (E + 1) / 2 + 1, NCH = (P1 + 15) / 16;
+  double vals[16 * NCH];
+  {
+    int pr = 0;
 #pragma unroll
-  for (int a = 0; a < E; a++)
+    for (int a = 0; a < E; a++)
 #pragma unroll
-    for (int b = a; b < E; b++) {
-      double v = warp_sum(bi0[a] * r0[b] + bi1[a] * r1[b]);
-      if (lane == 0) atomicAdd(s_acc + pr, v);
-      pr++;
+      for (int b = a; b < E; b++) { vals[pr] = bi0[a] * r0[b] + bi1[a] * r1[b]; pr++; }
+    vals[pr++] = tr;
+#pragma unroll
+    for (; pr < 16 * NCH; pr++) vals[pr] = 0.0;
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) {
+    double v16[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v16[k] = vals[16 * ch + k];
+    int idx;
+    const double tot = warp_reduce_multi<16>(v16, lane, idx);
+    if ((lane & 1) == 0 && 16 * ch + idx < P1) s_part[16 * ch + idx] += tot;
+  }
+}
+
+// Lane partial of one mean-part moment over the training points (rows lane, lane + 32, ...):
+//   o = a * nOut + q :  q = 0: h_a = sum_i e_i beta_a,i ;  q = 1 + d: g_a,d = sum_i e_i beta_a,i nu_i,d
+// (gp_model.py:138-153).  e_i sits in the spare slot of the hot-loop record; nu of the action / time dimensions is
+// rebuilt from x.
+template <int EV>
+__device__ __forceinline__ double uni_moment_lane(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
+                                                  const double* __restrict__ s_m, int o, int nOut, int lane) {
+  const int a = o / nOut, q = o - a * nOut, d = q - 1;
+  const int N = p.N, D = p.D;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int i = lane; i < N; i += 64) {
+    const int i1 = i + 32;
+    const double* ra = s_rec + (size_t)i * rlen;
+    const double* rb = s_rec + (size_t)i1 * rlen;     // i1 < NP always (NP is a multiple of 64); e_i = 0 for i >= N
+    const double la = ra[EV + 1 + a] * ra[2 * EV + 1];
+    const double lb = rb[EV + 1 + a] * rb[2 * EV + 1];
+    double fa = 1.0, fb = 1.0;
+    if (q > 0) {
+      if (d < EV) { fa = ra[d]; fb = rb[d]; }
+      else {
+        fa = __ldg(p.x + (size_t)i * D + d) - s_m[d];
+        fb = (i1 < N) ? __ldg(p.x + (size_t)i1 * D + d) - s_m[d] : 0.0;
+      }
     }
-  tr = warp_sum(tr);
-  if (lane == 0) atomicAdd(s_acc + pr, tr);
+    acc0 = fma(la, fa, acc0);
+    acc1 = fma(lb, fb, acc1);
+  }
+  return acc0 + acc1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -128,7 +180,8 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
   int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
-  const int nOut = L.nOut;
+  double* s_part = sm + L.part;
+  const int nOut = L.nOut, warp = tid >> 5, nwarps = NT >> 5;
   const UniRecLayout RL = uni_rec_layout(E);
   const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
   const double* il2 = p.il2;            // row 0 (all rows equal)
@@ -136,6 +189,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
   __syncthreads();
 
+  long long clk_ = clock64();
   for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
     if (tid < E) {
       double v = p.obs_mu[(p.per_cand_init ? (size_t)cand * E : 0) + tid];
@@ -196,10 +250,10 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         for (int e = 0; e < EV * EV; e++) s_Q[e] = Qm[e];
         s_misc[1] = detR;
       }
-      if (tid < P + 1) s_acc[tid] = 0.0;
-      if (tid < E * nOut) s_out[tid] = 0.0;
+      for (int o = tid; o < nwarps * L.partlen; o += NT) s_part[o] = 0.0;
       if (tid == 0) s_int[0] = 0;
       __syncthreads();
+      UNI_CLK(0);
       if (tid == 100) {
         double chk = 0.0;
         for (int d = 0; d < D; d++) chk += s_m[d];
@@ -233,21 +287,26 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         for (int e = 0; e < EV; e++) rec[e] = nu[e];
         rec[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;   // table units; log s2 factored out (s2^2 applied at the end)
 #pragma unroll
-        for (int a = 0; a < E; a++) {
-          const double be = __ldg(p.betaT + (size_t)i * E + a);
-          rec[EV + 1 + a] = be;
-          const double lb = ei * be;
-          double v = warp_sum(lb);
-          if (lane == 0) atomicAdd(s_out + a * nOut, v);
-#pragma unroll
-          for (int d = 0; d < GPMPC_MAX_D; d++)
-            if (d < D) {
-              v = warp_sum(lb * nu[d]);
-              if (lane == 0) atomicAdd(s_out + a * nOut + 1 + d, v);
-            }
-        }
+        for (int a = 0; a < E; a++) rec[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
+        rec[2 * EV + 1] = ei;   // spare slot of the (even-length) record
       }
       __syncthreads();
+      // ---- P1b: mean-part moments h_a, g_a: one warp per output (two at a time), lanes over the training points
+      for (int o = warp; o < E * nOut; o += 2 * nwarps) {
+        const int o2 = o + nwarps;
+        double va = uni_moment_lane<EV>(p, s_rec, L.rlen, s_m, o, nOut, lane);
+        double vb = (o2 < E * nOut) ? uni_moment_lane<EV>(p, s_rec, L.rlen, s_m, o2, nOut, lane) : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          va += __shfl_xor_sync(0xffffffffu, va, off);
+          vb += __shfl_xor_sync(0xffffffffu, vb, off);
+        }
+        if (lane == 0) {
+          s_out[o] = va;
+          if (o2 < E * nOut) s_out[o2] = vb;
+        }
+      }
+      UNI_CLK(1);
       // ---- P3: one N x N sweep for all pairs
       {
         const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg, nitems = nrb * nseg;
@@ -258,10 +317,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
           if (item >= nitems) break;
           const int I = item / nseg, js = item - I * nseg;
           const int jbeg = js * p.seg, jend = min(NP, jbeg + p.seg);
-          uni_fwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, I, jbeg, jend, lane, s_acc, s_tab);
+          uni_fwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, I, jbeg, jend, lane, s_part + warp * L.partlen, s_tab);
         }
       }
       __syncthreads();
+      UNI_CLK(2);
       // ---- P4: mean, V, S, recurrence
       if (tid == 0) {
         const double c = s_misc[0], detR = s_misc[1], rs = 1.0 / sqrt(detR);
@@ -284,6 +344,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
             rec[RL.offH + a] = h;
             for (int e = 0; e < E; e++) { rec[RL.offV + a * E + e] = s_V[a * D + e]; rec[RL.offG + a * E + e] = g[e]; }
           }
+        }
+        for (int k = 0; k <= P; k++) {
+          double v = 0.0;
+          for (int w = 0; w < nwarps; w++) v += s_part[w * L.partlen + k];
+          s_acc[k] = v;
         }
         const double trc = s_acc[P];
         int pr = 0;
@@ -318,6 +383,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         }
       }
       __syncthreads();
+      UNI_CLK(3);
     }
     if (tid == 0) {
       double cmu, cvar;
@@ -567,6 +633,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   // accumulator layout: [0] unused, [1 .. D] G_m, [1+D .. 1+D+E2) G_Q, then N-pass: Phi_m[D], Phi_A[P]
   const int accGm = 1, accGQ = 1 + D, accPm = 1 + D + EV * EV, accPA = accPm + D;
 
+  long long clk_ = clock64();
   for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
     const double* mus = p.states_mu + (size_t)cand * (H + 1) * E;
     const double* vars = p.states_var + (size_t)cand * (H + 1) * E * E;
@@ -612,6 +679,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       }
     }
     __syncthreads();
+    UNI_CLK(8);
     for (int t = H; t >= 1; t--) {
       const double* rec = p.records + ((size_t)cand * H + (t - 1)) * RL.size;
       const double* sp = vars + (size_t)(t - 1) * E * E;
@@ -689,6 +757,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         for (int e = 0; e < EV * EV; e++) s_scal[8 + e] = A_bar[e];   // needs 8 + E2 <= 72 doubles
       }
       __syncthreads();
+      UNI_CLK(9);
       // ---- B1: nu, exponent terms, hot-loop record (as in the forward) + N pass of the mean part
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
@@ -750,6 +819,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           }
       }
       __syncthreads();
+      UNI_CLK(10);
       // ---- B2: adjoint-weighted N^2 sweep (upper triangle)
       {
         const double wbar = s_scal[3];
@@ -769,6 +839,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         }
       }
       __syncthreads();
+      UNI_CLK(11);
       // ---- B3: column sums gam_j -> their share of G_m (D), G_Q (E x E)   [row sums were folded in per item]
       {
         double gm[GPMPC_MAX_D], gQ[EV * EV];
@@ -809,6 +880,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         }
       }
       __syncthreads();
+      UNI_CLK(12);
       // ---- B4: small algebra (thread 0): assemble m_bar, s_prev_bar, stage-cost adjoints
       if (tid == 0) {
         const double c = s_scal[0], detR = s_scal[1], detR_bar = s_scal[2], cbar_c = s_scal[4];
@@ -897,6 +969,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         for (int e = 0; e < E * E; e++) s_sbar[e] = nsb[e];
       }
       __syncthreads();
+      UNI_CLK(13);
     }
     if (p.limit_change && tid < Na) {
       double cum = 0.0;

@@ -6,7 +6,7 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, rlen, rhot, gam, rho, xi, pre, prelen, out, nOut;
+  int rec, rlen, rhot, gam, rho, xi, pre, prelen, out, nOut, part, partlen;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
@@ -31,6 +31,9 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.pre = o; if (bwd && premat) o += H * L.prelen;
   L.nOut = 1 + D;
   L.out = o; o += E * L.nOut;
+  // per-warp accumulator rows of the forward sweep (P + 1 sums, padded to the 16-wide halving reduction), 8 warps max
+  L.partlen = ((P + 1) + 15) & ~15;
+  L.part = o; if (!bwd) o += 8 * L.partlen;
   L.m = o; o += GPMPC_MAX_D;
   L.s = o; o += EV * EV;
   L.mu = o; o += GPMPC_MAX_EV;
