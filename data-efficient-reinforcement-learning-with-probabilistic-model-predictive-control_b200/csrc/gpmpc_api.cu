@@ -46,7 +46,7 @@ struct gpmpc_handle {
   DevBuf c_target, c_W, c_WT, c_smin, c_smax;
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
-  DevBuf dbg_clk;
+  DevBuf dbg_clk, ws_uni;
   DevBuf ws_kk, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
   long long launches = 0;
   bool timing = false;
@@ -155,7 +155,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
-                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk};
+                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -368,12 +368,10 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     } else {
       p.records = nullptr;
     }
-    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false, false);
-    size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true, false);
-    p.rowarr = smb <= 112 * 1024 ? 1 : 0;      // per-row arrays only while two CTAs still fit on an SM
-    if (!p.rowarr) smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false, false);
+    const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false);
+    size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false);
     {  // precomputed per-step matrices: only if they do not cost a resident CTA (or the launch itself)
-      const size_t with = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, p.rowarr != 0, true);
+      const size_t with = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true);
       const size_t lim = smb <= 112 * 1024 ? 112 * 1024 : h->smem_optin;
       p.premat = with <= lim ? 1 : 0;
       if (const char* e = getenv("GPMPC_UNI_PREMAT")) p.premat = (atoi(e) != 0 && with <= lim) ? 1 : 0;
@@ -412,6 +410,8 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     if (h->timing) { CU(cudaEventRecord(h->ev[1], st)); h->ev_fwd = true; }
     h->ev_bwd = false;
     if (want_grad) {
+      CU(h->ws_uni.ensure(sizeof(double) * (size_t)grid_b * h->NP * (2 + E)));   // zeroed by the kernel itself
+      p.ws_uni = h->ws_uni.as<double>();
       if (h->timing) CU(cudaEventRecord(h->ev[2], st));
       CU(launch_uniform(E, true, p, grad, grid_b, thr_b, smb, st));
       h->launches += 1;
@@ -422,9 +422,10 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       CU(cudaMemcpyAsync(c, h->dbg_clk.ptr, sizeof(c), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       const long long nf = (long long)((B + grid_f - 1) / grid_f) * H, nb = (long long)((B + grid_b - 1) / grid_b) * H;
-      fprintf(stderr, "[gpmpc clocks/step, CTA 0] fwd: P0 %lld  P1 %lld  P3 sweep %lld  P4 %lld | bwd: pre %lld  B0 %lld  B1 %lld  B2 sweep %lld  B3 %lld  B4 %lld\n",
-              c[0] / nf, c[1] / nf, c[2] / nf, c[3] / nf, want_grad ? c[8] / nb : 0, want_grad ? c[9] / nb : 0,
-              want_grad ? c[10] / nb : 0, want_grad ? c[11] / nb : 0, want_grad ? c[12] / nb : 0, want_grad ? c[13] / nb : 0);
+      fprintf(stderr, "[gpmpc clocks/step, CTA 0] fwd: P0 %lld  P1a %lld  P1b %lld  P3 sweep %lld  P4 %lld | bwd: pre %lld  B0 %lld  B1a %lld  B1b %lld  B2 sweep %lld  B3a %lld  B3b %lld  B4 %lld\n",
+              c[0] / nf, c[4] / nf, c[1] / nf, c[2] / nf, c[3] / nf, want_grad ? c[8] / nb : 0, want_grad ? c[9] / nb : 0,
+              want_grad ? c[14] / nb : 0, want_grad ? c[10] / nb : 0, want_grad ? c[11] / nb : 0, want_grad ? c[15] / nb : 0,
+              want_grad ? c[12] / nb : 0, want_grad ? c[13] / nb : 0);
     }
     return GPMPC_OK;
   }

@@ -39,7 +39,7 @@ struct RolloutParams {
   int group;           // pairs per N^2 phase
   int seg;             // columns per work item
   int premat;          // uniform reverse sweep: per-step matrices / stage-cost adjoints precomputed for all steps
-  int rowarr;          // uniform reverse sweep: per-row partial sums in shared memory (when they fit)
+  double* ws_uni;      // uniform reverse sweep: (grid, NP * (2 + EV)) row / column sums of the sweep, reduced at L2
   int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
   long long* dbg_clk;  // tuning aid (GPMPC_DEBUG_CLOCKS): CTA 0 accumulates clock64() deltas per phase here, else NULL
 };
@@ -59,7 +59,7 @@ size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int g
 int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, size_t smem_limit);
 cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
-size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool rowarr, bool premat);
+size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat);
 cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,

@@ -58,8 +58,8 @@ cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* gra
   }
 }
 
-size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool rowarr, bool premat) {
-  return (size_t)make_uni_layout(EV, bwd, NP, DP, D, H, Na, rowarr, premat).total * sizeof(double);
+size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat) {
+  return (size_t)make_uni_layout(EV, bwd, NP, DP, D, H, Na, premat).total * sizeof(double);
 }
 
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st) {

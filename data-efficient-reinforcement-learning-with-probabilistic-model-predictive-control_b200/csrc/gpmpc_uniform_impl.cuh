@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         rec[2 * EV + 1] = ei;   // spare slot of the (even-length) record
       }
       __syncthreads();
+      UNI_CLK(4);
       // ---- P1b: mean-part moments h_a, g_a: one warp per output (two at a time), lanes over the training points
       for (int o = warp; o < E * nOut; o += 2 * nwarps) {
         const int o2 = o + nwarps;
@@ -407,13 +408,15 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 // ---------------------------------------------------------------------------------------------
 // reverse sweep hot loop: upper-triangle sweep with the adjoint-weighted coefficient
 //   W_ij = p_i . beta_j - wbar iK_ij ,  w_ij = W_ij Eh_ij ; rows: rho_i, xi_i ; columns: gam_j
+// Row and column sums leave the warp as float64 reductions into the CTA's global scratch (native RED.ADD.F64 at L2,
+// fire and forget); float64 atomics on shared memory are CAS spin loops and cost ~15 % of an item.
 // ---------------------------------------------------------------------------------------------
-template <int EV, bool ROWARR>
+template <int EV>
 __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
-                                             int rhot, const double* __restrict__ Qm, const double* __restrict__ il2,
+                                             const double* __restrict__ Qm, const double* __restrict__ il2,
                                              const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
-                                             int lane, double* s_gam, double* s_accGm, double* s_accGQ,
-                                             double* s_rho, double* s_xi, unsigned s_tab) {
+                                             int lane, double* __restrict__ g_gam, double* __restrict__ g_rho,
+                                             double* __restrict__ g_xi, unsigned s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
@@ -458,19 +461,19 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
       double c[4] = {-wbar * __ldg(ik0), -wbar * __ldg(ik0 + 32), -wbar * __ldg(ik0 + NP), -wbar * __ldg(ik0 + NP + 32)};
       ik0 += 2 * (size_t)NP;
 #pragma unroll
-      for (int b = 0; b < E; b++) {
+      for (int b = 0; b < E; b++) {   // serpentine order (operand-reuse cache, see uni_fwd_item)
         c[0] = fma(p0[b], ba[b], c[0]);
         c[1] = fma(p1[b], ba[b], c[1]);
-        c[2] = fma(p0[b], bb[b], c[2]);
         c[3] = fma(p1[b], bb[b], c[3]);
+        c[2] = fma(p0[b], bb[b], c[2]);
       }
       double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, w[4];
 #pragma unroll
       for (int e = 0; e < EV; e++) {
         t[0] = fma(u0[e], na[e], t[0]);
         t[1] = fma(u1[e], na[e], t[1]);
-        t[2] = fma(u0[e], nb[e], t[2]);
         t[3] = fma(u1[e], nb[e], t[3]);
+        t[2] = fma(u0[e], nb[e], t[2]);
       }
       exp2s_x4(t, w, s_tab);
 #pragma unroll
@@ -485,65 +488,63 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
       rho1 += w[1] + w[3];
 #pragma unroll
       for (int e = 0; e < EV; e++) {
-        xi0[e] = fma(w[0], na[e], xi0[e]);
-        xi1[e] = fma(w[1], na[e], xi1[e]);
+        if (e & 1) { xi1[e] = fma(w[1], na[e], xi1[e]); xi0[e] = fma(w[0], na[e], xi0[e]); }
+        else       { xi0[e] = fma(w[0], na[e], xi0[e]); xi1[e] = fma(w[1], na[e], xi1[e]); }
       }
 #pragma unroll
       for (int e = 0; e < EV; e++) {
-        xi0[e] = fma(w[2], nb[e], xi0[e]);
-        xi1[e] = fma(w[3], nb[e], xi1[e]);
+        if (e & 1) { xi1[e] = fma(w[3], nb[e], xi1[e]); xi0[e] = fma(w[2], nb[e], xi0[e]); }
+        else       { xi0[e] = fma(w[2], nb[e], xi0[e]); xi1[e] = fma(w[3], nb[e], xi1[e]); }
       }
       v[2 * jp] = w[0] + w[1];
       v[2 * jp + 1] = w[2] + w[3];
     }
     int col;
     double tot = col_reduce8(v, lane, col);
-    if ((lane & 3) == 0) atomicAdd(s_gam + j0 + col, tot);
+    if ((lane & 3) == 0) atomicAdd(g_gam + j0 + col, tot);
   }
-  if (ROWARR) {   // shared memory has room for per-row partial sums: 2 (1 + EV) conflict-free atomics per lane
-    atomicAdd(s_rho + i0, rho0);
-    atomicAdd(s_rho + i1, rho1);
+  atomicAdd(g_rho + i0, rho0);
+  atomicAdd(g_rho + i1, rho1);
 #pragma unroll
-    for (int e = 0; e < EV; e++) { atomicAdd(s_xi + i0 * EV + e, xi0[e]); atomicAdd(s_xi + i1 * EV + e, xi1[e]); }
-    return;
+  for (int e = 0; e < EV; e++) { atomicAdd(g_xi + (size_t)e * NP + i0, xi0[e]); atomicAdd(g_xi + (size_t)e * NP + i1, xi1[e]); }
+}
+
+// Lane partials of the reverse sweep's O(N) reductions (rows lane, lane + 32, ...), one output per call:
+//  kind 0 (B1b, mean part):  o < D: sum_i phi_i nu_i,o ;  o >= D: sum_i phi_i nu_i,k nu_i,l  (k <= l, row-major pairs)
+//  kind 1 (B3b, pair part):  o < D: sum_i g_i nu_i,o   ;  o >= D: sum_i g_i z_k z_l + z_l x_k + z_k x_l
+// with phi_i / g_i in record slot `sa` and x_i in slots `sx` + e;  z = nu * il2 (state dimensions).
+template <int EV>
+__device__ __forceinline__ double uni_bwd_moment_lane(int kind, const double* __restrict__ s_rec, int rlen, int rhot,
+                                                      const double* __restrict__ il2, int N, int D, int o, int lane) {
+  const int sa = (kind == 0) ? 2 * EV + 1 : EV, sx = EV + 1;
+  int k = 0, l = 0;
+  if (o >= D) {
+    int w = o - D;
+    while (w >= EV - k) { w -= EV - k; k++; }
+    l = k + w;
   }
-  // otherwise the owner lanes turn their row sums (rho_i, xi_i) into contributions to dS/dm (D) and dS/dQ (E x E)
-  // right away (linear in the partial sums, so per-item flushing is exact); no per-row arrays in shared memory
-  const int D = p.D;
-  double gm[GPMPC_MAX_D], gQ[EV * EV];
-#pragma unroll
-  for (int e = 0; e < EV * EV; e++) gQ[e] = 0.0;
-  {
-    const double* ra = s_rec + (size_t)i0 * rlen;
-    const double* rb = s_rec + (size_t)i1 * rlen;
-    double za[EV], zb[EV], xa[EV], xb[EV];
-#pragma unroll
-    for (int e = 0; e < EV; e++) {
-      za[e] = ra[e] * il2[e]; zb[e] = rb[e] * il2[e];
-      xa[e] = xi0[e] * il2[e]; xb[e] = xi1[e] * il2[e];
-      gm[e] = rho0 * za[e] + rho1 * zb[e];
+  const int so = (o < EV) ? o : rhot + (o - EV);     // record slot of nu_o (state dims in front, the rest in the tail)
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int i = lane; i < N; i += 64) {
+    const double* ra = s_rec + (size_t)i * rlen;
+    const double* rb = ra + (size_t)32 * rlen;        // i + 32 < NP; phi / g are 0 for padded rows
+    if (o < D) {
+      acc0 = fma(ra[sa], ra[so], acc0);
+      acc1 = fma(rb[sa], rb[so], acc1);
+    } else if (kind == 0) {
+      acc0 = fma(ra[sa] * ra[k], ra[l], acc0);
+      acc1 = fma(rb[sa] * rb[k], rb[l], acc1);
+    } else {
+      const double zka = ra[k] * il2[k], zla = ra[l] * il2[l], zkb = rb[k] * il2[k], zlb = rb[l] * il2[l];
+      acc0 = fma(ra[sa] * zka, zla, acc0);
+      acc1 = fma(rb[sa] * zkb, zlb, acc1);
+      acc0 = fma(zla, ra[sx + k], acc0);
+      acc1 = fma(zlb, rb[sx + k], acc1);
+      acc0 = fma(zka, ra[sx + l], acc0);
+      acc1 = fma(zkb, rb[sx + l], acc1);
     }
-#pragma unroll
-    for (int d = EV; d < GPMPC_MAX_D; d++)
-      gm[d] = (d < D) ? (rho0 * ra[rhot + d - EV] + rho1 * rb[rhot + d - EV]) * il2[d] : 0.0;
-#pragma unroll
-    for (int e = 0; e < EV; e++)
-#pragma unroll
-      for (int f = 0; f < EV; f++)
-        gQ[e * EV + f] = rho0 * za[e] * za[f] + za[e] * xa[f] + za[f] * xa[e] +
-                         rho1 * zb[e] * zb[f] + zb[e] * xb[f] + zb[f] * xb[e];
   }
-#pragma unroll
-  for (int d = 0; d < GPMPC_MAX_D; d++)
-    if (d < D) {
-      const double v = warp_sum(gm[d]);
-      if (lane == 0) atomicAdd(s_accGm + d, v);
-    }
-#pragma unroll
-  for (int e = 0; e < EV * EV; e++) {
-    const double v = warp_sum(gQ[e]);
-    if (lane == 0) atomicAdd(s_accGQ + e, v);
-  }
+  return acc0 + acc1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -605,18 +606,23 @@ __device__ inline void uni_stage_adjoint(const RolloutParams& p, int Na, double 
 // ---------------------------------------------------------------------------------------------
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
-template <int EV, bool ROWARR>
+template <int EV>
 __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H, Dc = E + Na;
   const bool premat = p.premat != 0;
-  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, ROWARR, premat);
+  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, premat);
   double* s_pre = sm + L.pre;
   const int oA = 0, oQ = EV * EV, oRi = 2 * EV * EV, odS = 3 * EV * EV, oc = 4 * EV * EV, odet = oc + 1, odmu = oc + 2,
             oda = odmu + EV;
-  double* s_rec = sm + L.rec; double* s_gam = sm + L.gam; double* s_rho = sm + L.rho; double* s_xi = sm + L.xi;
+  double* s_rec = sm + L.rec;
+  // per-CTA global scratch of the sweep's row / column sums (L2 resident): gam[NP], rho[NP], xi[EV][NP]
+  double* g_gam = p.ws_uni + (size_t)blockIdx.x * NP * (2 + EV);
+  double* g_rho = g_gam + NP;
+  double* g_xi = g_rho + NP;
+  const int warp = tid >> 5, nwarps = NT >> 5;
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   double* s2p = sm + L.small2;
@@ -629,6 +635,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
   for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
+  for (int i = tid; i < NP * (2 + EV); i += NT) g_gam[i] = 0.0;   // B3a re-zeroes after every step
   __syncthreads();
   // accumulator layout: [0] unused, [1 .. D] G_m, [1+D .. 1+D+E2) G_Q, then N-pass: Phi_m[D], Phi_A[P]
   const int accGm = 1, accGQ = 1 + D, accPm = 1 + D + EV * EV, accPA = accPm + D;
@@ -688,11 +695,6 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       // ---- B0: model input, shared matrices, adjoint coefficients (thread 0: O(E^3))
       if (tid < D) s_m[tid] = (tid < E) ? mup[tid] : (tid < E + Na ? am[tid - E] : (double)(p.iter_ctrl + t - 1));
       for (int o = tid; o < L.accN + 1; o += NT) s_acc[o] = 0.0;
-      for (int o = tid; o < NP; o += NT) s_gam[o] = 0.0;
-      if (ROWARR) {
-        for (int o = tid; o < NP; o += NT) s_rho[o] = 0.0;
-        for (int o = tid; o < NP * EV; o += NT) s_xi[o] = 0.0;
-      }
       if (tid == 0) {
         s_int[0] = 0;
         double Ai[EV * EV], Rinv[EV * EV], Qm[EV * EV], c, detR;
@@ -792,7 +794,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
           if (d < D) rcd[L.rhot + d - EV] = nu[d];
-        // N pass of the mean part: phi_i = sum_a lb_a,i (h_bar_a + g_bar_a . nu_i^E)
+        // mean part weight phi_i = sum_a e_i beta_a,i (h_bar_a + g_bar_a . nu_i^E), kept in the record's spare slot
         double phi = 0.0;
 #pragma unroll
         for (int a = 0; a < E; a++) {
@@ -801,24 +803,25 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           for (int e = 0; e < EV; e++) w = fma(s_gbar[a * E + e], nu[e], w);
           phi = fma(ei * __ldg(p.betaT + (size_t)i * E + a), w, phi);
         }
-        // reduce phi * an (D) and phi * nu nu^T (P) over the block
-#pragma unroll
-        for (int d = 0; d < GPMPC_MAX_D; d++)
-          if (d < D) {
-            double v = warp_sum(phi * an[d]);
-            if (lane == 0) atomicAdd(s_acc + accPm + d, v);
-          }
-        int w = 0;
-#pragma unroll
-        for (int k = 0; k < EV; k++)
-#pragma unroll
-          for (int l = k; l < EV; l++) {
-            double v = warp_sum(phi * nu[k] * nu[l]);
-            if (lane == 0) atomicAdd(s_acc + accPA + w, v);
-            w++;
-          }
+        rcd[2 * EV + 1] = phi;
       }
       __syncthreads();
+      UNI_CLK(14);
+      // ---- B1b: raw moments sum_i phi_i nu_i,d (D) and sum_i phi_i nu_i,k nu_i,l (P): one warp per output
+      for (int o = warp; o < D + P; o += 2 * nwarps) {
+        const int o2 = o + nwarps;
+        double va = uni_bwd_moment_lane<EV>(0, s_rec, L.rlen, L.rhot, il2, N, D, o, lane);
+        double vb = (o2 < D + P) ? uni_bwd_moment_lane<EV>(0, s_rec, L.rlen, L.rhot, il2, N, D, o2, lane) : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          va += __shfl_xor_sync(0xffffffffu, va, off);
+          vb += __shfl_xor_sync(0xffffffffu, vb, off);
+        }
+        if (lane == 0) {
+          s_acc[accPm + o] = va;             // accPA = accPm + D: the pair moments follow the D first moments
+          if (o2 < D + P) s_acc[accPm + o2] = vb;
+        }
+      }
       UNI_CLK(10);
       // ---- B2: adjoint-weighted N^2 sweep (upper triangle)
       {
@@ -834,49 +837,50 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           const int jend = min(NP, jbeg + p.seg_bwd);
           if (jend <= 64 * I) continue;
           jbeg = max(jbeg, 64 * I);
-          uni_bwd_item<EV, ROWARR>(p, s_rec, L.rlen, L.rhot, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, s_gam,
-                                   s_acc + accGm, s_acc + accGQ, s_rho, s_xi, s_tab);
+          uni_bwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, g_gam, g_rho, g_xi, s_tab);
         }
       }
       __syncthreads();
       UNI_CLK(11);
-      // ---- B3: column sums gam_j -> their share of G_m (D), G_Q (E x E)   [row sums were folded in per item]
-      {
-        double gm[GPMPC_MAX_D], gQ[EV * EV];
+      // ---- B3a: per training point, g_i = gam_i + rho_i and x_i = xi_i * il2 from the scratch (L2 loads: the sums were
+      //           formed by reductions at L2), scratch re-zeroed; they overwrite kap / beta in the record (sweep is done)
+      for (int i = tid; i < NP; i += NT) {
+        double* rc = s_rec + (size_t)i * L.rlen;
+        rc[EV] = __ldcg(g_gam + i) + __ldcg(g_rho + i);
+        g_gam[i] = 0.0;
+        g_rho[i] = 0.0;
 #pragma unroll
-        for (int d = 0; d < GPMPC_MAX_D; d++) gm[d] = 0.0;
+        for (int e = 0; e < EV; e++) {
+          rc[EV + 1 + e] = __ldcg(g_xi + (size_t)e * NP + i) * il2[e];
+          g_xi[(size_t)e * NP + i] = 0.0;
+        }
+      }
+      __syncthreads();
+      UNI_CLK(15);
+      // ---- B3b: G_m (D) and the upper triangle of G_Q (P): one warp per output
+      for (int o = warp; o < D + P; o += 2 * nwarps) {
+        const int o2 = o + nwarps;
+        double va = uni_bwd_moment_lane<EV>(1, s_rec, L.rlen, L.rhot, il2, N, D, o, lane);
+        double vb = (o2 < D + P) ? uni_bwd_moment_lane<EV>(1, s_rec, L.rlen, L.rhot, il2, N, D, o2, lane) : 0.0;
 #pragma unroll
-        for (int e = 0; e < EV * EV; e++) gQ[e] = 0.0;
-        for (int i = tid; i < N; i += NT) {
-          const double g = s_gam[i] + (ROWARR ? s_rho[i] : 0.0);
-          const double* rc = s_rec + (size_t)i * L.rlen;
-          double z[EV];
+        for (int off = 16; off > 0; off >>= 1) {
+          va += __shfl_xor_sync(0xffffffffu, va, off);
+          vb += __shfl_xor_sync(0xffffffffu, vb, off);
+        }
+        if (lane == 0) {
 #pragma unroll
-          for (int e = 0; e < EV; e++) { z[e] = rc[e] * il2[e]; gm[e] = fma(g, z[e], gm[e]); }
-          if (ROWARR) {
-#pragma unroll
-            for (int e = 0; e < EV; e++) {
-              const double xe = s_xi[(size_t)i * EV + e] * il2[e];
-#pragma unroll
-              for (int f = 0; f < EV; f++) { gQ[f * EV + e] = fma(z[f], xe, gQ[f * EV + e]); gQ[e * EV + f] = fma(z[f], xe, gQ[e * EV + f]); }
+          for (int h2 = 0; h2 < 2; h2++) {
+            const int oo = h2 ? o2 : o;
+            const double val = h2 ? vb : va;
+            if (oo < D) s_acc[accGm + oo] = val * il2[oo];
+            else if (oo < D + P) {
+              int k = 0, w = oo - D;
+              while (w >= EV - k) { w -= EV - k; k++; }
+              const int l = k + w;
+              s_acc[accGQ + k * EV + l] = val;
+              s_acc[accGQ + l * EV + k] = val;
             }
           }
-#pragma unroll
-          for (int d = EV; d < GPMPC_MAX_D; d++)
-            if (d < D) gm[d] = fma(g * il2[d], rc[L.rhot + d - EV], gm[d]);
-#pragma unroll
-          for (int e = 0; e < EV; e++)
-#pragma unroll
-            for (int f = 0; f < EV; f++) gQ[e * EV + f] = fma(g * z[e], z[f], gQ[e * EV + f]);
-        }
-        for (int d = 0; d < D; d++) {
-          double v = warp_sum(gm[d]);
-          if (lane == 0) atomicAdd(s_acc + accGm + d, v);
-        }
-#pragma unroll
-        for (int e = 0; e < EV * EV; e++) {
-          double v = warp_sum(gQ[e]);
-          if (lane == 0) atomicAdd(s_acc + accGQ + e, v);
         }
       }
       __syncthreads();
@@ -912,7 +916,12 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
             sp_bar[i * E + k] += 0.5 * RQ[i * E + k] - v * Wd[k] + detR_bar * detR * s_Rinv[k * E + i] * Wd[k];
           }
         // mean part: m_bar += Phi_m - sum_a h_a g_bar_a (state dims) ; A_bar += -1/2 Phi_A
-        for (int d = 0; d < D; d++) m_bar[d] += s_acc[accPm + d];
+        for (int d = 0; d < D; d++) {   // Phi_m = A (sum_i phi_i nu_i) on the state block, il2 * (...) elsewhere
+          double v;
+          if (d < EV) { v = 0.0; for (int f = 0; f < EV; f++) v += s_A[d * EV + f] * s_acc[accPm + f]; }
+          else v = il2[d] * s_acc[accPm + d];
+          m_bar[d] += v;
+        }
         for (int a = 0; a < E; a++) {
           const double h = rec[RL.offH + a];
           for (int e = 0; e < E; e++) m_bar[e] -= h * s_gbar[a * E + e];
@@ -986,14 +995,10 @@ template <int EV>
 cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem,
                                 cudaStream_t st) {
   cudaError_t e;
-  if (bwd && p.rowarr) {
-    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (bwd) {
+    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uniform_bwd_kernel<EV, true><<<grid, threads, smem, st>>>(p, grad);
-  } else if (bwd) {
-    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    uniform_bwd_kernel<EV, false><<<grid, threads, smem, st>>>(p, grad);
+    uniform_bwd_kernel<EV><<<grid, threads, smem, st>>>(p, grad);
   } else {
     e = cudaFuncSetAttribute(uniform_fwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -6,15 +6,13 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, rlen, rhot, gam, rho, xi, pre, prelen, out, nOut, part, partlen;
+  int rec, rlen, rhot, pre, prelen, out, nOut, part, partlen;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
-// bwd=false: forward kernel; bwd=true: reverse-sweep kernel (needs rho/gam/xi arrays)
-// rowarr (reverse sweep only): keep per-row partial sums rho_i, xi_i in shared memory (fast path when it fits)
+// bwd=false: forward kernel; bwd=true: reverse-sweep kernel (its row / column sums live in a global per-CTA scratch)
 // premat (reverse sweep only): per-step small matrices + stage-cost adjoints precomputed for all H steps in parallel
-HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool rowarr = false,
-                             bool premat = false) {
+HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat = false) {
   UniLayout L;
   const int E = EV, P = E * (E + 1) / 2;
   int o = 0;
@@ -24,9 +22,6 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.rhot = (EV + 1 + E + 1) & ~1;
   L.rlen = L.rhot + (bwd ? ((D - EV + 1) & ~1) : 0);
   L.rec = o; o += NP * L.rlen;
-  L.gam = o; if (bwd) o += NP;       // column sums of the triangular sweep
-  L.rho = o; L.xi = o;
-  if (bwd && rowarr) { L.rho = o; o += NP; L.xi = o; o += NP * EV; }
   L.prelen = (4 * EV * EV + 2 + EV + Na + 1) & ~1;   // A, Q, Rinv, dS (E x E each), c, detR, dmu (E), da (Na)
   L.pre = o; if (bwd && premat) o += H * L.prelen;
   L.nOut = 1 + D;
