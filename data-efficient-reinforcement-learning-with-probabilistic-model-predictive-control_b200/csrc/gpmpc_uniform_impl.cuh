@@ -134,34 +134,33 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   }
 }
 
-// Lane partial of one mean-part moment over the training points (rows lane, lane + 32, ...):
-//   o = a * nOut + q :  q = 0: h_a = sum_i e_i beta_a,i ;  q = 1 + d: g_a,d = sum_i e_i beta_a,i nu_i,d
-// (gp_model.py:138-153).  e_i sits in the spare slot of the hot-loop record; nu of the action / time dimensions is
-// rebuilt from x.
+// Mean-part moments (gp_model.py:138-153), lane-per-output: lane o = a * nOut + q of every warp sums its output over the
+// warp's slice of training points,
+//   q = 0: h_a = sum_i e_i beta_a,i ;  q = 1 + d: g_a,d = sum_i e_i beta_a,i nu_i,d ,
+// reading the hot-loop records as multicast LDS (all lanes: the same record, different slots); e_i sits in the
+// record's spare slot, nu of the action / time dimensions in its tail.  No shuffles, no atomics: the per-warp
+// partial rows s_wp[warp][o] are added up by the consumer (P4).
 template <int EV>
-__device__ __forceinline__ double uni_moment_lane(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
-                                                  const double* __restrict__ s_m, int o, int nOut, int lane) {
-  const int a = o / nOut, q = o - a * nOut, d = q - 1;
-  const int N = p.N, D = p.D;
-  double acc0 = 0.0, acc1 = 0.0;
-  for (int i = lane; i < N; i += 64) {
-    const int i1 = i + 32;
-    const double* ra = s_rec + (size_t)i * rlen;
-    const double* rb = s_rec + (size_t)i1 * rlen;     // i1 < NP always (NP is a multiple of 64); e_i = 0 for i >= N
-    const double la = ra[EV + 1 + a] * ra[2 * EV + 1];
-    const double lb = rb[EV + 1 + a] * rb[2 * EV + 1];
-    double fa = 1.0, fb = 1.0;
-    if (q > 0) {
-      if (d < EV) { fa = ra[d]; fb = rb[d]; }
-      else {
-        fa = __ldg(p.x + (size_t)i * D + d) - s_m[d];
-        fb = (i1 < N) ? __ldg(p.x + (size_t)i1 * D + d) - s_m[d] : 0.0;
+__device__ __forceinline__ void uni_moments_slice(const double* __restrict__ s_rec, int rlen, int rhot, int nOut,
+                                                  int ibeg, int iend, int lane, double* __restrict__ s_wp_row) {
+  const int nTot = EV * nOut;
+  for (int ob = 0; ob < nTot; ob += 32) {
+    const int o = ob + lane;
+    const bool act = o < nTot;
+    const int a = act ? o / nOut : 0, q = act ? o - a * nOut : 0, d = q - 1;
+    const int sb = EV + 1 + a, sd = (d < 0) ? 0 : (d < EV ? d : rhot + d - EV);   // slot of nu_d (tail: action / time dims)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i0 = ibeg; i0 < iend; i0 += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double* r = s_rec + (i0 + k) * rlen;
+        const double lb = r[sb] * r[2 * EV + 1];
+        const double f = (q == 0) ? 1.0 : r[sd];
+        acc[k] = fma(lb, f, acc[k]);
       }
     }
-    acc0 = fma(la, fa, acc0);
-    acc1 = fma(lb, fb, acc1);
+    if (act) s_wp_row[o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   }
-  return acc0 + acc1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -180,10 +179,15 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
   int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
-  double* s_part = sm + L.part;
+  double* s_part = sm + L.part; double* s_wp = sm + L.wp; double* s_S = sm + L.S; double* s_cst = sm + L.cst;
   const int nOut = L.nOut, warp = tid >> 5, nwarps = NT >> 5;
   const UniRecLayout RL = uni_rec_layout(E);
-  const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
+  // cost description staged in shared memory (the stage cost is on the serial path of every step)
+  for (int i = tid; i < E + Na; i += NT) s_cst[i] = p.c_target[i];
+  for (int i = tid; i < (E + Na) * (E + Na); i += NT) s_cst[GPMPC_MAX_D + i] = p.c_W[i];
+  for (int i = tid; i < E * E; i += NT) s_cst[GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + i] = p.c_WT[i];
+  const CostView cv{s_cst, s_cst + GPMPC_MAX_D, s_cst + GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D, p.c_smin, p.c_smax,
+                    p.kappa, p.use_constraints};
   const double* il2 = p.il2;            // row 0 (all rows equal)
   const double s2 = p.s2[0];
   for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
@@ -289,23 +293,16 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 #pragma unroll
         for (int a = 0; a < E; a++) rec[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
         rec[2 * EV + 1] = ei;   // spare slot of the (even-length) record
+#pragma unroll
+        for (int d = EV; d < GPMPC_MAX_D; d++)
+          if (d < D) rec[L.rhot + d - EV] = nu[d];
       }
       __syncthreads();
       UNI_CLK(4);
-      // ---- P1b: mean-part moments h_a, g_a: one warp per output (two at a time), lanes over the training points
-      for (int o = warp; o < E * nOut; o += 2 * nwarps) {
-        const int o2 = o + nwarps;
-        double va = uni_moment_lane<EV>(p, s_rec, L.rlen, s_m, o, nOut, lane);
-        double vb = (o2 < E * nOut) ? uni_moment_lane<EV>(p, s_rec, L.rlen, s_m, o2, nOut, lane) : 0.0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          va += __shfl_xor_sync(0xffffffffu, va, off);
-          vb += __shfl_xor_sync(0xffffffffu, vb, off);
-        }
-        if (lane == 0) {
-          s_out[o] = va;
-          if (o2 < E * nOut) s_out[o2] = vb;
-        }
+      // ---- P1b: mean-part moments h_a, g_a (lane per output, warp per slice of points; summed over warps in P4)
+      {
+        const int per = NP / nwarps;
+        uni_moments_slice<EV>(s_rec, L.rlen, L.rhot, nOut, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
       }
       UNI_CLK(1);
       // ---- P3: one N x N sweep for all pairs
@@ -323,64 +320,92 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
       }
       __syncthreads();
       UNI_CLK(2);
-      // ---- P4: mean, V, S, recurrence
-      if (tid == 0) {
+      // ---- P4: mean, V, S, recurrence (gp_model.py:150-180, :92-99): warp 0, one small stage per __syncwarp
+      if (warp == 0) {
         const double c = s_misc[0], detR = s_misc[1], rs = 1.0 / sqrt(detR);
         const bool bad = s_int[1] != 0;
-        double S[GPMPC_MAX_EV * GPMPC_MAX_EV];
         double* rec = p.records ? p.records + ((size_t)cand * H + (t - 1)) * RL.size : nullptr;
-        for (int a = 0; a < E; a++) {
-          const double* out = s_out + a * nOut;
-          const double h = out[0];
-          const double* g = out + 1;
-          s_M[a] = c * h;
-          for (int e = 0; e < EV; e++) {
-            double v = 0.0;
-            for (int f = 0; f < EV; f++) v += s_A[e * EV + f] * g[f];
-            s_V[a * D + e] = c * v;
-          }
-          for (int d = EV; d < D; d++) s_V[a * D + d] = c * g[d] * il2[d];
-          if (rec) {
-            rec[RL.offM + a] = s_M[a];
-            rec[RL.offH + a] = h;
-            for (int e = 0; e < E; e++) { rec[RL.offV + a * E + e] = s_V[a * D + e]; rec[RL.offG + a * E + e] = g[e]; }
-          }
+        // A: add up the per-warp partial rows
+        for (int o = lane; o < E * nOut; o += 32) {
+          double v = 0.0;
+          for (int w = 0; w < nwarps; w++) v += s_wp[w * L.wplen + o];
+          s_out[o] = v;
         }
-        for (int k = 0; k <= P; k++) {
+        for (int k = lane; k <= P; k += 32) {
           double v = 0.0;
           for (int w = 0; w < nwarps; w++) v += s_part[w * L.partlen + k];
           s_acc[k] = v;
         }
-        const double trc = s_acc[P];
-        int pr = 0;
-        for (int a = 0; a < E; a++)
-          for (int b = a; b < E; b++) {
-            const double Sraw = s2 * s2 * (s_acc[pr] - (a == b ? trc : 0.0));
-            if (rec) rec[RL.offS + pr] = Sraw;
-            double v = Sraw * rs - s_M[a] * s_M[b] + (a == b ? s2 : 0.0);
-            if (bad) v = nan("");
-            S[a * E + b] = v;
-            S[b * E + a] = v;
-            pr++;
+        __syncwarp();
+        // B: M_a = c h_a ; V_a = c A g_a (state block), c g_a il2 (action / time dims)
+        for (int o = lane; o < E * D; o += 32) {
+          const int a = o / D, d = o - a * D;
+          const double* g = s_out + a * nOut + 1;
+          double v;
+          if (d < EV) {
+            v = 0.0;
+#pragma unroll
+            for (int f = 0; f < EV; f++) v = fma(s_A[d * EV + f], g[f], v);
+          } else {
+            v = g[d] * il2[d];
           }
-        double sv[GPMPC_MAX_EV * GPMPC_MAX_EV], sn[GPMPC_MAX_EV * GPMPC_MAX_EV];
-        for (int e = 0; e < E; e++)
-          for (int a = 0; a < E; a++) {
-            double v = 0.0;
-            for (int k = 0; k < E; k++) v += s_s[e * E + k] * s_V[a * D + k];
-            sv[e * E + a] = v;
-          }
-        for (int e = 0; e < E; e++)
-          for (int f = 0; f < E; f++) sn[e * E + f] = S[e * E + f] + s_s[e * E + f] + sv[e * E + f] + sv[f * E + e];
-        for (int e = 0; e < E; e++) {
-          double v = s_mu[e] + s_M[e];
-          if (bad) v = nan("");
-          s_mu[e] = v;
-          p.states_mu[((size_t)cand * (H + 1) + t) * E + e] = v;
+          v *= c;
+          s_V[o] = v;
+          if (rec && d < E) { rec[RL.offV + a * E + d] = v; rec[RL.offG + a * E + d] = g[d]; }
         }
-        for (int e = 0; e < E * E; e++) {
-          s_s[e] = sn[e];
-          p.states_var[((size_t)cand * (H + 1) + t) * E * E + e] = sn[e];
+        if (lane < E) {
+          const double h = s_out[lane * nOut];
+          s_M[lane] = c * h;
+          if (rec) { rec[RL.offM + lane] = c * h; rec[RL.offH + lane] = h; }
+        }
+        __syncwarp();
+        // C: S_ab (pairs) and s V^T
+        const double trc = s_acc[P];
+        for (int pr = lane; pr < P; pr += 32) {
+          int a = 0, w = pr;
+          while (w >= E - a) { w -= E - a; a++; }
+          const int b = a + w;
+          const double Sraw = s2 * s2 * (s_acc[pr] - (a == b ? trc : 0.0));
+          if (rec) rec[RL.offS + pr] = Sraw;
+          double v = Sraw * rs - s_M[a] * s_M[b] + (a == b ? s2 : 0.0);
+          if (bad) v = nan("");
+          s_S[a * E + b] = v;
+          s_S[b * E + a] = v;
+        }
+        for (int o = lane; o < E * E; o += 32) {
+          const int e = o / E, a = o - e * E;
+          double v = 0.0;
+#pragma unroll
+          for (int k = 0; k < E; k++) v = fma(s_s[e * E + k], s_V[a * D + k], v);
+          s_S[E * E + o] = v;            // sv[e][a]
+        }
+        __syncwarp();
+        // D: recurrence
+        constexpr int NR = (E * E + 31) / 32;
+        double sn[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          const int o = lane + 32 * r;
+          sn[r] = 0.0;
+          if (o < E * E) {
+            const int e = o / E, f = o - e * E;
+            sn[r] = s_S[o] + s_s[o] + s_S[E * E + o] + s_S[E * E + f * E + e];
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          const int o = lane + 32 * r;
+          if (o < E * E) {
+            s_s[o] = sn[r];
+            p.states_var[((size_t)cand * (H + 1) + t) * E * E + o] = sn[r];
+          }
+        }
+        if (lane < E) {
+          double v = s_mu[lane] + s_M[lane];
+          if (bad) v = nan("");
+          s_mu[lane] = v;
+          p.states_mu[((size_t)cand * (H + 1) + t) * E + lane] = v;
         }
       }
       __syncthreads();
@@ -509,42 +534,48 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   for (int e = 0; e < EV; e++) { atomicAdd(g_xi + (size_t)e * NP + i0, xi0[e]); atomicAdd(g_xi + (size_t)e * NP + i1, xi1[e]); }
 }
 
-// Lane partials of the reverse sweep's O(N) reductions (rows lane, lane + 32, ...), one output per call:
+// O(N) reductions of the reverse sweep, lane-per-output (see uni_moments_slice): lane o of every warp sums its output
+// over the warp's slice of training points; the per-warp partial rows are added up by the consumer.
 //  kind 0 (B1b, mean part):  o < D: sum_i phi_i nu_i,o ;  o >= D: sum_i phi_i nu_i,k nu_i,l  (k <= l, row-major pairs)
 //  kind 1 (B3b, pair part):  o < D: sum_i g_i nu_i,o   ;  o >= D: sum_i g_i z_k z_l + z_l x_k + z_k x_l
-// with phi_i / g_i in record slot `sa` and x_i in slots `sx` + e;  z = nu * il2 (state dimensions).
+// with phi_i in the record's spare slot, g_i / x_i in the kap / beta slots (B3a);  z = nu * il2 (state dimensions).
 template <int EV>
-__device__ __forceinline__ double uni_bwd_moment_lane(int kind, const double* __restrict__ s_rec, int rlen, int rhot,
-                                                      const double* __restrict__ il2, int N, int D, int o, int lane) {
+__device__ __forceinline__ void uni_bwd_moments_slice(int kind, const double* __restrict__ s_rec, int rlen, int rhot,
+                                                      const double* __restrict__ il2, int D, int ibeg, int iend,
+                                                      int lane, double* __restrict__ s_wp_row) {
+  constexpr int P = EV * (EV + 1) / 2;
   const int sa = (kind == 0) ? 2 * EV + 1 : EV, sx = EV + 1;
-  int k = 0, l = 0;
-  if (o >= D) {
-    int w = o - D;
-    while (w >= EV - k) { w -= EV - k; k++; }
-    l = k + w;
-  }
-  const int so = (o < EV) ? o : rhot + (o - EV);     // record slot of nu_o (state dims in front, the rest in the tail)
-  double acc0 = 0.0, acc1 = 0.0;
-  for (int i = lane; i < N; i += 64) {
-    const double* ra = s_rec + (size_t)i * rlen;
-    const double* rb = ra + (size_t)32 * rlen;        // i + 32 < NP; phi / g are 0 for padded rows
-    if (o < D) {
-      acc0 = fma(ra[sa], ra[so], acc0);
-      acc1 = fma(rb[sa], rb[so], acc1);
-    } else if (kind == 0) {
-      acc0 = fma(ra[sa] * ra[k], ra[l], acc0);
-      acc1 = fma(rb[sa] * rb[k], rb[l], acc1);
-    } else {
-      const double zka = ra[k] * il2[k], zla = ra[l] * il2[l], zkb = rb[k] * il2[k], zlb = rb[l] * il2[l];
-      acc0 = fma(ra[sa] * zka, zla, acc0);
-      acc1 = fma(rb[sa] * zkb, zlb, acc1);
-      acc0 = fma(zla, ra[sx + k], acc0);
-      acc1 = fma(zlb, rb[sx + k], acc1);
-      acc0 = fma(zka, ra[sx + l], acc0);
-      acc1 = fma(zkb, rb[sx + l], acc1);
+  for (int ob = 0; ob < D + P; ob += 32) {
+    const int o = ob + lane;
+    const bool act = o < D + P, pairo = act && o >= D;
+    int k = 0, l = 0;
+    if (pairo) {
+      int w = o - D;
+      while (w >= EV - k) { w -= EV - k; k++; }
+      l = k + w;
     }
+    const int so = pairo ? k : ((act && o >= EV) ? rhot + (o - EV) : (act ? o : 0));   // slot of nu_o / nu_k
+    const double ik = il2[k], il = il2[l];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i0 = ibeg; i0 < iend; i0 += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double* r = s_rec + (i0 + q) * rlen;
+        const double wgt = r[sa], n1 = r[so];
+        if (!pairo) {
+          acc[q] = fma(wgt, n1, acc[q]);
+        } else if (kind == 0) {
+          acc[q] = fma(wgt * n1, r[l], acc[q]);
+        } else {
+          const double zk = n1 * ik, zl = r[l] * il;
+          acc[q] = fma(wgt * zk, zl, acc[q]);
+          acc[q] = fma(zl, r[sx + k], acc[q]);
+          acc[q] = fma(zk, r[sx + l], acc[q]);
+        }
+      }
+    }
+    if (act) s_wp_row[o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   }
-  return acc0 + acc1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -623,6 +654,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   double* g_rho = g_gam + NP;
   double* g_xi = g_rho + NP;
   const int warp = tid >> 5, nwarps = NT >> 5;
+  double* s_wp = sm + L.wp;
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   double* s2p = sm + L.small2;
@@ -807,20 +839,10 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       }
       __syncthreads();
       UNI_CLK(14);
-      // ---- B1b: raw moments sum_i phi_i nu_i,d (D) and sum_i phi_i nu_i,k nu_i,l (P): one warp per output
-      for (int o = warp; o < D + P; o += 2 * nwarps) {
-        const int o2 = o + nwarps;
-        double va = uni_bwd_moment_lane<EV>(0, s_rec, L.rlen, L.rhot, il2, N, D, o, lane);
-        double vb = (o2 < D + P) ? uni_bwd_moment_lane<EV>(0, s_rec, L.rlen, L.rhot, il2, N, D, o2, lane) : 0.0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          va += __shfl_xor_sync(0xffffffffu, va, off);
-          vb += __shfl_xor_sync(0xffffffffu, vb, off);
-        }
-        if (lane == 0) {
-          s_acc[accPm + o] = va;             // accPA = accPm + D: the pair moments follow the D first moments
-          if (o2 < D + P) s_acc[accPm + o2] = vb;
-        }
+      // ---- B1b: raw moments sum_i phi_i nu_i,d (D) and sum_i phi_i nu_i,k nu_i,l (P): lane per output, per-warp rows
+      {
+        const int per = NP / nwarps;
+        uni_bwd_moments_slice<EV>(0, s_rec, L.rlen, L.rhot, il2, D, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
       }
       UNI_CLK(10);
       // ---- B2: adjoint-weighted N^2 sweep (upper triangle)
@@ -842,6 +864,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       }
       __syncthreads();
       UNI_CLK(11);
+      for (int o = tid; o < D + P; o += NT) {   // B1b's per-warp rows -> raw moments (accPA = accPm + D: pairs follow)
+        double v = 0.0;
+        for (int w = 0; w < nwarps; w++) v += s_wp[w * L.wplen + o];
+        s_acc[accPm + o] = v;
+      }
       // ---- B3a: per training point, g_i = gam_i + rho_i and x_i = xi_i * il2 from the scratch (L2 loads: the sums were
       //           formed by reductions at L2), scratch re-zeroed; they overwrite kap / beta in the record (sweep is done)
       for (int i = tid; i < NP; i += NT) {
@@ -857,30 +884,22 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       }
       __syncthreads();
       UNI_CLK(15);
-      // ---- B3b: G_m (D) and the upper triangle of G_Q (P): one warp per output
-      for (int o = warp; o < D + P; o += 2 * nwarps) {
-        const int o2 = o + nwarps;
-        double va = uni_bwd_moment_lane<EV>(1, s_rec, L.rlen, L.rhot, il2, N, D, o, lane);
-        double vb = (o2 < D + P) ? uni_bwd_moment_lane<EV>(1, s_rec, L.rlen, L.rhot, il2, N, D, o2, lane) : 0.0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          va += __shfl_xor_sync(0xffffffffu, va, off);
-          vb += __shfl_xor_sync(0xffffffffu, vb, off);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int h2 = 0; h2 < 2; h2++) {
-            const int oo = h2 ? o2 : o;
-            const double val = h2 ? vb : va;
-            if (oo < D) s_acc[accGm + oo] = val * il2[oo];
-            else if (oo < D + P) {
-              int k = 0, w = oo - D;
-              while (w >= EV - k) { w -= EV - k; k++; }
-              const int l = k + w;
-              s_acc[accGQ + k * EV + l] = val;
-              s_acc[accGQ + l * EV + k] = val;
-            }
-          }
+      // ---- B3b: G_m (D) and the upper triangle of G_Q (P): lane per output, per-warp rows
+      {
+        const int per = NP / nwarps;
+        uni_bwd_moments_slice<EV>(1, s_rec, L.rlen, L.rhot, il2, D, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
+      }
+      __syncthreads();
+      for (int o = tid; o < D + P; o += NT) {
+        double v = 0.0;
+        for (int w = 0; w < nwarps; w++) v += s_wp[w * L.wplen + o];
+        if (o < D) s_acc[accGm + o] = v * il2[o];
+        else {
+          int k = 0, w = o - D;
+          while (w >= EV - k) { w -= EV - k; k++; }
+          const int l = k + w;
+          s_acc[accGQ + k * EV + l] = v;
+          s_acc[accGQ + l * EV + k] = v;
         }
       }
       __syncthreads();

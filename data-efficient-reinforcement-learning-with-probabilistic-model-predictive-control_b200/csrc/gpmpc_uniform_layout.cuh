@@ -6,7 +6,7 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, rlen, rhot, pre, prelen, out, nOut, part, partlen;
+  int rec, rlen, rhot, pre, prelen, out, nOut, part, partlen, wp, wplen, S, cst;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
@@ -18,9 +18,9 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   int o = 0;
   // hot-loop record per training point j: { nu_j[0..EV), kap_j, beta_j[0..E) } padded to an even length so that
   // every lane fetches it with (rlen/2) broadcast LDS.128
-  // (the reverse sweep appends the action/time dims of nu, needed by its dS/dm reductions)
+  // (followed by the action/time dims of nu, needed by the O(N) reductions that read the records)
   L.rhot = (EV + 1 + E + 1) & ~1;
-  L.rlen = L.rhot + (bwd ? ((D - EV + 1) & ~1) : 0);
+  L.rlen = L.rhot + ((D - EV + 1) & ~1);
   L.rec = o; o += NP * L.rlen;
   L.prelen = (4 * EV * EV + 2 + EV + Na + 1) & ~1;   // A, Q, Rinv, dS (E x E each), c, detR, dmu (E), da (Na)
   L.pre = o; if (bwd && premat) o += H * L.prelen;
@@ -29,6 +29,11 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   // per-warp accumulator rows of the forward sweep (P + 1 sums, padded to the 16-wide halving reduction), 8 warps max
   L.partlen = ((P + 1) + 15) & ~15;
   L.part = o; if (!bwd) o += 8 * L.partlen;
+  // per-warp partial rows of the O(N) reductions (lane per output): forward E (1 + D) outputs, reverse sweep D + P
+  L.wplen = bwd ? (D + P) : (E * L.nOut);
+  L.wp = o; o += 8 * L.wplen;
+  L.S = o; o += 2 * E * E;          // S and s V^T of the recurrence stage
+  L.cst = o; o += GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + GPMPC_MAX_EV * GPMPC_MAX_EV;   // target, W, WT
   L.m = o; o += GPMPC_MAX_D;
   L.s = o; o += EV * EV;
   L.mu = o; o += GPMPC_MAX_EV;
