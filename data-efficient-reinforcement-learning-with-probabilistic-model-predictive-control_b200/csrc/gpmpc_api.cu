@@ -46,7 +46,7 @@ struct gpmpc_handle {
   DevBuf c_target, c_W, c_WT, c_smin, c_smax;
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
-  DevBuf dbg_clk, ws_uni;
+  DevBuf dbg_clk, ws_uni, queue;
   DevBuf ws_kk, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
   long long launches = 0;
   bool timing = false;
@@ -155,7 +155,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
-                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni};
+                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -276,7 +276,7 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
   p.seg_bwd = 64;
   if (uniform) {
     p.group = 1;
-    p.seg = 256;
+    p.seg = 32;   // forward sweep: columns per chunk of the static tile-triangle split (divides 64)
     *smem = 0;
     *grid = 0;
     return GPMPC_OK;
@@ -396,14 +396,23 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     int thr_f, grid_f, thr_b, grid_b;
     plan(smf, &thr_f, &grid_f, "GPMPC_UNI_FWD_THREADS", "GPMPC_UNI_FWD_CTAS");
     plan(smb, &thr_b, &grid_b, "GPMPC_UNI_BWD_THREADS", "GPMPC_UNI_BWD_CTAS");
-    if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg = v; }
+    {  // small training sets: finer chunks so that every warp of the forward sweep gets a run
+      const int nrb = h->NP / 64, nw = thr_f / 32;
+      while (p.seg > 8 && (64 / p.seg) * nrb * (nrb + 1) / 2 < 2 * nw) p.seg /= 2;
+    }
+    if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) p.seg = v; }
     if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg_bwd = v; }
     const bool dbg = getenv("GPMPC_DEBUG_CLOCKS") != nullptr;   // tuning aid: per-phase cycles of CTA 0 on stderr
     if (dbg) {
-      CU(h->dbg_clk.ensure(sizeof(long long) * 16));
-      CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * 16, st));
+      CU(h->dbg_clk.ensure(sizeof(long long) * (16 + 4 * 2048)));
+      CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * (16 + 4 * 2048), st));
       p.dbg_clk = h->dbg_clk.as<long long>();
     }
+    CU(h->queue.ensure(sizeof(int) * (2 + 512)));
+    CU(cudaMemsetAsync(h->queue.ptr, 0, sizeof(int) * (2 + 512), st));
+    p.queue = h->queue.as<int>();
+    p.stagger = 0;
+    if (const char* e = getenv("GPMPC_UNI_STAGGER")) { int v = atoi(e); if (v >= 0) p.stagger = v; }
     if (h->timing) CU(cudaEventRecord(h->ev[0], st));
     CU(launch_uniform(E, false, p, nullptr, grid_f, thr_f, smf, st));
     h->launches += 1;
@@ -418,9 +427,30 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       if (h->timing) { CU(cudaEventRecord(h->ev[3], st)); h->ev_bwd = true; }
     }
     if (dbg) {
-      long long c[16];
+      static long long c[16 + 4 * 2048];
       CU(cudaMemcpyAsync(c, h->dbg_clk.ptr, sizeof(c), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
+      for (int k = 0; k < (want_grad ? 2 : 1); k++) {   // per-CTA life: cycles, wall time, start skew
+        const long long* d = c + 16 + 4 * 1024 * k;
+        const int g = k ? grid_b : grid_f;
+        if (g > 1024) continue;
+        long long cmin = d[0], cmax = d[0], nmin = d[1], nmax = d[1], t0min = d[3], endmax = d[3] + d[1];
+        double csum = 0, nsum = 0;
+        int imax = 0;
+        for (int i = 0; i < g; i++) {
+          const long long* q = d + 4 * i;
+          if (q[0] < cmin) cmin = q[0];
+          if (q[0] > cmax) cmax = q[0];
+          if (q[1] < nmin) nmin = q[1];
+          if (q[1] > nmax) { nmax = q[1]; imax = i; }
+          if (q[3] < t0min) t0min = q[3];
+          if (q[3] + q[1] > endmax) endmax = q[3] + q[1];
+          csum += (double)q[0]; nsum += (double)q[1];
+        }
+        fprintf(stderr, "[gpmpc CTA life %s] grid %d: cycles min %.2fM mean %.2fM max %.2fM | ns min %.2fM mean %.2fM max %.2fM (CTA %d, SM %lld) | mean clock %.0f MHz | first start -> last end %.2f ms\n",
+                k ? "bwd" : "fwd", g, cmin * 1e-6, csum / g * 1e-6, cmax * 1e-6, nmin * 1e-6, nsum / g * 1e-6, nmax * 1e-6, imax,
+                d[4 * imax + 2], csum / nsum * 1e3, (endmax - t0min) * 1e-6);
+      }
       const long long nf = (long long)((B + grid_f - 1) / grid_f) * H, nb = (long long)((B + grid_b - 1) / grid_b) * H;
       fprintf(stderr, "[gpmpc clocks/step, CTA 0] fwd: P0 %lld  P1a %lld  P1b %lld  P3 sweep %lld  P4 %lld | bwd: pre %lld  B0 %lld  B1a %lld  B1b %lld  B2 sweep %lld  B3a %lld  B3b %lld  B4 %lld\n",
               c[0] / nf, c[4] / nf, c[1] / nf, c[2] / nf, c[3] / nf, want_grad ? c[8] / nb : 0, want_grad ? c[9] / nb : 0,

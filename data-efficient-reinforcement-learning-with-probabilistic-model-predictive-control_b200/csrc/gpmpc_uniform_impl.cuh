@@ -22,6 +22,34 @@ namespace gpmpc {
 // tuning aid: thread 0 of CTA 0 adds the cycles since the previous mark to slot k (after a __syncthreads)
 #define UNI_CLK(k) do { if (p.dbg_clk && blockIdx.x == 0 && tid == 0) { const long long c_ = clock64(); p.dbg_clk[k] += c_ - clk_; clk_ = c_; } } while (0)
 
+__device__ __forceinline__ unsigned long long uni_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned uni_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+// tuning aid: every CTA reports {cycles, wall ns, SM id, start ns} of its whole life to dbg_clk[16 + 4 * (off + blockIdx.x)]
+#define UNI_CTA_BEGIN() const long long cta_c0_ = clock64(); const unsigned long long cta_t0_ = uni_globaltimer()
+#define UNI_CTA_END(off) do { if (p.dbg_clk && tid == 0) { long long* d_ = p.dbg_clk + 16 + 4 * ((off) + (size_t)blockIdx.x); \
+    d_[0] = clock64() - cta_c0_; d_[1] = (long long)(uni_globaltimer() - cta_t0_); d_[2] = uni_smid(); d_[3] = (long long)cta_t0_; } } while (0)
+
+// Dynamic scheduling: CTAs draw candidates from a global counter (kernel k = 0 forward, 1 reverse sweep).  SMs differ
+// in speed by up to ~25 % on this workload (distance to the L2 slices), so a static round-robin split leaves the fast
+// SMs idle at the end.  Ends with a barrier; s_int[3] is the hand-over slot.
+__device__ __forceinline__ int uni_next_candidate(const RolloutParams& p, int k, int* s_int, int tid) {
+  if (tid == 0) s_int[3] = atomicAdd(p.queue + k, 1);
+  __syncthreads();
+  const int c = s_int[3];
+  __syncthreads();
+  return c;
+}
+// the second CTA to arrive on an SM waits p.stagger cycles, so that its serial phases fall into its neighbour's sweep
+__device__ __forceinline__ void uni_stagger(const RolloutParams& p, int k, int tid) {
+  if (p.stagger > 0) {
+    if (tid == 0 && atomicAdd(p.queue + 2 + 256 * k + (uni_smid() & 255), 1) % 2 == 1) {
+      const long long c0 = clock64();
+      while (clock64() - c0 < p.stagger) {}
+    }
+    __syncthreads();
+  }
+}
+
 #ifndef UNI_MINB
 #define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
 #endif
@@ -43,6 +71,57 @@ __device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, i
   kap = buf[EV];
 #pragma unroll
   for (int b = 0; b < EV; b++) beta[b] = buf[EV + 1 + b];
+}
+
+// columns [jbeg, jend) of the forward sweep for rows i0, i0 + 32:  r_b,i += Eh_ij beta_b,j ; TR: tr += Eh_ij iK_ij
+template <int EV, bool TR>
+__device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const double* __restrict__ s_rec, int rlen, int i0,
+                                             int jbeg, int jend, const double (&u0)[EV], const double (&u1)[EV],
+                                             double kr0, double kr1, double (&r0)[EV], double (&r1)[EV], double& trOut,
+                                             unsigned s_tab) {
+  constexpr int E = EV;
+  const int NP = p.NP;
+  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
+  double tr = 0.0, tr2 = 0.0;
+#pragma unroll 2
+  for (int j = jbeg; j < jend; j += 2) {   // 2 columns x 2 rows = 4 independent chains per warp
+    double na[EV], nb[EV], ba[E], bb[E], ka, kb;
+    uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
+    uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
+    double k0a = 0.0, k1a = 0.0, k0b = 0.0, k1b = 0.0;
+    if (TR) {
+      k0a = __ldg(ik0); k1a = __ldg(ik0 + 32); k0b = __ldg(ik0 + NP); k1b = __ldg(ik0 + NP + 32);
+      ik0 += 2 * (size_t)NP;
+    }
+    double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, ex[4];
+    // serpentine order: every FMA shares one register operand with its predecessor (operand-reuse cache; a DFMA
+    // with three fresh register operands issues at 2/3 rate on B200, tools/micro/dfma_operands.cu)
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      t[0] = fma(u0[e], na[e], t[0]);
+      t[1] = fma(u1[e], na[e], t[1]);
+      t[3] = fma(u1[e], nb[e], t[3]);
+      t[2] = fma(u0[e], nb[e], t[2]);
+    }
+    exp2s_x4(t, ex, s_tab);
+#pragma unroll
+    for (int b = 0; b < E; b++) {
+      if (b & 1) { r1[b] = fma(ex[1], ba[b], r1[b]); r0[b] = fma(ex[0], ba[b], r0[b]); }
+      else       { r0[b] = fma(ex[0], ba[b], r0[b]); r1[b] = fma(ex[1], ba[b], r1[b]); }
+    }
+#pragma unroll
+    for (int b = 0; b < E; b++) {
+      if (b & 1) { r1[b] = fma(ex[3], bb[b], r1[b]); r0[b] = fma(ex[2], bb[b], r0[b]); }
+      else       { r0[b] = fma(ex[2], bb[b], r0[b]); r1[b] = fma(ex[3], bb[b], r1[b]); }
+    }
+    if (TR) {
+      tr = fma(ex[0], k0a, tr);
+      tr2 = fma(ex[1], k1a, tr2);
+      tr = fma(ex[2], k0b, tr);
+      tr2 = fma(ex[3], k1b, tr2);
+    }
+  }
+  if (TR) trOut += tr + tr2;
 }
 
 template <int EV>
@@ -70,45 +149,23 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
       u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2[e];
     }
   }
-  double r0[E], r1[E], tr = 0.0;
+  double r0[E], r1[E];
 #pragma unroll
   for (int b = 0; b < E; b++) { r0[b] = 0.0; r1[b] = 0.0; }
-  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
-  double tr2 = 0.0;
-#pragma unroll 2
-  for (int j = jbeg; j < jend; j += 2) {   // 2 columns x 2 rows = 4 independent chains per warp
-    double na[EV], nb[EV], ba[E], bb[E], ka, kb;
-    uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
-    uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
-    const double k0a = __ldg(ik0), k1a = __ldg(ik0 + 32), k0b = __ldg(ik0 + NP), k1b = __ldg(ik0 + NP + 32);
-    ik0 += 2 * (size_t)NP;
-    double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, ex[4];
-    // serpentine order: every FMA shares one register operand with its predecessor (operand-reuse cache; a DFMA
-    // with three fresh register operands issues at 2/3 rate on B200, tools/micro/dfma_operands.cu)
+  // Eh and iK are symmetric, so only tiles on or above the diagonal are swept (columns j >= 64 I):
+  //   S_ab = sum_{tiles above} (X_ab + X_ba) + sum_{diagonal tiles} (X_ab + X_ba) / 2 ,  X_ab = sum_ij beta_a,i Eh_ij beta_b,j
+  //   tr(iK Eh) = 2 sum_{above} + sum_{diagonal}
+  // -- the tile below the diagonal contributes X_ba of its mirror image.  The row sums r_b,i of the diagonal-tile
+  // columns are halved before the columns above it are added.
+  const int jd1 = 64 * I + 64;
+  double trD = 0.0, trU = 0.0;
+  if (jbeg < jd1) {
+    uni_fwd_cols<EV, true>(p, s_rec, rlen, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD, s_tab);
 #pragma unroll
-    for (int e = 0; e < EV; e++) {
-      t[0] = fma(u0[e], na[e], t[0]);
-      t[1] = fma(u1[e], na[e], t[1]);
-      t[3] = fma(u1[e], nb[e], t[3]);
-      t[2] = fma(u0[e], nb[e], t[2]);
-    }
-    exp2s_x4(t, ex, s_tab);
-#pragma unroll
-    for (int b = 0; b < E; b++) {
-      if (b & 1) { r1[b] = fma(ex[1], ba[b], r1[b]); r0[b] = fma(ex[0], ba[b], r0[b]); }
-      else       { r0[b] = fma(ex[0], ba[b], r0[b]); r1[b] = fma(ex[1], ba[b], r1[b]); }
-    }
-#pragma unroll
-    for (int b = 0; b < E; b++) {
-      if (b & 1) { r1[b] = fma(ex[3], bb[b], r1[b]); r0[b] = fma(ex[2], bb[b], r0[b]); }
-      else       { r0[b] = fma(ex[2], bb[b], r0[b]); r1[b] = fma(ex[3], bb[b], r1[b]); }
-    }
-    tr = fma(ex[0], k0a, tr);
-    tr2 = fma(ex[1], k1a, tr2);
-    tr = fma(ex[2], k0b, tr);
-    tr2 = fma(ex[3], k1b, tr2);
+    for (int b = 0; b < E; b++) { r0[b] *= 0.5; r1[b] *= 0.5; }
   }
-  tr += tr2;
+  uni_fwd_cols<EV, true>(p, s_rec, rlen, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU, s_tab);
+  const double tr = fma(2.0, trU, trD);
   // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace: halving reduction of the P + 1 lane partials, 16 at a time, into
   // this warp's private accumulator row (no shared-memory float64 atomics: those are CAS spin loops)
   constexpr int P1 = E * (E + 1) / 2 + 1, NCH = (P1 + 15) / 16;
@@ -118,7 +175,11 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 #pragma unroll
     for (int a = 0; a < E; a++)
 #pragma unroll
-      for (int b = a; b < E; b++) { vals[pr] = bi0[a] * r0[b] + bi1[a] * r1[b]; pr++; }
+      for (int b = a; b < E; b++) {
+        vals[pr] = (a == b) ? 2.0 * (bi0[a] * r0[a] + bi1[a] * r1[a])
+                            : (bi0[a] * r0[b] + bi0[b] * r0[a]) + (bi1[a] * r1[b] + bi1[b] * r1[a]);
+        pr++;
+      }
     vals[pr++] = tr;
 #pragma unroll
     for (; pr < 16 * NCH; pr++) vals[pr] = 0.0;
@@ -194,7 +255,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   __syncthreads();
 
   long long clk_ = clock64();
-  for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
+  UNI_CTA_BEGIN();
+  uni_stagger(p, 0, tid);
+  for (;;) {
+    const int cand = uni_next_candidate(p, 0, s_int, tid);
+    if (cand >= p.B) break;
     if (tid < E) {
       double v = p.obs_mu[(p.per_cand_init ? (size_t)cand * E : 0) + tid];
       s_mu[tid] = v;
@@ -305,17 +370,21 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         uni_moments_slice<EV>(s_rec, L.rlen, L.rhot, nOut, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
       }
       UNI_CLK(1);
-      // ---- P3: one N x N sweep for all pairs
+      // ---- P3: one sweep over the upper tile triangle for all pairs.  Static balanced split: row block I (64 rows)
+      //      holds 2 (nrb - I) chunks of p.seg/... 32 columns from its diagonal on; the chunks of all row blocks, in
+      //      row-major order, are dealt to the warps in equal contiguous runs (a run is cut at row-block boundaries).
       {
-        const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg, nitems = nrb * nseg;
-        for (;;) {
-          int item = 0;
-          if (lane == 0) item = atomicAdd(&s_int[0], 1);
-          item = __shfl_sync(0xffffffffu, item, 0);
-          if (item >= nitems) break;
-          const int I = item / nseg, js = item - I * nseg;
-          const int jbeg = js * p.seg, jend = min(NP, jbeg + p.seg);
-          uni_fwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, I, jbeg, jend, lane, s_part + warp * L.partlen, s_tab);
+        const int CH = p.seg, nrb = NP / 64, cpt = 64 / CH;       // chunks per 64-column tile
+        const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps - 1) / nwarps;
+        int c0 = warp * per;
+        const int c1 = min(T, c0 + per);
+        int I = 0, base = 0;
+        while (c0 < c1) {
+          while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
+          const int ce = min(c1, base + cpt * (nrb - I));
+          uni_fwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base), lane,
+                           s_part + warp * L.partlen, s_tab);
+          c0 = ce;
         }
       }
       __syncthreads();
@@ -428,6 +497,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
     }
     __syncthreads();
   }
+  UNI_CTA_END(0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -673,7 +743,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const int accGm = 1, accGQ = 1 + D, accPm = 1 + D + EV * EV, accPA = accPm + D;
 
   long long clk_ = clock64();
-  for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
+  UNI_CTA_BEGIN();
+  uni_stagger(p, 1, tid);
+  for (;;) {
+    const int cand = uni_next_candidate(p, 1, s_int, tid);
+    if (cand >= p.B) break;
     const double* mus = p.states_mu + (size_t)cand * (H + 1) * E;
     const double* vars = p.states_var + (size_t)cand * (H + 1) * E * E;
     const double* rvs = p.rewards_var + (size_t)cand * (H + 1);
@@ -1008,6 +1082,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
     }
     __syncthreads();
   }
+  UNI_CTA_END(1024);
 }
 
 template <int EV>
