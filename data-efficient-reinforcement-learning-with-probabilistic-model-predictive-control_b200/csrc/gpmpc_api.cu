@@ -273,7 +273,7 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
   p.B = B; p.H = H;
   p.betaT = h->betaT.as<double>();
   p.seg = 256;
-  p.seg_bwd = 64;
+  p.seg_bwd = 32;
   if (uniform) {
     p.group = 1;
     p.seg = 32;   // forward sweep: columns per chunk of the static tile-triangle split (divides 64)
@@ -396,12 +396,13 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     int thr_f, grid_f, thr_b, grid_b;
     plan(smf, &thr_f, &grid_f, "GPMPC_UNI_FWD_THREADS", "GPMPC_UNI_FWD_CTAS");
     plan(smb, &thr_b, &grid_b, "GPMPC_UNI_BWD_THREADS", "GPMPC_UNI_BWD_CTAS");
-    {  // small training sets: finer chunks so that every warp of the forward sweep gets a run
-      const int nrb = h->NP / 64, nw = thr_f / 32;
-      while (p.seg > 8 && (64 / p.seg) * nrb * (nrb + 1) / 2 < 2 * nw) p.seg /= 2;
+    {  // small training sets: finer chunks so that every warp of the sweeps gets a run
+      const int nrb = h->NP / 64;
+      while (p.seg > 8 && (64 / p.seg) * nrb * (nrb + 1) / 2 < 2 * (thr_f / 32)) p.seg /= 2;
+      while (p.seg_bwd > 8 && (64 / p.seg_bwd) * nrb * (nrb + 1) / 2 < 2 * (thr_b / 32)) p.seg_bwd /= 2;
     }
     if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) p.seg = v; }
-    if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v >= 8 && v % 8 == 0) p.seg_bwd = v; }
+    if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) p.seg_bwd = v; }
     const bool dbg = getenv("GPMPC_DEBUG_CLOCKS") != nullptr;   // tuning aid: per-phase cycles of CTA 0 on stderr
     if (dbg) {
       CU(h->dbg_clk.ensure(sizeof(long long) * (16 + 4 * 2048)));

@@ -506,6 +506,69 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 // Row and column sums leave the warp as float64 reductions into the CTA's global scratch (native RED.ADD.F64 at L2,
 // fire and forget); float64 atomics on shared memory are CAS spin loops and cost ~15 % of an item.
 // ---------------------------------------------------------------------------------------------
+// columns [jbeg, jend) (a multiple of 8) of the reverse sweep for rows i0, i0 + 32, with coefficient row vectors p0, p1
+// and trace weight wbar as given (the caller halves them on the diagonal tile)
+template <int EV>
+__device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const double* __restrict__ s_rec, int rlen, int i0,
+                                             int jbeg, int jend, const double (&u0)[EV], const double (&u1)[EV],
+                                             double kr0, double kr1, const double (&p0)[EV], const double (&p1)[EV],
+                                             double wbar, double& rho0, double& rho1, double (&xi0)[EV], double (&xi1)[EV],
+                                             int lane, double* __restrict__ g_gam, unsigned s_tab) {
+  constexpr int E = EV;
+  const int NP = p.NP;
+  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int jp = 0; jp < 4; jp++) {   // pairs of columns: 2 columns x 2 rows = 4 independent chains per warp
+      const int j = j0 + 2 * jp;
+      double na[EV], nb[EV], ba[E], bb[E], ka, kb;
+      uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
+      uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
+      double c[4] = {-wbar * __ldg(ik0), -wbar * __ldg(ik0 + 32), -wbar * __ldg(ik0 + NP), -wbar * __ldg(ik0 + NP + 32)};
+      ik0 += 2 * (size_t)NP;
+#pragma unroll
+      for (int b = 0; b < E; b++) {   // serpentine order (operand-reuse cache, see uni_fwd_cols)
+        c[0] = fma(p0[b], ba[b], c[0]);
+        c[1] = fma(p1[b], ba[b], c[1]);
+        c[3] = fma(p1[b], bb[b], c[3]);
+        c[2] = fma(p0[b], bb[b], c[2]);
+      }
+      double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, w[4];
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+        t[0] = fma(u0[e], na[e], t[0]);
+        t[1] = fma(u1[e], na[e], t[1]);
+        t[3] = fma(u1[e], nb[e], t[3]);
+        t[2] = fma(u0[e], nb[e], t[2]);
+      }
+      exp2s_x4(t, w, s_tab);
+#pragma unroll
+      for (int q = 0; q < 4; q++) w[q] *= c[q];
+      rho0 += w[0] + w[2];
+      rho1 += w[1] + w[3];
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+        if (e & 1) { xi1[e] = fma(w[1], na[e], xi1[e]); xi0[e] = fma(w[0], na[e], xi0[e]); }
+        else       { xi0[e] = fma(w[0], na[e], xi0[e]); xi1[e] = fma(w[1], na[e], xi1[e]); }
+      }
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+        if (e & 1) { xi1[e] = fma(w[3], nb[e], xi1[e]); xi0[e] = fma(w[2], nb[e], xi0[e]); }
+        else       { xi0[e] = fma(w[2], nb[e], xi0[e]); xi1[e] = fma(w[3], nb[e], xi1[e]); }
+      }
+      v[2 * jp] = w[0] + w[1];
+      v[2 * jp + 1] = w[2] + w[3];
+    }
+    int col;
+    double tot = col_reduce8(v, lane, col);
+    if ((lane & 3) == 0) atomicAdd(g_gam + j0 + col, tot);
+  }
+}
+
+// One run of columns [jbeg, jend), jbeg >= 64 I, of row block I.  w is symmetric, and the O(N) reductions that consume
+// the sums (B3b) only need  g_i = rho_i + gam_i  and  sum_i z_i,k xi_i,l + xi_i,k z_i,l : both come out the same if the
+// diagonal tile is swept in full with HALF weights instead of its upper triangle -- no element masks anywhere.
 template <int EV>
 __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
                                              const double* __restrict__ Qm, const double* __restrict__ il2,
@@ -543,61 +606,17 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   double rho0 = 0.0, rho1 = 0.0, xi0[EV], xi1[EV];
 #pragma unroll
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
-  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;
-  for (int j0 = jbeg; j0 < jend; j0 += 8) {
-    const bool masked = (j0 < 64 * I + 64);
-    double v[8];
+  const int jd1 = 64 * I + 64;
+  if (jbeg < jd1) {
 #pragma unroll
-    for (int jp = 0; jp < 4; jp++) {   // pairs of columns: 2 columns x 2 rows = 4 independent chains per warp
-      const int j = j0 + 2 * jp;
-      double na[EV], nb[EV], ba[E], bb[E], ka, kb;
-      uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
-      uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
-      double c[4] = {-wbar * __ldg(ik0), -wbar * __ldg(ik0 + 32), -wbar * __ldg(ik0 + NP), -wbar * __ldg(ik0 + NP + 32)};
-      ik0 += 2 * (size_t)NP;
+    for (int a = 0; a < E; a++) { p0[a] *= 0.5; p1[a] *= 0.5; }
+    uni_bwd_cols<EV>(p, s_rec, rlen, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, p0, p1, 0.5 * wbar, rho0, rho1, xi0, xi1,
+                     lane, g_gam, s_tab);
 #pragma unroll
-      for (int b = 0; b < E; b++) {   // serpentine order (operand-reuse cache, see uni_fwd_item)
-        c[0] = fma(p0[b], ba[b], c[0]);
-        c[1] = fma(p1[b], ba[b], c[1]);
-        c[3] = fma(p1[b], bb[b], c[3]);
-        c[2] = fma(p0[b], bb[b], c[2]);
-      }
-      double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, w[4];
-#pragma unroll
-      for (int e = 0; e < EV; e++) {
-        t[0] = fma(u0[e], na[e], t[0]);
-        t[1] = fma(u1[e], na[e], t[1]);
-        t[3] = fma(u1[e], nb[e], t[3]);
-        t[2] = fma(u0[e], nb[e], t[2]);
-      }
-      exp2s_x4(t, w, s_tab);
-#pragma unroll
-      for (int q = 0; q < 4; q++) w[q] *= c[q];
-      if (masked) {
-        w[0] = (j > i0) ? w[0] : ((j == i0) ? 0.5 * w[0] : 0.0);
-        w[1] = (j > i1) ? w[1] : ((j == i1) ? 0.5 * w[1] : 0.0);
-        w[2] = (j + 1 > i0) ? w[2] : ((j + 1 == i0) ? 0.5 * w[2] : 0.0);
-        w[3] = (j + 1 > i1) ? w[3] : ((j + 1 == i1) ? 0.5 * w[3] : 0.0);
-      }
-      rho0 += w[0] + w[2];
-      rho1 += w[1] + w[3];
-#pragma unroll
-      for (int e = 0; e < EV; e++) {
-        if (e & 1) { xi1[e] = fma(w[1], na[e], xi1[e]); xi0[e] = fma(w[0], na[e], xi0[e]); }
-        else       { xi0[e] = fma(w[0], na[e], xi0[e]); xi1[e] = fma(w[1], na[e], xi1[e]); }
-      }
-#pragma unroll
-      for (int e = 0; e < EV; e++) {
-        if (e & 1) { xi1[e] = fma(w[3], nb[e], xi1[e]); xi0[e] = fma(w[2], nb[e], xi0[e]); }
-        else       { xi0[e] = fma(w[2], nb[e], xi0[e]); xi1[e] = fma(w[3], nb[e], xi1[e]); }
-      }
-      v[2 * jp] = w[0] + w[1];
-      v[2 * jp + 1] = w[2] + w[3];
-    }
-    int col;
-    double tot = col_reduce8(v, lane, col);
-    if ((lane & 3) == 0) atomicAdd(g_gam + j0 + col, tot);
+    for (int a = 0; a < E; a++) { p0[a] *= 2.0; p1[a] *= 2.0; }
   }
+  uni_bwd_cols<EV>(p, s_rec, rlen, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, p0, p1, wbar, rho0, rho1, xi0, xi1, lane,
+                   g_gam, s_tab);
   atomicAdd(g_rho + i0, rho0);
   atomicAdd(g_rho + i1, rho1);
 #pragma unroll
@@ -919,21 +938,20 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         uni_bwd_moments_slice<EV>(0, s_rec, L.rlen, L.rhot, il2, D, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
       }
       UNI_CLK(10);
-      // ---- B2: adjoint-weighted N^2 sweep (upper triangle)
+      // ---- B2: adjoint-weighted sweep over the upper tile triangle (static balanced split as in the forward, P3)
       {
         const double wbar = s_scal[3];
-        const int nrb = NP / 64, nseg = (NP + p.seg_bwd - 1) / p.seg_bwd, nitems = nrb * nseg;
-        for (;;) {
-          int item = 0;
-          if (lane == 0) item = atomicAdd(&s_int[0], 1);
-          item = __shfl_sync(0xffffffffu, item, 0);
-          if (item >= nitems) break;
-          const int I = item / nseg, js = item - I * nseg;
-          int jbeg = js * p.seg_bwd;
-          const int jend = min(NP, jbeg + p.seg_bwd);
-          if (jend <= 64 * I) continue;
-          jbeg = max(jbeg, 64 * I);
-          uni_bwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, s_Om, wbar, I, jbeg, jend, lane, g_gam, g_rho, g_xi, s_tab);
+        const int CH = p.seg_bwd, nrb = NP / 64, cpt = 64 / CH;
+        const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps - 1) / nwarps;
+        int c0 = warp * per;
+        const int c1 = min(T, c0 + per);
+        int I = 0, base = 0;
+        while (c0 < c1) {
+          while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
+          const int ce = min(c1, base + cpt * (nrb - I));
+          uni_bwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, s_Om, wbar, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base),
+                           lane, g_gam, g_rho, g_xi, s_tab);
+          c0 = ce;
         }
       }
       __syncthreads();
@@ -947,13 +965,17 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       //           formed by reductions at L2), scratch re-zeroed; they overwrite kap / beta in the record (sweep is done)
       for (int i = tid; i < NP; i += NT) {
         double* rc = s_rec + (size_t)i * L.rlen;
-        rc[EV] = __ldcg(g_gam + i) + __ldcg(g_rho + i);
+        double xv[EV];
+        const double gv = __ldcg(g_gam + i), rv = __ldcg(g_rho + i);   // all loads first (the stores below may alias)
+#pragma unroll
+        for (int e = 0; e < EV; e++) xv[e] = __ldcg(g_xi + (size_t)e * NP + i);
         g_gam[i] = 0.0;
         g_rho[i] = 0.0;
+        rc[EV] = gv + rv;
 #pragma unroll
         for (int e = 0; e < EV; e++) {
-          rc[EV + 1 + e] = __ldcg(g_xi + (size_t)e * NP + i) * il2[e];
           g_xi[(size_t)e * NP + i] = 0.0;
+          rc[EV + 1 + e] = xv[e] * il2[e];
         }
       }
       __syncthreads();
