@@ -409,11 +409,9 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * (16 + 4 * 2048), st));
       p.dbg_clk = h->dbg_clk.as<long long>();
     }
-    CU(h->queue.ensure(sizeof(int) * (2 + 512)));
-    CU(cudaMemsetAsync(h->queue.ptr, 0, sizeof(int) * (2 + 512), st));
+    CU(h->queue.ensure(sizeof(int) * 2));
+    CU(cudaMemsetAsync(h->queue.ptr, 0, sizeof(int) * 2, st));
     p.queue = h->queue.as<int>();
-    p.stagger = 0;
-    if (const char* e = getenv("GPMPC_UNI_STAGGER")) { int v = atoi(e); if (v >= 0) p.stagger = v; }
     if (h->timing) CU(cudaEventRecord(h->ev[0], st));
     CU(launch_uniform(E, false, p, nullptr, grid_f, thr_f, smf, st));
     h->launches += 1;

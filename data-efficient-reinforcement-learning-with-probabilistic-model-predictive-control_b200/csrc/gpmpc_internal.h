@@ -42,9 +42,7 @@ struct RolloutParams {
   double* ws_uni;      // uniform reverse sweep: (grid, NP * (2 + EV)) row / column sums of the sweep, reduced at L2
   int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
   int* queue;          // uniform kernels: [0] forward / [1] reverse candidate counters (dynamic scheduling: SMs differ in
-                       // speed by up to ~25 %, L2 distance), [2 + 256 k + smid] resident-slot counters of kernel k
-  int stagger;         // cycles the second resident CTA of an SM waits before its first candidate (desynchronises the
-                       // serial small-matrix phases of the two CTAs sharing an SM), 0 = off
+                       // speed by up to ~25 %, L2 distance),
   long long* dbg_clk;  // tuning aid (GPMPC_DEBUG_CLOCKS): CTA 0 accumulates clock64() deltas per phase here, else NULL
 };
 

@@ -39,17 +39,6 @@ __device__ __forceinline__ int uni_next_candidate(const RolloutParams& p, int k,
   __syncthreads();
   return c;
 }
-// the second CTA to arrive on an SM waits p.stagger cycles, so that its serial phases fall into its neighbour's sweep
-__device__ __forceinline__ void uni_stagger(const RolloutParams& p, int k, int tid) {
-  if (p.stagger > 0) {
-    if (tid == 0 && atomicAdd(p.queue + 2 + 256 * k + (uni_smid() & 255), 1) % 2 == 1) {
-      const long long c0 = clock64();
-      while (clock64() - c0 < p.stagger) {}
-    }
-    __syncthreads();
-  }
-}
-
 #ifndef UNI_MINB
 #define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
 #endif
@@ -256,7 +245,6 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 
   long long clk_ = clock64();
   UNI_CTA_BEGIN();
-  uni_stagger(p, 0, tid);
   for (;;) {
     const int cand = uni_next_candidate(p, 0, s_int, tid);
     if (cand >= p.B) break;
@@ -623,47 +611,34 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   for (int e = 0; e < EV; e++) { atomicAdd(g_xi + (size_t)e * NP + i0, xi0[e]); atomicAdd(g_xi + (size_t)e * NP + i1, xi1[e]); }
 }
 
-// O(N) reductions of the reverse sweep, lane-per-output (see uni_moments_slice): lane o of every warp sums its output
-// over the warp's slice of training points; the per-warp partial rows are added up by the consumer.
-//  kind 0 (B1b, mean part):  o < D: sum_i phi_i nu_i,o ;  o >= D: sum_i phi_i nu_i,k nu_i,l  (k <= l, row-major pairs)
-//  kind 1 (B3b, pair part):  o < D: sum_i g_i nu_i,o   ;  o >= D: sum_i g_i z_k z_l + z_l x_k + z_k x_l
-// with phi_i in the record's spare slot, g_i / x_i in the kap / beta slots (B3a);  z = nu * il2 (state dimensions).
+// O(N) reductions of the reverse sweep.  Every thread has summed, over its own training points, P "pair" values
+// (k <= l, row-major) and up to GPMPC_MAX_D "single" values; the warp adds them up with halving exchanges (16 values
+// per round, 16 shuffles instead of 80) and stores its totals as row[o]: o < D singles, o = D + pr pairs.  The per-warp
+// rows are added up by the consumer.  Two uses:
+//  B1 (mean part):  singles sum_i phi_i nu_i,d ;  pairs sum_i phi_i nu_i,k nu_i,l
+//  B3 (pair part):  singles sum_i g_i nu_i,d   ;  pairs sum_i g_i z_k z_l + z_l x_k + z_k x_l   (z = nu * il2, state dims)
 template <int EV>
-__device__ __forceinline__ void uni_bwd_moments_slice(int kind, const double* __restrict__ s_rec, int rlen, int rhot,
-                                                      const double* __restrict__ il2, int D, int ibeg, int iend,
-                                                      int lane, double* __restrict__ s_wp_row) {
-  constexpr int P = EV * (EV + 1) / 2;
-  const int sa = (kind == 0) ? 2 * EV + 1 : EV, sx = EV + 1;
-  for (int ob = 0; ob < D + P; ob += 32) {
-    const int o = ob + lane;
-    const bool act = o < D + P, pairo = act && o >= D;
-    int k = 0, l = 0;
-    if (pairo) {
-      int w = o - D;
-      while (w >= EV - k) { w -= EV - k; k++; }
-      l = k + w;
-    }
-    const int so = pairo ? k : ((act && o >= EV) ? rhot + (o - EV) : (act ? o : 0));   // slot of nu_o / nu_k
-    const double ik = il2[k], il = il2[l];
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i0 = ibeg; i0 < iend; i0 += 4) {
+__device__ __forceinline__ void uni_warp_point_sums(const double (&vp)[EV * (EV + 1) / 2], const double (&vs)[GPMPC_MAX_D],
+                                                    int D, int lane, double* __restrict__ row) {
+  constexpr int P = EV * (EV + 1) / 2, NCH = (P + GPMPC_MAX_D + 15) / 16;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const double* r = s_rec + (i0 + q) * rlen;
-        const double wgt = r[sa], n1 = r[so];
-        if (!pairo) {
-          acc[q] = fma(wgt, n1, acc[q]);
-        } else if (kind == 0) {
-          acc[q] = fma(wgt * n1, r[l], acc[q]);
-        } else {
-          const double zk = n1 * ik, zl = r[l] * il;
-          acc[q] = fma(wgt * zk, zl, acc[q]);
-          acc[q] = fma(zl, r[sx + k], acc[q]);
-          acc[q] = fma(zk, r[sx + l], acc[q]);
-        }
+  for (int ch = 0; ch < NCH; ch++) {
+    if (16 * ch < P + D) {   // warp-uniform: rounds that hold only unused single slots are skipped
+      double v16[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        constexpr int dummy = 0; (void)dummy;
+        const int sl = 16 * ch + k;
+        v16[k] = (sl < P) ? vp[sl < P ? sl : 0] : ((sl - P < GPMPC_MAX_D) ? vs[(sl - P >= 0 && sl - P < GPMPC_MAX_D) ? sl - P : 0] : 0.0);
+      }
+      int idx;
+      const double tot = warp_reduce_multi<16>(v16, lane, idx);
+      const int sl = 16 * ch + idx;
+      if ((lane & 1) == 0) {
+        if (sl < P) row[D + sl] = tot;
+        else if (sl - P < D) row[sl - P] = tot;
       }
     }
-    if (act) s_wp_row[o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   }
 }
 
@@ -743,7 +718,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   double* g_rho = g_gam + NP;
   double* g_xi = g_rho + NP;
   const int warp = tid >> 5, nwarps = NT >> 5;
-  double* s_wp = sm + L.wp;
+  double* s_wp = sm + L.wp; double* s_wp2 = s_wp + 8 * L.wplen;   // per-warp rows of the B1 / B3 point sums
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   double* s2p = sm + L.small2;
@@ -763,7 +738,6 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
 
   long long clk_ = clock64();
   UNI_CTA_BEGIN();
-  uni_stagger(p, 1, tid);
   for (;;) {
     const int cand = uni_next_candidate(p, 1, s_int, tid);
     if (cand >= p.B) break;
@@ -886,6 +860,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       __syncthreads();
       UNI_CLK(9);
       // ---- B1: nu, exponent terms, hot-loop record (as in the forward) + N pass of the mean part
+      double vp[P], vs[GPMPC_MAX_D];
+#pragma unroll
+      for (int k = 0; k < P; k++) vp[k] = 0.0;
+#pragma unroll
+      for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = 0.0;
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
@@ -928,15 +907,23 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           for (int e = 0; e < EV; e++) w = fma(s_gbar[a * E + e], nu[e], w);
           phi = fma(ei * __ldg(p.betaT + (size_t)i * E + a), w, phi);
         }
-        rcd[2 * EV + 1] = phi;
+        // raw moments of the mean part: sum_i phi_i nu_i,d (D) and sum_i phi_i nu_i,k nu_i,l (P)
+#pragma unroll
+        for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = fma(phi, nu[d], vs[d]);   // nu = 0 beyond D
+        {
+          int pr = 0;
+#pragma unroll
+          for (int k = 0; k < EV; k++) {
+            const double pk = phi * nu[k];
+#pragma unroll
+            for (int l = k; l < EV; l++) { vp[pr] = fma(pk, nu[l], vp[pr]); pr++; }
+          }
+        }
       }
-      __syncthreads();
       UNI_CLK(14);
-      // ---- B1b: raw moments sum_i phi_i nu_i,d (D) and sum_i phi_i nu_i,k nu_i,l (P): lane per output, per-warp rows
-      {
-        const int per = NP / nwarps;
-        uni_bwd_moments_slice<EV>(0, s_rec, L.rlen, L.rhot, il2, D, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
-      }
+      // ---- B1b: the warp's totals of the raw moments -> s_wp row (added up over warps after the sweep)
+      uni_warp_point_sums<EV>(vp, vs, D, lane, s_wp + warp * L.wplen);
+      __syncthreads();
       UNI_CLK(10);
       // ---- B2: adjoint-weighted sweep over the upper tile triangle (static balanced split as in the forward, P3)
       {
@@ -961,34 +948,55 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         for (int w = 0; w < nwarps; w++) v += s_wp[w * L.wplen + o];
         s_acc[accPm + o] = v;
       }
-      // ---- B3a: per training point, g_i = gam_i + rho_i and x_i = xi_i * il2 from the scratch (L2 loads: the sums were
-      //           formed by reductions at L2), scratch re-zeroed; they overwrite kap / beta in the record (sweep is done)
+      // ---- B3: per training point, g_i = gam_i + rho_i and x_i = xi_i * il2 from the scratch (L2 loads: the sums were
+      //          formed by reductions at L2; scratch re-zeroed), folded straight into the thread's share of
+      //          G_m (D singles: sum_i g_i nu_i,d) and the upper triangle of G_Q (P pairs), then reduced per warp
+#pragma unroll
+      for (int k = 0; k < P; k++) vp[k] = 0.0;
+#pragma unroll
+      for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = 0.0;
       for (int i = tid; i < NP; i += NT) {
-        double* rc = s_rec + (size_t)i * L.rlen;
-        double xv[EV];
+        const double* rc = s_rec + (size_t)i * L.rlen;
+        double xv[EV], z[EV];
         const double gv = __ldcg(g_gam + i), rv = __ldcg(g_rho + i);   // all loads first (the stores below may alias)
 #pragma unroll
         for (int e = 0; e < EV; e++) xv[e] = __ldcg(g_xi + (size_t)e * NP + i);
         g_gam[i] = 0.0;
         g_rho[i] = 0.0;
-        rc[EV] = gv + rv;
+#pragma unroll
+        for (int e = 0; e < EV; e++) g_xi[(size_t)e * NP + i] = 0.0;
+        const double g = gv + rv;
 #pragma unroll
         for (int e = 0; e < EV; e++) {
-          g_xi[(size_t)e * NP + i] = 0.0;
-          rc[EV + 1 + e] = xv[e] * il2[e];
+          const double ne = rc[e];
+          vs[e] = fma(g, ne, vs[e]);
+          z[e] = ne * il2[e];
+          xv[e] *= il2[e];
+        }
+#pragma unroll
+        for (int d = EV; d < GPMPC_MAX_D; d++)
+          if (d < D) vs[d] = fma(g, rc[L.rhot + d - EV], vs[d]);
+        {
+          int pr = 0;
+#pragma unroll
+          for (int k = 0; k < EV; k++) {
+            const double gk = g * z[k];
+#pragma unroll
+            for (int l = k; l < EV; l++) {
+              double acc = fma(gk, z[l], vp[pr]);
+              acc = fma(z[l], xv[k], acc);
+              vp[pr] = fma(z[k], xv[l], acc);
+              pr++;
+            }
+          }
         }
       }
-      __syncthreads();
       UNI_CLK(15);
-      // ---- B3b: G_m (D) and the upper triangle of G_Q (P): lane per output, per-warp rows
-      {
-        const int per = NP / nwarps;
-        uni_bwd_moments_slice<EV>(1, s_rec, L.rlen, L.rhot, il2, D, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
-      }
+      uni_warp_point_sums<EV>(vp, vs, D, lane, s_wp2 + warp * L.wplen);
       __syncthreads();
       for (int o = tid; o < D + P; o += NT) {
         double v = 0.0;
-        for (int w = 0; w < nwarps; w++) v += s_wp[w * L.wplen + o];
+        for (int w = 0; w < nwarps; w++) v += s_wp2[w * L.wplen + o];
         if (o < D) s_acc[accGm + o] = v * il2[o];
         else {
           int k = 0, w = o - D;

@@ -31,7 +31,7 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.part = o; if (!bwd) o += 8 * L.partlen;
   // per-warp partial rows of the O(N) reductions (lane per output): forward E (1 + D) outputs, reverse sweep D + P
   L.wplen = bwd ? (D + P) : (E * L.nOut);
-  L.wp = o; o += 8 * L.wplen;
+  L.wp = o; o += (bwd ? 16 : 8) * L.wplen;   // reverse sweep: two sets (B1, B3)
   L.S = o; o += 2 * E * E;          // S and s V^T of the recurrence stage
   L.cst = o; o += GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + GPMPC_MAX_EV * GPMPC_MAX_EV;   // target, W, WT
   L.m = o; o += GPMPC_MAX_D;
