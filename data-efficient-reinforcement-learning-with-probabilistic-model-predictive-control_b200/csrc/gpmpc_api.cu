@@ -173,7 +173,7 @@ int gpmpc_prepare(gpmpc_handle* h, const double* x, const double* y, const doubl
   CU(cudaSetDevice(h->device));
   const int NP = (N + 63) / 64 * 64;
   h->prepared = false;
-  CU(h->x.ensure(sizeof(double) * N * D));
+  CU(h->x.ensure(sizeof(double) * NP * D));   // room for gpmpc_append up to the padded size
   CU(h->ls.ensure(sizeof(double) * E * D));
   CU(h->il2.ensure(sizeof(double) * E * D));
   CU(h->s2.ensure(sizeof(double) * E));
@@ -214,6 +214,33 @@ int gpmpc_prepare(gpmpc_handle* h, const double* x, const double* y, const doubl
     }
   h->N = N; h->NP = NP; h->D = D; h->DP = (D + 1) & ~1; h->E = E;
   h->prepared = true;
+  return GPMPC_OK;
+}
+
+int gpmpc_append_room(const gpmpc_handle* h) { return (h && h->prepared) ? h->NP - h->N : 0; }
+
+int gpmpc_append(gpmpc_handle* h, const double* x_new, const double* y_new, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!h->prepared) return fail(h, GPMPC_ERR_NOT_PREPARED, "append: call gpmpc_prepare first");
+  if (!x_new || !y_new) return fail(h, GPMPC_ERR_BAD_ARG, "append: null pointer");
+  if (h->N >= h->NP) return fail(h, GPMPC_ERR_UNSUPPORTED, "append: padded size exhausted (N is a multiple of 64), call gpmpc_prepare");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->device));
+  const int N = h->N, NP = h->NP, D = h->D, E = h->E;
+  CU(launch_append(h->x.as<double>(), x_new, y_new, h->ls.as<double>(), h->s2.as<double>(), h->noise.as<double>(),
+                   h->Kbuf.as<double>(), h->Zbuf.as<double>(), h->iK.as<double>(), h->beta.as<double>(),
+                   h->betaT.as<double>(), h->info.as<int>(), N, NP, D, E, st, &h->launches));
+  CU(cudaMemcpyAsync(h->x.as<double>() + (size_t)N * D, x_new, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
+  int info[GPMPC_MAX_STATE];
+  CU(cudaMemcpyAsync(info, h->info.ptr, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int a = 0; a < E; a++)
+    if (info[a] != 0) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "append: Schur complement of GP %d is not positive (factorisation left unchanged)", a);
+      return fail(h, GPMPC_ERR_NOT_PD, msg);
+    }
+  h->N = N + 1;
   return GPMPC_OK;
 }
 
@@ -359,6 +386,10 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     CU(h->records.ensure(sizeof(double) * (size_t)B * H * RL.size));
     p.records = h->records.as<double>();
   }
+  // candidate counters of the dynamic scheduling: [0] uniform forward, [1] uniform reverse sweep, [2] general kernel
+  CU(h->queue.ensure(sizeof(int) * 4));
+  CU(cudaMemsetAsync(h->queue.ptr, 0, sizeof(int) * 4, st));
+  p.queue = h->queue.as<int>();
   if (use_uniform) {
     // uniform-kernel fast path: one exp per (i, j) for all output pairs; reverse-mode second sweep for the gradient
     const UniRecLayout UR = uni_rec_layout(E);
@@ -409,9 +440,6 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * (16 + 4 * 2048), st));
       p.dbg_clk = h->dbg_clk.as<long long>();
     }
-    CU(h->queue.ensure(sizeof(int) * 2));
-    CU(cudaMemsetAsync(h->queue.ptr, 0, sizeof(int) * 2, st));
-    p.queue = h->queue.as<int>();
     if (h->timing) CU(cudaEventRecord(h->ev[0], st));
     CU(launch_uniform(E, false, p, nullptr, grid_f, thr_f, smf, st));
     h->launches += 1;

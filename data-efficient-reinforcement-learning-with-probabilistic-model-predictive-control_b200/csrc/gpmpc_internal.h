@@ -41,8 +41,8 @@ struct RolloutParams {
   int premat;          // uniform reverse sweep: per-step matrices / stage-cost adjoints precomputed for all steps
   double* ws_uni;      // uniform reverse sweep: (grid, NP * (2 + EV)) row / column sums of the sweep, reduced at L2
   int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
-  int* queue;          // uniform kernels: [0] forward / [1] reverse candidate counters (dynamic scheduling: SMs differ in
-                       // speed by up to ~25 %, L2 distance),
+  int* queue;          // candidate counters of the dynamic scheduling (SMs differ in speed by up to ~25 % on this workload:
+                       // L2 distance): [0] uniform forward, [1] uniform reverse sweep, [2] general kernel; NULL = round-robin
   long long* dbg_clk;  // tuning aid (GPMPC_DEBUG_CLOCKS): CTA 0 accumulates clock64() deltas per phase here, else NULL
 };
 
@@ -66,6 +66,9 @@ cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* gra
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
                            double* iK, double* beta, double* betaT, int* info, cudaStream_t st, long long* launches);
+cudaError_t launch_append(const double* x, const double* xnew, const double* ynew, const double* ls, const double* s2,
+                          const double* noise, double* Lbuf, double* ws, double* iK, double* beta, double* betaT,
+                          int* info, int N, int NP, int D, int E, cudaStream_t st, long long* launches);
 cudaError_t launch_mll(const double* x, const double* y, const double* ls, const double* s2, const double* Lbuf,
                        const double* iK, const double* beta, double* out, int N, int NP, int D, int E, int stride,
                        cudaStream_t st, long long* launches);

@@ -329,6 +329,150 @@ __global__ void __launch_bounds__(256) mll_grad_kernel(const double* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ one-point append (O(N^2) per GP)
+// The training set grows by one point per control step (gp_memory.py:31-64 -> gp_mpc_controller.py:114-118, where the
+// reference refactorises from scratch).  With K' = [[K, k], [k^T, kap]]:
+//   L l = k,  sig = kap - l.l  (exactly the row a full Cholesky of K' would append),  L^T v = l  (v = iK k),
+//   iK' = [[iK + v v^T / sig, -v / sig], [-v^T / sig, 1 / sig]],   gam = (y_new - k.beta) / sig,   beta' = [beta - gam v ; gam].
+// append_solve_kernel: one CTA per GP, blocked (32) forward / backward substitution; writes the new row of L, and v,
+// sig, gam into the workspace.  append_update_kernel: the rank-one update of iK, beta, betaT over the whole GPU.
+__global__ void __launch_bounds__(256) append_solve_kernel(const double* __restrict__ x, const double* __restrict__ xnew,
+                                                           const double* __restrict__ ynew, const double* __restrict__ ls,
+                                                           const double* __restrict__ s2, const double* __restrict__ noise,
+                                                           double* __restrict__ Lall, const double* __restrict__ beta,
+                                                           double* __restrict__ ws, int N, int NP, int D, int E,
+                                                           int* __restrict__ info) {
+  extern __shared__ double sh[];
+  double* s_k = sh;              // k, then l   (NP)
+  double* s_v = sh + NP;         // v           (NP)
+  __shared__ double s_blk[32][33], s_part[8][33], s_red[8];
+  const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* L = Lall + (size_t)a * NP * NP;
+  // ---- k_i = s2 exp(-1/2 |(x_i - x_new) / l|^2)  and  k . beta
+  double dot = 0.0;
+  for (int i = tid; i < N; i += 256) {
+    double d2 = 0.0;
+    for (int d = 0; d < D; d++) {
+      const double t = (x[(size_t)i * D + d] - xnew[d]) / ls[a * D + d];
+      d2 = fma(t, t, d2);
+    }
+    const double k = s2[a] * exp(-0.5 * d2);
+    s_k[i] = k;
+    dot = fma(k, beta[(size_t)a * NP + i], dot);
+  }
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if (lane == 0) s_red[warp] = dot;
+  __syncthreads();
+  double kbeta = 0.0;
+  for (int w = 0; w < 8; w++) kbeta += s_red[w];
+  const int nb = (N + 31) / 32;
+  // ---- forward substitution L l = k
+  for (int b = 0; b < nb; b++) {
+    const int r0 = 32 * b, rows = min(32, N - r0);
+    for (int rr = warp; rr < rows; rr += 8) {
+      const double* Lr = L + (size_t)(r0 + rr) * NP;
+      double acc = 0.0;
+      for (int c = lane; c < r0; c += 32) acc = fma(Lr[c], s_k[c], acc);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) s_k[r0 + rr] -= acc;
+    }
+    for (int rr = warp; rr < 32; rr += 8)
+      s_blk[rr][lane] = (rr < rows && lane < rows) ? L[(size_t)(r0 + rr) * NP + r0 + lane] : (rr == lane ? 1.0 : 0.0);
+    __syncthreads();
+    if (warp == 0) {
+      double kj = (lane < rows) ? s_k[r0 + lane] : 0.0;
+      for (int c = 0; c < rows; c++) {
+        const double lc = __shfl_sync(0xffffffffu, kj, c) / s_blk[c][c];
+        if (lane == c) kj = lc;
+        else if (lane > c) kj = fma(-s_blk[lane][c], lc, kj);
+      }
+      if (lane < rows) s_k[r0 + lane] = kj;
+    }
+    __syncthreads();
+  }
+  // ---- sig = kap - l.l
+  double ll = 0.0;
+  for (int i = tid; i < N; i += 256) ll = fma(s_k[i], s_k[i], ll);
+  for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = ll;
+  __syncthreads();
+  ll = 0.0;
+  for (int w = 0; w < 8; w++) ll += s_red[w];
+  const double sig = (s2[a] + noise[a]) - ll;
+  // ---- backward substitution L^T v = l
+  for (int b = nb - 1; b >= 0; b--) {
+    const int r0 = 32 * b, rows = min(32, N - r0);
+    double acc = 0.0;
+    if (lane < rows)
+      for (int j = r0 + 32 + warp; j < N; j += 8) acc = fma(L[(size_t)j * NP + r0 + lane], s_v[j], acc);
+    s_part[warp][lane] = acc;
+    for (int rr = warp; rr < 32; rr += 8)
+      s_blk[rr][lane] = (rr < rows && lane < rows) ? L[(size_t)(r0 + rr) * NP + r0 + lane] : (rr == lane ? 1.0 : 0.0);
+    __syncthreads();
+    if (warp == 0) {
+      double vj = 0.0;
+      if (lane < rows) {
+        vj = s_k[r0 + lane];
+        for (int w = 0; w < 8; w++) vj -= s_part[w][lane];
+      }
+      for (int c = rows - 1; c >= 0; c--) {
+        const double vc = __shfl_sync(0xffffffffu, vj, c) / s_blk[c][c];
+        if (lane == c) vj = vc;
+        else if (lane < c) vj = fma(-s_blk[c][lane], vc, vj);
+      }
+      if (lane < rows) s_v[r0 + lane] = vj;
+    }
+    __syncthreads();
+  }
+  // ---- results: new row of L, v, sig, gam
+  if (!(sig > 0.0)) {
+    if (tid == 0) atomicExch(info + a, N + 1);
+    return;
+  }
+  double* Lrow = L + (size_t)N * NP;
+  for (int i = tid; i < NP; i += 256) {
+    Lrow[i] = (i < N) ? s_k[i] : (i == N ? sqrt(sig) : 0.0);
+    ws[(size_t)a * NP + i] = (i < N) ? s_v[i] : 0.0;
+  }
+  if (tid == 0) {
+    ws[(size_t)E * NP + 2 * a] = sig;
+    ws[(size_t)E * NP + 2 * a + 1] = (ynew[a] - kbeta) / sig;
+  }
+}
+
+__global__ void append_update_kernel(const double* __restrict__ ws, double* __restrict__ iK, double* __restrict__ beta,
+                                     double* __restrict__ betaT, const int* __restrict__ info, int N, int NP, int E) {
+  const int a = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > N || j > N) return;
+  for (int q = 0; q < E; q++)
+    if (info[q] != 0) return;          // a failed append leaves the whole factorisation untouched
+  const double* v = ws + (size_t)a * NP;
+  const double sig = ws[(size_t)E * NP + 2 * a], gam = ws[(size_t)E * NP + 2 * a + 1];
+  double* out = iK + ((size_t)a * NP + i) * NP + j;
+  if (i < N && j < N) *out = fma(v[i] / sig, v[j], *out);
+  else if (i == N && j == N) *out = 1.0 / sig;
+  else *out = -v[i < N ? i : j] / sig;
+  if (j == 0) {
+    const double b = (i < N) ? fma(-gam, v[i], beta[(size_t)a * NP + i]) : gam;
+    beta[(size_t)a * NP + i] = b;
+    betaT[(size_t)i * E + a] = b;
+  }
+}
+
+cudaError_t launch_append(const double* x, const double* xnew, const double* ynew, const double* ls, const double* s2,
+                          const double* noise, double* Lbuf, double* ws, double* iK, double* beta, double* betaT,
+                          int* info, int N, int NP, int D, int E, cudaStream_t st, long long* launches) {
+  cudaMemsetAsync(info, 0, sizeof(int) * E, st);
+  append_solve_kernel<<<E, 256, sizeof(double) * 2 * NP, st>>>(x, xnew, ynew, ls, s2, noise, Lbuf, beta, ws, N, NP, D, E, info);
+  dim3 blk(32, 8);
+  append_update_kernel<<<dim3(N / 32 + 1, N / 8 + 1, E), blk, 0, st>>>(ws, iK, beta, betaT, info, N, NP, E);
+  *launches += 2;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mll(const double* x, const double* y, const double* ls, const double* s2, const double* Lbuf,
                        const double* iK, const double* beta, double* out, int N, int NP, int D, int E, int stride,
                        cudaStream_t st, long long* launches) {

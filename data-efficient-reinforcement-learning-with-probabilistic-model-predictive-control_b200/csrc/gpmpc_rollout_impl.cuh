@@ -332,7 +332,17 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   double* kk = p.ws_kk + (size_t)blockIdx.x * E * NP;
   __syncthreads();
 
-  for (int cand = blockIdx.x; cand < p.B; cand += gridDim.x) {
+  // candidates are drawn from a global counter when the host provides one (rollouts; SM speeds differ by up to ~25 %,
+  // see the uniform kernels), else dealt round-robin (single steps)
+  __shared__ int s_next;
+  for (int cand = blockIdx.x;; cand += gridDim.x) {
+    if (p.queue) {
+      if (tid == 0) s_next = atomicAdd(p.queue + 2, 1);
+      __syncthreads();
+      cand = s_next;
+      __syncthreads();
+    }
+    if (cand >= p.B) break;
     // ================================================================== candidate init
     if (p.mode == 0) {
       if (tid < E) {

@@ -21,6 +21,8 @@ _SIGNATURES = {
     "gpmpc_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "gpmpc_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "gpmpc_prepare": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
+    "gpmpc_append": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "gpmpc_append_room": (ctypes.c_int, [ctypes.c_void_p]),
     "gpmpc_get_factorization": (ctypes.c_int, [ctypes.c_void_p] * 4),
     "gpmpc_set_cost": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
                                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -129,6 +131,17 @@ class Engine:
             self._check(self._lib.gpmpc_prepare(self._h, _ptr(x), _ptr(y), _ptr(ls), _ptr(s2), _ptr(nz), N, D, E,
                                                 self._stream()))
         self.N, self.D, self.E = N, D, E
+
+    def append_room(self):
+        """Points that can still be appended before a full prepare() is needed (padded size)."""
+        return int(self._lib.gpmpc_append_room(self._h))
+
+    def append(self, x_new, y_new):
+        """Adds one training point to the prepared factorisation in O(N^2) (new Cholesky row, block-inverse update)."""
+        x_new = _f64(x_new, self.device, (self.D,)); y_new = _f64(y_new, self.device, (self.E,))
+        with torch.cuda.device(self.device):
+            self._check(self._lib.gpmpc_append(self._h, _ptr(x_new), _ptr(y_new), self._stream()))
+        self.N += 1
 
     def factorization(self):
         iK = torch.empty((self.E, self.N, self.N), dtype=torch.float64, device=self.device)

@@ -102,6 +102,9 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
         self._engine = None
         self._cost_key = None
         self.x_mem = self.y_mem = None
+        self.incremental_updates = True     # O(N^2) append instead of a full refactorisation when the memory grew
+        self.last_prepare_mode = None
+        self._prep_x = self._prep_y = self._prep_hyp = None
 
     # ------------------------------------------------------------------ engine plumbing
     @property
@@ -126,14 +129,39 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
 
     # ------------------------------------------------------------------ reference API
     def prepare_inference(self, inputs, state_changes):
+        """Caches the factorisation of the training set in the engine (reference gp_model.py:182-191).
+
+        The reference refactorises from scratch at every control step.  Here, when the call brings the PREVIOUS
+        training set plus a few new rows under unchanged hyper-parameters -- what GpMpcController.get_action does after
+        Memory.add (gp_mpc_controller.py:114-118) -- the new rows are appended in O(N^2) each (gpmpc_append) while the
+        padded size allows, i.e. at most 63 times in a row before a full refactorisation.
+        `incremental_updates = False` restores the reference's behaviour; `last_prepare_mode` says which path ran."""
+        inputs = torch.as_tensor(inputs)
+        state_changes = torch.as_tensor(state_changes)
+        ls, s2, noise = _hyperparameters(self.models)
+        hyp = torch.cat([ls.detach().double().flatten(), s2.detach().double().flatten(), noise.detach().double().flatten()]).cpu()
+        n_old = 0 if self._prep_x is None else len(self._prep_x)
+        n_new = len(inputs) - n_old
+        can_append = (self.incremental_updates and self._engine is not None and n_old > 0 and 0 < n_new <= self._engine.append_room()
+                      and self._prep_hyp is not None and torch.equal(hyp, self._prep_hyp)
+                      and inputs.shape[1:] == self._prep_x.shape[1:]
+                      and torch.equal(torch.as_tensor(inputs[:n_old], dtype=torch.float64).cpu(), self._prep_x)
+                      and torch.equal(torch.as_tensor(state_changes[:n_old], dtype=torch.float64).cpu(), self._prep_y))
         self.x_mem = inputs
         self.y_mem = state_changes
-        self.lengthscales, self.variances, noise = _hyperparameters(self.models)
-        self.engine.prepare(inputs, state_changes, self.lengthscales, self.variances, noise)
+        self.lengthscales, self.variances = ls, s2
+        if can_append:
+            for i in range(n_old, n_old + n_new):
+                self.engine.append(inputs[i], state_changes[i])
+            self.last_prepare_mode = "append"
+        else:
+            self.engine.prepare(inputs, state_changes, ls, s2, noise)
+            self.last_prepare_mode = "full"
+        self._prep_x = torch.as_tensor(inputs, dtype=torch.float64).cpu().clone()
+        self._prep_y = torch.as_tensor(state_changes, dtype=torch.float64).cpu().clone()
+        self._prep_hyp = hyp
         self.iL = torch.diag_embed(1.0 / self.lengthscales)
         self._fact = None
-        if self._cost_key is not None and self._cost_key != "zero":
-            pass  # cost buffers live in the handle and survive prepare
 
     def _factorization(self):
         if self._fact is None:

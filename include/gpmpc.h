@@ -55,6 +55,18 @@ int gpmpc_destroy(gpmpc_handle* h);
 int gpmpc_prepare(gpmpc_handle* h, const double* x, const double* y, const double* lengthscale,
                   const double* outputscale, const double* noise, int N, int D, int E, void* stream);
 
+/*
+ * Appends ONE training point to the factorisation of the last gpmpc_prepare in O(N^2) per GP (new Cholesky row, block
+ * inverse update of iK, beta) instead of refactorising: the step the reference repeats from scratch every control
+ * step after Memory.add (control_objects/memories/gp_memory.py:31-64 ->
+ * controllers/gp_mpc_controller.py:114-118 -> gp_model.py:182-191).   x_new (D)  y_new (E), device pointers.
+ * Works while N is below the padded size (next multiple of 64; gpmpc_append_room() = points left); beyond that it
+ * returns GPMPC_ERR_UNSUPPORTED and the caller runs gpmpc_prepare, which also bounds the accumulated rounding of
+ * successive rank-one updates.  GPMPC_ERR_NOT_PD (after a stream sync) leaves the factorisation unchanged.
+ */
+int gpmpc_append(gpmpc_handle* h, const double* x_new, const double* y_new, void* stream);
+int gpmpc_append_room(const gpmpc_handle* h);
+
 /* Copies the cached factorisation out: iK (E,N,N), beta (E,N)  (attributes read at gp_model.py:186). */
 int gpmpc_get_factorization(gpmpc_handle* h, double* iK, double* beta, void* stream);
 
