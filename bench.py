@@ -161,16 +161,17 @@ def workload_config(cfg, args):
 
 def fp64_report(uniform, E, N, preds, fwd_ms, bwd_ms, f_alg, peak):
     """Float64 roofline: (a) SURVEY 8(d)'s algorithmic flops (E^2-pair algorithm) and (b) the float64 instructions the
-    kernels actually execute per prediction (op-count model of the hot loops), each counted as
-    one FMA = 2 flops, against the measured DFMA peak.  NB: DFMAs with three distinct register operands issue at
-    2/3 of that peak on B200 (tools/micro/dfma_operands.cu), 9 of the 21 per-element ops of the uniform kernel."""
+    kernels actually execute per prediction in their hot loops (counted in the SASS), each counted
+    as one FMA = 2 flops, against the measured DFMA peak.  NB: a DFMA with three distinct register operands issues at
+    2/3 of that peak on B200 (tools/micro/dfma_operands.cu)."""
     NP = (N + 63) // 64 * 64
     if uniform:
-        fwd_ops = NP * NP * ((E + 1) + 11 + E + 1)
-        bwd_ops = NP * (NP + 64) // 2 * ((E + 1) + 11 + (E + 1) + 1 + 2 + E + 1.1)
+        tri = (NP // 64) * (NP // 64 + 1) // 2 * 64 * 64      # elements of the upper tile triangle (both sweeps)
+        fwd_ops = tri * ((E + 1) + 7 + E + 1)                 # exponent, exp2s, beta-weighted row sums, trace
+        bwd_ops = tri * ((E + 1) + 7 + (E + 1) + 3.06 + E)    # + coefficient, w, rho/col sums, xi
     else:
         elems = E * NP * (NP + 64) // 2 + E * (E - 1) // 2 * NP * NP
-        fwd_ops = elems * ((E + 1) + 11 + 2 + 1 + (E + 3.1))   # gradient mode: + rho/gamma/xi accumulation
+        fwd_ops = elems * ((E + 1) + 7 + 2 + 1 + (E + 3.1))   # gradient mode: + rho/gamma/xi accumulation
         bwd_ops = 0
     ex_f = 2.0 * fwd_ops * preds / (fwd_ms * 1e-3)
     out = {"peak_tflops": peak / 1e12, "peak_source": "measured (gpmpc_fp64_peak: register-resident DFMA loop)",
@@ -184,6 +185,20 @@ def fp64_report(uniform, E, N, preds, fwd_ms, bwd_ms, f_alg, peak):
         out.update({"executed_flops_per_prediction_bwd": 2.0 * bwd_ops, "executed_tflops_bwd": ex_b / 1e12,
                     "executed_frac_bwd": ex_b / peak})
     return out
+
+
+def ncu_traffic(kernel_prefix, workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
+    (profiles/dram_traffic.json, written by tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum`); None when no capture of this kernel/workload is committed."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        for row in tab["launches"]:
+            if row["kernel"].startswith(kernel_prefix) and row["workload"] == workload:
+                return row["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
@@ -243,6 +258,16 @@ def main():
     tm.prepare_inference(torch.as_tensor(cfg["x"]), torch.as_tensor(cfg["y"]))
     torch.cuda.synchronize()
     prepare_ms = (time.perf_counter() - t0) * 1e3
+    # one-point append (gpmpc_append): factorise N-1 points, time adding the N-th, then refactorise for the run
+    tm.prepare_inference(torch.as_tensor(cfg["x"][:-1]), torch.as_tensor(cfg["y"][:-1]))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tm.prepare_inference(torch.as_tensor(cfg["x"]), torch.as_tensor(cfg["y"]))
+    torch.cuda.synchronize()
+    append_ms = (time.perf_counter() - t0) * 1e3 if tm.last_prepare_mode == "append" else None
+    tm.incremental_updates = False
+    tm.prepare_inference(torch.as_tensor(cfg["x"]), torch.as_tensor(cfg["y"]))
+    tm.incremental_updates = True
     eng = tm.engine
     eng.enable_timing(True)
     obs_mu, obs_var = torch.as_tensor(cfg["mu0"]), torch.as_tensor(cfg["Sigma0"])
@@ -332,15 +357,16 @@ def main():
         kname = ("gpmpc::uniform_fwd_kernel<%d> (one exp per (i,j) for all output pairs)" % E) if uniform else \
             ("gpmpc::rollout_kernel<%d,true> (per-pair sweep + forward-mode Jacobian records)" % E)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                    "traffic": ncu_traffic("uniform_fwd" if uniform else "rollout_kernel", "%s B=%d H=%d" % (cfg["name"], Bl, H)),
+                    "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                     "kernel": "%s, %.2f ms/launch for %d predictions" % (kname, fwd_ms, preds_rank0),
                     "reverse_sweep_kernel": ("gpmpc::uniform_bwd_kernel<%d> (adjoint-weighted upper-triangle N^2 sweep), "
                                              "%.2f ms/launch" % (E, bwd_ms)) if uniform else
                     ("gpmpc::backward_kernel<%d> (small-matrix algebra on records), %.2f ms/launch" % (E, bwd_ms)),
                     "algorithmic_bytes_per_prediction": b_alg,
                     "note": "algorithmic bytes (SURVEY 8(d): 8*(E N^2 + E N + N D) per prediction) are served from L2/L1/"
-                            "shared memory -- the training block is shared by all candidates (ncu: 2.5 MB DRAM traffic per "
-                            "launch, L2 hit rate 98.8 %) -- so frac>1 is expected; the binding roofline is float64 FMA "
+                            "shared memory -- the training block is shared by all candidates (`traffic` = DRAM bytes per launch "
+                            "from ncu, mostly the per-step records and outputs) -- so frac>1 is expected; the binding roofline is float64 FMA "
                             "throughput (fp64 block)",
                     "fp64": fp64_report(uniform, E, N, preds_rank0, fwd_ms, bwd_ms, f_alg, fp64_peak)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -351,8 +377,9 @@ def main():
                                  "ms_per_step": ms_fwd / args.steps},
                 "kernel_path": "uniform (all GPs share their hyper-parameters)" if uniform else "general (per-pair)",
                 "kernel_ms": {"rollout_fwd": fwd_ms, "reverse_sweep": bwd_ms},
-                "prepare_ms": {"first_call": prepare_ms_first, "steady": prepare_ms,
-                               "what": "Gram + Cholesky + iK + beta for %d GPs, N=%d (once per control step)" % (E, N)},
+                "prepare_ms": {"first_call": prepare_ms_first, "steady": prepare_ms, "append_one_point": append_ms,
+                               "what": "Gram + Cholesky + iK + beta for %d GPs, N=%d (once per control step); "
+                                       "append_one_point = gpmpc_append through prepare_inference when the memory grew by one" % (E, N)},
                 "e2e": {"value": preds * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": int(actions_host.numel() * 8 * world),
                         "d2h_bytes_per_step": int((Bl + Bl * H * Na) * 8 * world),

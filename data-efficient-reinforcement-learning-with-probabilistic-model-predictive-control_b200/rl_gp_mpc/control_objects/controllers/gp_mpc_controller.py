@@ -105,7 +105,7 @@ class GpMpcController(BaseControllerObject):
         else:
             next_action_raw = self.past_action
         self.iter_ctrl += 1
-        return np.array(next_action_raw)
+        return np.array(torch.as_tensor(next_action_raw).detach().cpu().numpy())
 
     def _prepare(self):
         x_mem, y_mem = self.memory.get()
