@@ -128,7 +128,7 @@ def run_reference(args, cfg, rank):
     if rank != 0:
         return
     cores = torch.get_num_threads()
-    cand, hor = 1, min(cfg["H"], 10)
+    cand, hor = min(4, cfg["B"]), cfg["H"]      # ~3 s of host work per step at the headline shape
     for _ in range(args.warmup):
         cpu_port_rate(cfg, 1, min(2, hor))
     t0 = time.perf_counter()
@@ -386,10 +386,10 @@ def main():
                         "api": "GpMpcController.compute_mean_lcb_trajectory_batch (pinned host actions in, costs+grads out)"},
                 "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
         if not args.no_cpu_baseline:
-            rate, dt = cpu_port_rate(cfg, min(4, B), min(H, 10))
+            rate, dt = cpu_port_rate(cfg, min(16, B), H)      # ~10-15 s of host work at the headline shape
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d candidates x %d horizon steps, objective+autograd gradient, %.1f s "
-                                              "(oracle/gpmpc_oracle.py, float64)" % (min(4, B), min(H, 10), dt)}
+                                              "(oracle/gpmpc_oracle.py, float64)" % (min(16, B), H, dt)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -147,6 +147,7 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   // -- the tile below the diagonal contributes X_ba of its mirror image.  The row sums r_b,i of the diagonal-tile
   // columns are halved before the columns above it are added.
   const int jd1 = 64 * I + 64;
+  jend = min(jend, (p.N + 1) & ~1);   // zero-padded columns (beta = 0, iK = 0) contribute exact zeros: skip them
   double trD = 0.0, trU = 0.0;
   if (jbeg < jd1) {
     uni_fwd_cols<EV, true>(p, s_rec, rlen, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD, s_tab);
@@ -595,6 +596,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
 #pragma unroll
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
   const int jd1 = 64 * I + 64;
+  jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns contribute exact zeros: skip them (8 columns per round)
   if (jbeg < jd1) {
 #pragma unroll
     for (int a = 0; a < E; a++) { p0[a] *= 0.5; p1[a] *= 0.5; }
