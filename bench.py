@@ -58,6 +58,17 @@ def parse_args():
     return ap.parse_args()
 
 
+_STDOUT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
@@ -146,7 +157,7 @@ def run_reference(args, cfg, rank):
                              "sample": "%d candidate x %d horizon steps per step, objective+autograd gradient "
                                        "(oracle/gpmpc_oracle.py), float64" % (cand, hor)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(cfg, args):
@@ -204,8 +215,13 @@ def ncu_traffic(kernel_prefix, workload):
 # ------------------------------------------------------------------------------------------ CUDA arm
 def main():
     args = parse_args()
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
+    # stdout carries exactly ONE line, the JSON: native libraries write there too (NCCL prints its version at communicator
+    # creation whatever NCCL_DEBUG says on some boxes), so file descriptor 1 is pointed at stderr for the whole run and
+    # the JSON line goes to a private duplicate of the original stdout (emit()).
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -390,7 +406,7 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d candidates x %d horizon steps, objective+autograd gradient, %.1f s "
                                               "(oracle/gpmpc_oracle.py, float64)" % (min(16, B), H, dt)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
