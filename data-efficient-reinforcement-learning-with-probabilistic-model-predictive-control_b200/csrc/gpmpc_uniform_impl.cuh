@@ -4,12 +4,13 @@
 // whole exponent are independent of (a, b):
 //       L^{ab}_ij = s2^2 * Eh_ij ,   Eh_ij = exp(kap_i + kap_j + u_i . nu_j)
 //       S^raw_ab  = s2^2 * ( beta_a^T Eh beta_b  -  [a==b] tr(iK Eh) )
-// so one N x N sweep with ONE exp per element serves all E(E+1)/2 output pairs: N^2 exps per prediction
-// instead of (E/2 + E(E-1)/2) N^2.  The mean part shares A = (s + Lambda)^-1 and exp(-q_i/2) as well.
+// so one sweep with ONE exp per element serves all E(E+1)/2 output pairs -- and, Eh and iK being symmetric, only
+// over the 64 x 64 tiles on or above the diagonal (uni_fwd_item): ~N^2/2 exps per prediction instead of
+// (E/2 + E(E-1)/2) N^2.  The mean part shares A = (s + Lambda)^-1 and exp(-q_i/2) as well.
 //
 // Gradient: reverse mode.  With P = E(E+1)/2 scalar outputs per exp, emitting forward-mode Jacobians (general
-// path) would cost ~4x more than a second N^2 sweep with the adjoint-weighted coefficient
-//       W_ij = (Omega beta_i) . beta_j - wbar * iK_ij ,    w_ij = W_ij Eh_ij   (symmetric, upper-triangle sweep)
+// path) would cost ~4x more than a second sweep with the adjoint-weighted coefficient
+//       W_ij = (Omega beta_i) . beta_j - wbar * iK_ij ,    w_ij = W_ij Eh_ij   (symmetric, same tile triangle)
 // from which dS/dm and dS/dQ follow exactly as for a diagonal pair of the general path (rho, gamma, xi sums).
 // uniform_fwd_kernel stores only (M, V^E, h, g^E, S^raw) per step; uniform_bwd_kernel runs the reverse sweep
 // with one CTA per candidate.  tests/algo_spec.py remains the executable spec of the mathematics.
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         for (int e = 0; e < EV * EV; e++) chk += s_s[e];
         s_int[1] = isfinite(chk) ? 0 : 1;
       }
-      // ---- P1: nu, shared exponent terms, hot-loop record; mean-part sums h_a, g_a reduced on the fly
+      // ---- P1: nu, shared exponent terms, hot-loop record (thread per training point)
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
@@ -360,8 +361,8 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
       }
       UNI_CLK(1);
       // ---- P3: one sweep over the upper tile triangle for all pairs.  Static balanced split: row block I (64 rows)
-      //      holds 2 (nrb - I) chunks of p.seg/... 32 columns from its diagonal on; the chunks of all row blocks, in
-      //      row-major order, are dealt to the warps in equal contiguous runs (a run is cut at row-block boundaries).
+      //      holds (64 / p.seg) (nrb - I) chunks of p.seg columns from its diagonal on; the chunks of all row blocks,
+      //      in row-major order, are dealt to the warps in equal contiguous runs (cut at row-block boundaries).
       {
         const int CH = p.seg, nrb = NP / 64, cpt = 64 / CH;       // chunks per 64-column tile
         const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps - 1) / nwarps;

@@ -124,3 +124,58 @@ def test_controller_constructs_and_exposes_reference_attributes():
     assert abs(m.covar_module.outputscale.item() - 0.1) < 1e-15
     assert set(m.state_dict()) == {"covar_module.base_kernel.lengthscale", "covar_module.outputscale", "likelihood.noise"}
     assert c.compute_cost_unnormalized(np.zeros(3), np.zeros(1))[0] > 0
+
+
+def test_prepare_inference_chooses_append_or_full_refactorisation():
+    """Host logic of SURVEY 8(f) N3 with a recording stand-in for the engine (no device needed): the O(N^2) append is
+    taken only for 'previous training set + new rows, same hyper-parameters, room left', else a full prepare."""
+    from rl_gp_mpc.config_classes.model_config import ModelConfig
+    from rl_gp_mpc.control_objects.models.gp_model import GpStateTransitionModel
+
+    class FakeEngine:
+        def __init__(self):
+            self.calls, self.N, self.NP = [], 0, 0
+
+        def prepare(self, x, y, ls, s2, noise):
+            self.N = len(x)
+            self.NP = (self.N + 63) // 64 * 64
+            self.calls.append(("prepare", self.N))
+
+        def append(self, x_new, y_new):
+            assert self.N < self.NP
+            self.N += 1
+            self.calls.append(("append", self.N))
+
+        def append_room(self):
+            return self.NP - self.N
+
+    model = GpStateTransitionModel(ModelConfig(gp_init={"noise_covar.noise": [1e-4] * 2,
+                                                         "base_kernel.lengthscale": [[0.75] * 3] * 2,
+                                                         "outputscale": [5e-2] * 2}), dim_state=2, dim_action=1)
+    eng = model._engine = FakeEngine()
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.rand(200, 3, generator=g), torch.rand(200, 2, generator=g)
+    model.prepare_inference(x[:60], y[:60])
+    assert model.last_prepare_mode == "full" and eng.calls[-1] == ("prepare", 60)
+    model.prepare_inference(x[:62], y[:62])                           # grew by two rows
+    assert model.last_prepare_mode == "append" and eng.calls[-2:] == [("append", 61), ("append", 62)]
+    model.prepare_inference(x[:62], y[:62])                           # unchanged: the reference refactorises, so do we
+    assert model.last_prepare_mode == "full"
+    model.prepare_inference(x[:64], y[:64])
+    assert model.last_prepare_mode == "append" and eng.append_room() == 0
+    model.prepare_inference(x[:65], y[:65])                           # padded size used up
+    assert model.last_prepare_mode == "full" and eng.calls[-1] == ("prepare", 65)
+    x2 = x.clone(); x2[3, 1] += 0.5
+    model.prepare_inference(x2[:66], y[:66])                          # an old row changed
+    assert model.last_prepare_mode == "full"
+    model.prepare_inference(x2[:67], y[:67])
+    assert model.last_prepare_mode == "append"
+    model.models[0].covar_module.outputscale = 0.07                  # hyper-parameters changed (training result)
+    model.prepare_inference(x2[:68], y[:68])
+    assert model.last_prepare_mode == "full"
+    model.incremental_updates = False
+    model.prepare_inference(x2[:69], y[:69])
+    assert model.last_prepare_mode == "full"
+    model.incremental_updates = True
+    model.prepare_inference(x2[:30], y[:30])                          # shrank
+    assert model.last_prepare_mode == "full" and eng.N == 30
