@@ -138,6 +138,10 @@ def run_reference(args, cfg, rank):
     GPU box) on the host cores, same metric/unit/config.  Each step = a bounded sample of the workload."""
     if rank != 0:
         return
+    try:                                  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it may
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     cand, hor = min(4, cfg["B"]), cfg["H"]      # ~3 s of host work per step at the headline shape
     for _ in range(args.warmup):

@@ -944,6 +944,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           c0 = ce;
         }
       }
+      __threadfence();   // the sweep's row / column sums are reductions at L2: make them visible before B3 loads them
       __syncthreads();
       UNI_CLK(11);
       for (int o = tid; o < D + P; o += NT) {   // B1b's per-warp rows -> raw moments (accPA = accPm + D: pairs follow)
