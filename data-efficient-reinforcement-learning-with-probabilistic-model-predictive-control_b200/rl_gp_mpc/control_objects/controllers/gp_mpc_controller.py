@@ -5,8 +5,11 @@ its objective evaluated by the B200 CUDA engine.
   compute_mean_lcb_trajectory_batch  NEW: B candidate sequences in one call -> costs (B,), grads (B, H*Na)
   get_action / _get_optimal_actions  gp_mpc_controller.py:52-153  same orchestration (scipy L-BFGS-B, restarts)
 The five side-effect tensors (:279-283) are kept; for a batch they describe the best candidate."""
+import atexit
 import multiprocessing
+import sys
 import threading
+import weakref
 
 import numpy as np
 import torch
@@ -30,16 +33,21 @@ from .iteration_info_class import IterationInformation
 
 class _TrainingThread(threading.Thread):
     """threading.Thread with the few multiprocessing.Process members the controller logic relies on
-    (`_closed`, `close()`), so that check_and_close_processes reads like the reference's (:216-227)."""
+    (`_closed`, `close()`), so that check_and_close_processes reads like the reference's (:216-227).  The fit can be
+    asked to stop (`stop_event`, polled once per objective evaluation); live threads are stopped and joined at
+    interpreter exit, because a daemon thread killed inside a CUDA call aborts the process."""
+    _live = weakref.WeakSet()
 
     def __init__(self, target, args):
         super().__init__(target=self._guarded, daemon=True)
         self._fn, self._fn_args, self._closed = target, args, False
+        self.stop_event = threading.Event()
+        _TrainingThread._live.add(self)
 
     def _guarded(self):
         queue, saved_state = self._fn_args[0], self._fn_args[1]
         try:
-            self._fn(*self._fn_args)
+            self._fn(*self._fn_args, stop_event=self.stop_event)
         except Exception as exc:        # never leave the controller waiting on an empty queue
             print("training failed:", exc)
             saved_state.to_arrays()
@@ -47,6 +55,17 @@ class _TrainingThread(threading.Thread):
 
     def close(self):
         self._closed = True
+
+    def stop(self, timeout=60.0):
+        self.stop_event.set()
+        if self.is_alive():
+            self.join(timeout)
+
+
+@atexit.register
+def _stop_training_threads():
+    for t in list(_TrainingThread._live):
+        t.stop()
 
 
 class GpMpcController(BaseControllerObject):
@@ -210,6 +229,10 @@ class GpMpcController(BaseControllerObject):
                                        args=(self.queue_train, saved_state, tr.lr_train, tr.iter_train,
                                              tr.clip_grad_value, tr.print_train, tr.step_print_train,
                                              self.transition_model._device))
+        # the fit and the control loop both make many short blocking CUDA calls; with CPython's default 5 ms switch
+        # interval every hand-over of the interpreter lock can stall that long (measured: 26 ms per objective evaluation
+        # of the fit instead of ~1 ms), so the interval is shortened while both are active
+        sys.setswitchinterval(min(sys.getswitchinterval(), 2e-4))
         self.p_train.start()
 
     def check_and_close_processes(self):
@@ -220,6 +243,11 @@ class GpMpcController(BaseControllerObject):
                 model.initialize(**p)
             self.p_train.close()
             self._prepare()
+
+    def close(self):
+        """Stops a hyper-parameter fit that is still running (its result is dropped) -- call at the end of a run."""
+        if "p_train" in self.__dict__:
+            self.p_train.stop()
 
     # ------------------------------------------------------------------ objective
     def _bind_cost(self):

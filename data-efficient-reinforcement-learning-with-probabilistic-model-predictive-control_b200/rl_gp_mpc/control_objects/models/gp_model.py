@@ -214,7 +214,7 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
 
     @staticmethod
     def train(queue, saved_state, lr_train, num_iter_train, clip_grad_value, print_train=False, step_print_train=25,
-              device=None):
+              device=None, stop_event=None):
         """Hyper-parameter fitting with the reference's procedure (gp_model.py:193-306): for every GP, uniform random
         re-initialisation inside the Interval bounds, torch LBFGS (strong Wolfe) on the unconstrained parameters,
         keep the best negative marginal log-likelihood (per data point, as gpytorch's ExactMarginalLogLikelihood
@@ -249,6 +249,8 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
         class _NegMll(torch.autograd.Function):
             @staticmethod
             def forward(ctx, theta, y_col):            # theta = [lengthscale (D), outputscale, noise] constrained
+                if stop_event is not None and stop_event.is_set():
+                    raise InterruptedError("training stopped")
                 engine.prepare(x, y_col, theta[:d].reshape(1, d), theta[d:d + 1], theta[d + 1:d + 2])
                 out = engine.mll(y_col)[0].cpu()
                 grad = torch.cat([out[3:3 + d], out[1:3]])
@@ -268,6 +270,8 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
             best_theta = prev_theta.clone()
             try:
                 best_loss = float(_NegMll.apply(prev_theta, y_col))
+            except InterruptedError:
+                break
             except Exception:
                 best_loss = float("inf")
             prev_loss = best_loss
@@ -289,6 +293,8 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
                     if loss < best_loss:
                         best_loss = loss
                         best_theta = (lo + (hi - lo) * torch.sigmoid(raw)).detach().clone()
+            except InterruptedError:                   # controller shut down: hand back what is there
+                break
             except Exception as exc:                   # e.g. a trial point with a non positive definite kernel matrix
                 print(exc)
             print("training - model %d - time %.2f s - loss %.5f -> %.5f - outputscale %s - lengthscales %s - noise %s" % (
@@ -297,6 +303,8 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
             params_out.append({"covar_module.base_kernel.lengthscale": best_theta[:d].reshape(1, d).numpy(),
                                "covar_module.outputscale": best_theta[d].reshape(()).numpy(),
                                "likelihood.noise": best_theta[d + 1].reshape(1).numpy()})
+        for prev in saved_state.parameters[len(params_out):]:      # stopped early: the remaining GPs keep their values
+            params_out.append({k: np.asarray(v) for k, v in prev.items()})
         queue.put(params_out)
 
     def save_state(self):

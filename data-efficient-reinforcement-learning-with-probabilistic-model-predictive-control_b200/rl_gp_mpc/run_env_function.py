@@ -39,6 +39,7 @@ def run_env(env, control_config: Config, visu_config: VisuConfig, random_actions
             print(str(iter_info))
     visu_obj.save(ctrl_obj)
     ctrl_obj.check_and_close_processes()
+    ctrl_obj.close()                    # a hyper-parameter fit still running is stopped, not abandoned mid-kernel
     if hasattr(env, "close"):
         env.close()
     visu_obj.close()
