@@ -272,12 +272,57 @@ class GpMpcController(BaseControllerObject):
         self.rewards_traj_var = out["rewards_traj_var"][idx].cpu()
         self.states_var_pred = out["states_var_pred"][idx].cpu()
 
+    def _packed_outputs(self, batch):
+        """One flat device buffer holding every output of a rollout of `batch` sequences, plus views into it in the
+        engine's naming -- so that the legacy single-sequence call brings everything back with ONE device-to-host copy
+        (it is called once per L-BFGS-B iteration: six separate .cpu() syncs were 40 % of its latency)."""
+        key = (batch, self.config.controller.len_horizon)
+        if getattr(self, "_packed_key", None) != key:
+            h, e, na = self.config.controller.len_horizon, self.transition_model.dim_state, self.actions_mapper.dim_action
+            shapes = [("cost", (batch,)), ("grad", (batch, h * na)), ("states_mu_pred", (batch, h + 1, e)),
+                      ("states_var_pred", (batch, h + 1, e, e)), ("rewards_trajectory", (batch, h + 1)),
+                      ("rewards_traj_var", (batch, h + 1)), ("actions_model", (batch, h, na))]
+            total = sum(int(np.prod(sh)) for _, sh in shapes)
+            flat = torch.empty(total, dtype=torch.float64, device=self.transition_model.engine.device)
+            host = torch.empty(total, dtype=torch.float64).pin_memory()
+            views, hviews, off = {}, {}, 0
+            for name, sh in shapes:
+                n = int(np.prod(sh))
+                views[name] = flat[off:off + n].view(sh)
+                hviews[name] = host[off:off + n].view(sh)
+                off += n
+            self._packed_key, self._packed = key, (flat, host, views, hviews)
+        return self._packed
+
     def compute_mean_lcb_trajectory(self, actions_mpc, obs_mu, obs_var):
         """(H*Na,) numpy -> (float, numpy (H*Na,)): LCB of the mean trajectory cost and its gradient."""
-        a = torch.as_tensor(np.asarray(actions_mpc, dtype=np.float64)).reshape(1, -1)
-        out = self._rollout(a, obs_mu, obs_var, need_grad=True)
-        self._store_side_effects(out, 0)
-        return out["cost"][0].item(), out["grad"][0].cpu().numpy()
+        flat, host, views, hviews = self._packed_outputs(1)
+        # inputs: one pinned staging buffer, one host-to-device copy
+        e = self.transition_model.dim_state
+        na_h = self.config.controller.len_horizon * self.actions_mapper.dim_action
+        if getattr(self, "_in_host", None) is None or self._in_host.numel() != na_h + e + e * e:
+            self._in_host = torch.empty(na_h + e + e * e, dtype=torch.float64).pin_memory()
+            self._in_dev = torch.empty_like(self._in_host, device=flat.device)
+        self._in_host[:na_h] = torch.as_tensor(np.asarray(actions_mpc, dtype=np.float64)).reshape(-1)
+        self._in_host[na_h:na_h + e] = torch.as_tensor(obs_mu, dtype=torch.float64).reshape(-1)
+        self._in_host[na_h + e:] = torch.as_tensor(obs_var, dtype=torch.float64).reshape(-1)
+        self._in_dev.copy_(self._in_host, non_blocking=True)
+        a = self._in_dev[:na_h].view(1, na_h)
+        obs_mu, obs_var = self._in_dev[na_h:na_h + e], self._in_dev[na_h + e:].view(e, e)
+        self._bind_cost()
+        am = self.actions_mapper
+        limit = bool(self.config.actions.limit_action_change)
+        self.transition_model.engine.rollout(
+            a, obs_mu, obs_var, self.config.controller.len_horizon, iter_ctrl=self.iter_ctrl, limit_action_change=limit,
+            max_change=self.config.actions.max_change_action_norm if limit else None,
+            action_prev=am.action_model_previous_iter if limit else None, need_grad=True, out=dict(views))
+        host.copy_(flat)                                   # one synchronous device-to-host copy
+        self.cost_traj_mean_lcb = -hviews["cost"][0].clone()
+        self.states_mu_pred = hviews["states_mu_pred"][0].clone()
+        self.rewards_trajectory = hviews["rewards_trajectory"][0].clone()
+        self.rewards_traj_var = hviews["rewards_traj_var"][0].clone()
+        self.states_var_pred = hviews["states_var_pred"][0].clone()
+        return float(hviews["cost"][0]), hviews["grad"][0].numpy().copy()
 
     def compute_mean_lcb_trajectory_batch(self, actions_mpc, obs_mu, obs_var, need_grad=True):
         """(B, H*Na) -> costs (B,), grads (B, H*Na) as CUDA tensors; side effects = best candidate."""
