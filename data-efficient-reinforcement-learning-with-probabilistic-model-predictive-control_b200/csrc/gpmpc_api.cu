@@ -46,7 +46,7 @@ struct gpmpc_handle {
   DevBuf c_target, c_W, c_WT, c_smin, c_smax;
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
-  DevBuf dbg_clk, ws_uni, queue;
+  DevBuf dbg_clk, ws_uni, queue, ws_cl;
   DevBuf ws_kk, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
   long long launches = 0;
   bool timing = false;
@@ -155,7 +155,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
-                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue};
+                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue, &h->ws_cl};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -427,10 +427,27 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     int thr_f, grid_f, thr_b, grid_b;
     plan(smf, &thr_f, &grid_f, "GPMPC_UNI_FWD_THREADS", "GPMPC_UNI_FWD_CTAS");
     plan(smb, &thr_b, &grid_b, "GPMPC_UNI_BWD_THREADS", "GPMPC_UNI_BWD_CTAS");
-    {  // small training sets: finer chunks so that every warp of the sweeps gets a run
+    // Small batches (fewer candidates than SMs, e.g. the single sequence scipy's L-BFGS-B evaluates): a thread-block
+    // cluster of 2 / 4 / 8 CTAs shares each candidate, provided the tile triangle has >= 2 chunks of 8 columns per warp.
+    p.cluster = 1;
+    {
+      const int nrb = h->NP / 64, chunks8 = 8 * nrb * (nrb + 1) / 2;
+      int c = 8;
+      while (c > 1 && (B * c > h->num_sms || chunks8 < 2 * c * (thr_f / 32))) c /= 2;
+      if (E <= 5) p.cluster = c;       // the 255-register kernels (E > 5) stay on the plain path
+      if (const char* e = getenv("GPMPC_UNI_CLUSTER")) { int v = atoi(e); if (v == 1 || ((v == 2 || v == 4 || v == 8) && B * v <= h->num_sms)) p.cluster = v; }
+    }
+    if (p.cluster > 1) {
+      grid_f = grid_b = B * p.cluster;
+      thr_f = thr_b = 256;
+      CU(h->ws_cl.ensure(sizeof(double) * (size_t)B * 3 * 64));
+      CU(cudaMemsetAsync(h->ws_cl.ptr, 0, sizeof(double) * (size_t)B * 3 * 64, st));
+      p.ws_cl = h->ws_cl.as<double>();
+    }
+    {  // small training sets / clusters: finer chunks so that every warp of the sweeps gets a run
       const int nrb = h->NP / 64;
-      while (p.seg > 8 && (64 / p.seg) * nrb * (nrb + 1) / 2 < 2 * (thr_f / 32)) p.seg /= 2;
-      while (p.seg_bwd > 8 && (64 / p.seg_bwd) * nrb * (nrb + 1) / 2 < 2 * (thr_b / 32)) p.seg_bwd /= 2;
+      while (p.seg > 8 && (64 / p.seg) * nrb * (nrb + 1) / 2 < 2 * p.cluster * (thr_f / 32)) p.seg /= 2;
+      while (p.seg_bwd > 8 && (64 / p.seg_bwd) * nrb * (nrb + 1) / 2 < 2 * p.cluster * (thr_b / 32)) p.seg_bwd /= 2;
     }
     if (const char* e = getenv("GPMPC_UNI_SEG")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) p.seg = v; }
     if (const char* e = getenv("GPMPC_UNI_SEG_BWD")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) p.seg_bwd = v; }
@@ -446,7 +463,13 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     if (h->timing) { CU(cudaEventRecord(h->ev[1], st)); h->ev_fwd = true; }
     h->ev_bwd = false;
     if (want_grad) {
-      CU(h->ws_uni.ensure(sizeof(double) * (size_t)grid_b * h->NP * (2 + E)));   // zeroed by the kernel itself
+      const size_t scr = sizeof(double) * (size_t)h->NP * (2 + E);
+      if (p.cluster > 1) {             // three rotating buffers per cluster, zeroed here
+        CU(h->ws_uni.ensure(scr * 3 * B));
+        CU(cudaMemsetAsync(h->ws_uni.ptr, 0, scr * 3 * B, st));
+      } else {
+        CU(h->ws_uni.ensure(scr * grid_b));   // zeroed by the kernel itself
+      }
       p.ws_uni = h->ws_uni.as<double>();
       if (h->timing) CU(cudaEventRecord(h->ev[2], st));
       CU(launch_uniform(E, true, p, grad, grid_b, thr_b, smb, st));

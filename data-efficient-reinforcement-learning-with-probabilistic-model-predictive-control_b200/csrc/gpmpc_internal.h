@@ -43,6 +43,8 @@ struct RolloutParams {
   int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
   int* queue;          // candidate counters of the dynamic scheduling (SMs differ in speed by up to ~25 % on this workload:
                        // L2 distance): [0] uniform forward, [1] uniform reverse sweep, [2] general kernel; NULL = round-robin
+  int cluster;         // uniform kernels: CTAs (thread-block cluster) sharing one candidate, 1 = none (small batches only)
+  double* ws_cl;       // uniform forward, cluster mode: (clusters, 3, 64) accumulators of the sweep sums (zeroed by the host)
   long long* dbg_clk;  // tuning aid (GPMPC_DEBUG_CLOCKS): CTA 0 accumulates clock64() deltas per phase here, else NULL
 };
 

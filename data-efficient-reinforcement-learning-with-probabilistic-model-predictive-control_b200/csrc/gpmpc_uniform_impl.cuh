@@ -40,6 +40,21 @@ __device__ __forceinline__ int uni_next_candidate(const RolloutParams& p, int k,
   __syncthreads();
   return c;
 }
+// Thread-block clusters for small batches: with fewer candidates than SMs, p.cluster (2, 4 or 8) CTAs on neighbouring
+// SMs share ONE candidate.  Every CTA repeats the cheap O(N) / O(E^3) phases (bitwise identically), the tile-triangle
+// sweep is split over all their warps, and the partial sums meet in L2 (float64 RED into a per-cluster accumulator,
+// rotating over three buffers so that zeroing never races with the next step) followed by ONE hardware cluster barrier
+// per horizon step.  Only the cluster's rank-0 CTA writes outputs.
+__device__ __forceinline__ unsigned uni_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void uni_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// float64 reduction at L2 without a return value (RED.E.ADD.F64: fire and forget)
+__device__ __forceinline__ void uni_red_add(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forward sweep (P + 1 <= 37 used)
+
 #ifndef UNI_MINB
 #define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
 #endif
@@ -247,18 +262,24 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 
   long long clk_ = clock64();
   UNI_CTA_BEGIN();
-  for (;;) {
-    const int cand = uni_next_candidate(p, 0, s_int, tid);
+  const int C = p.cluster;                                  // CTAs per candidate (1: no cluster)
+  const int crank = C > 1 ? (int)uni_cluster_rank() : 0, cid = blockIdx.x / C;
+  const bool lead = crank == 0;                             // writes the outputs
+  double* cl_acc = C > 1 ? p.ws_cl + (size_t)cid * 3 * UNI_CL_ACC : nullptr;
+  int gstep = 0;                                            // running step count: accumulator buffer = gstep % 3
+  for (int cand_static = cid;; cand_static += gridDim.x / C) {
+    // clusters walk the candidates in lock step (their barriers must match); single CTAs draw from the global counter
+    const int cand = C > 1 ? cand_static : uni_next_candidate(p, 0, s_int, tid);
     if (cand >= p.B) break;
     if (tid < E) {
       double v = p.obs_mu[(p.per_cand_init ? (size_t)cand * E : 0) + tid];
       s_mu[tid] = v;
-      p.states_mu[((size_t)cand * (H + 1)) * E + tid] = v;
+      if (lead) p.states_mu[((size_t)cand * (H + 1)) * E + tid] = v;
     }
     if (tid < E * E) {
       double v = p.obs_var[(p.per_cand_init ? (size_t)cand * E * E : 0) + tid];
       s_s[tid] = v;
-      p.states_var[((size_t)cand * (H + 1)) * E * E + tid] = v;
+      if (lead) p.states_var[((size_t)cand * (H + 1)) * E * E + tid] = v;
     }
     if (tid < Na) {
       double cum = 0.0;
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
           am = raw;
         }
         s_am[t * Na + tid] = am;
-        p.actions_model[(size_t)cand * H * Na + t * Na + tid] = am;
+        if (lead) p.actions_model[(size_t)cand * H * Na + t * Na + tid] = am;
       }
     }
     __syncthreads();
@@ -365,8 +386,8 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
       //      in row-major order, are dealt to the warps in equal contiguous runs (cut at row-block boundaries).
       {
         const int CH = p.seg, nrb = NP / 64, cpt = 64 / CH;       // chunks per 64-column tile
-        const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps - 1) / nwarps;
-        int c0 = warp * per;
+        const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps * C - 1) / (nwarps * C);
+        int c0 = (crank * nwarps + warp) * per;
         const int c1 = min(T, c0 + per);
         int I = 0, base = 0;
         while (c0 < c1) {
@@ -378,12 +399,25 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         }
       }
       __syncthreads();
+      if (C > 1) {   // cluster: this CTA's share of the sweep sums -> L2 accumulator of the step, then the cluster barrier
+        double* acc = cl_acc + (gstep % 3) * UNI_CL_ACC;
+        if (warp == 0)
+          for (int k = lane; k <= P; k += 32) {
+            double v = 0.0;
+            for (int w = 0; w < nwarps; w++) v += s_part[w * L.partlen + k];
+            uni_red_add(acc + k, v);
+          }
+        if (lead && warp == 1)
+          for (int k = lane; k < UNI_CL_ACC; k += 32) cl_acc[((gstep + 1) % 3) * UNI_CL_ACC + k] = 0.0;   // next step's buffer
+        __threadfence();
+        uni_cluster_sync();
+      }
       UNI_CLK(2);
       // ---- P4: mean, V, S, recurrence (gp_model.py:150-180, :92-99): warp 0, one small stage per __syncwarp
       if (warp == 0) {
         const double c = s_misc[0], detR = s_misc[1], rs = 1.0 / sqrt(detR);
         const bool bad = s_int[1] != 0;
-        double* rec = p.records ? p.records + ((size_t)cand * H + (t - 1)) * RL.size : nullptr;
+        double* rec = (p.records && lead) ? p.records + ((size_t)cand * H + (t - 1)) * RL.size : nullptr;
         // A: add up the per-warp partial rows
         for (int o = lane; o < E * nOut; o += 32) {
           double v = 0.0;
@@ -392,7 +426,8 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         }
         for (int k = lane; k <= P; k += 32) {
           double v = 0.0;
-          for (int w = 0; w < nwarps; w++) v += s_part[w * L.partlen + k];
+          if (C > 1) v = __ldcg(cl_acc + (gstep % 3) * UNI_CL_ACC + k);
+          else for (int w = 0; w < nwarps; w++) v += s_part[w * L.partlen + k];
           s_acc[k] = v;
         }
         __syncwarp();
@@ -457,20 +492,21 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
           const int o = lane + 32 * r;
           if (o < E * E) {
             s_s[o] = sn[r];
-            p.states_var[((size_t)cand * (H + 1) + t) * E * E + o] = sn[r];
+            if (lead) p.states_var[((size_t)cand * (H + 1) + t) * E * E + o] = sn[r];
           }
         }
         if (lane < E) {
           double v = s_mu[lane] + s_M[lane];
           if (bad) v = nan("");
           s_mu[lane] = v;
-          p.states_mu[((size_t)cand * (H + 1) + t) * E + lane] = v;
+          if (lead) p.states_mu[((size_t)cand * (H + 1) + t) * E + lane] = v;
         }
       }
+      gstep++;
       __syncthreads();
       UNI_CLK(3);
     }
-    if (tid == 0) {
+    if (tid == 0 && lead) {
       double cmu, cvar;
       terminal_cost(cv, E, s_mu, s_s, cmu, cvar);
       s_r[H] = -cmu;
@@ -552,7 +588,7 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
     }
     int col;
     double tot = col_reduce8(v, lane, col);
-    if ((lane & 3) == 0) atomicAdd(g_gam + j0 + col, tot);
+    if ((lane & 3) == 0) uni_red_add(g_gam + j0 + col, tot);
   }
 }
 
@@ -608,10 +644,10 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   }
   uni_bwd_cols<EV>(p, s_rec, rlen, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, p0, p1, wbar, rho0, rho1, xi0, xi1, lane,
                    g_gam, s_tab);
-  atomicAdd(g_rho + i0, rho0);
-  atomicAdd(g_rho + i1, rho1);
+  uni_red_add(g_rho + i0, rho0);
+  uni_red_add(g_rho + i1, rho1);
 #pragma unroll
-  for (int e = 0; e < EV; e++) { atomicAdd(g_xi + (size_t)e * NP + i0, xi0[e]); atomicAdd(g_xi + (size_t)e * NP + i1, xi1[e]); }
+  for (int e = 0; e < EV; e++) { uni_red_add(g_xi + (size_t)e * NP + i0, xi0[e]); uni_red_add(g_xi + (size_t)e * NP + i1, xi1[e]); }
 }
 
 // O(N) reductions of the reverse sweep.  Every thread has summed, over its own training points, P "pair" values
@@ -716,10 +752,17 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const int oA = 0, oQ = EV * EV, oRi = 2 * EV * EV, odS = 3 * EV * EV, oc = 4 * EV * EV, odet = oc + 1, odmu = oc + 2,
             oda = odmu + EV;
   double* s_rec = sm + L.rec;
-  // per-CTA global scratch of the sweep's row / column sums (L2 resident): gam[NP], rho[NP], xi[EV][NP]
-  double* g_gam = p.ws_uni + (size_t)blockIdx.x * NP * (2 + EV);
+  // global scratch of the sweep's row / column sums (L2 resident): gam[NP], rho[NP], xi[EV][NP] -- one per CTA, or three
+  // per cluster (rotating with the step, see uni_cluster_sync) when p.cluster CTAs share a candidate
+  const int C = p.cluster;
+  const int crank = C > 1 ? (int)uni_cluster_rank() : 0, cid = blockIdx.x / C;
+  const bool lead = crank == 0;
+  const size_t scr = (size_t)NP * (2 + EV);
+  double* g_base = p.ws_uni + (C > 1 ? (size_t)cid * 3 : (size_t)blockIdx.x) * scr;
+  double* g_gam = g_base;
   double* g_rho = g_gam + NP;
   double* g_xi = g_rho + NP;
+  int gstep = 0;
   const int warp = tid >> 5, nwarps = NT >> 5;
   double* s_wp = sm + L.wp; double* s_wp2 = s_wp + 8 * L.wplen;   // per-warp rows of the B1 / B3 point sums
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
@@ -734,15 +777,16 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
   for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
-  for (int i = tid; i < NP * (2 + EV); i += NT) g_gam[i] = 0.0;   // B3a re-zeroes after every step
+  if (C == 1)
+    for (int i = tid; i < NP * (2 + EV); i += NT) g_gam[i] = 0.0;   // B3 re-zeroes after every step (clusters: host memset)
   __syncthreads();
   // accumulator layout: [0] unused, [1 .. D] G_m, [1+D .. 1+D+E2) G_Q, then N-pass: Phi_m[D], Phi_A[P]
   const int accGm = 1, accGQ = 1 + D, accPm = 1 + D + EV * EV, accPA = accPm + D;
 
   long long clk_ = clock64();
   UNI_CTA_BEGIN();
-  for (;;) {
-    const int cand = uni_next_candidate(p, 1, s_int, tid);
+  for (int cand_static = cid;; cand_static += gridDim.x / C) {
+    const int cand = C > 1 ? cand_static : uni_next_candidate(p, 1, s_int, tid);
     if (cand >= p.B) break;
     const double* mus = p.states_mu + (size_t)cand * (H + 1) * E;
     const double* vars = p.states_var + (size_t)cand * (H + 1) * E * E;
@@ -932,10 +976,15 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       {
         const double wbar = s_scal[3];
         const int CH = p.seg_bwd, nrb = NP / 64, cpt = 64 / CH;
-        const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps - 1) / nwarps;
-        int c0 = warp * per;
+        const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps * C - 1) / (nwarps * C);
+        int c0 = (crank * nwarps + warp) * per;
         const int c1 = min(T, c0 + per);
         int I = 0, base = 0;
+        if (C > 1) {   // this step's buffer of the cluster scratch
+          g_gam = g_base + (size_t)(gstep % 3) * scr;
+          g_rho = g_gam + NP;
+          g_xi = g_rho + NP;
+        }
         while (c0 < c1) {
           while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
           const int ce = min(c1, base + cpt * (nrb - I));
@@ -946,6 +995,13 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
       }
       __threadfence();   // the sweep's row / column sums are reductions at L2: make them visible before B3 loads them
       __syncthreads();
+      if (C > 1) {
+        uni_cluster_sync();
+        // the buffer of step gstep + 2 (last read at step gstep - 1) is cleared now, a slice per CTA: every CTA passes the
+        // next barrier only after its slice is done, and the reductions into that buffer start after that barrier
+        double* nz = g_base + (size_t)((gstep + 2) % 3) * scr;
+        for (int i = crank * NT + tid; i < (int)scr; i += C * NT) nz[i] = 0.0;
+      }
       UNI_CLK(11);
       for (int o = tid; o < D + P; o += NT) {   // B1b's per-warp rows -> raw moments (accPA = accPm + D: pairs follow)
         double v = 0.0;
@@ -965,10 +1021,12 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         const double gv = __ldcg(g_gam + i), rv = __ldcg(g_rho + i);   // all loads first (the stores below may alias)
 #pragma unroll
         for (int e = 0; e < EV; e++) xv[e] = __ldcg(g_xi + (size_t)e * NP + i);
-        g_gam[i] = 0.0;
-        g_rho[i] = 0.0;
+        if (C == 1) {
+          g_gam[i] = 0.0;
+          g_rho[i] = 0.0;
 #pragma unroll
-        for (int e = 0; e < EV; e++) g_xi[(size_t)e * NP + i] = 0.0;
+          for (int e = 0; e < EV; e++) g_xi[(size_t)e * NP + i] = 0.0;
+        }
         const double g = gv + rv;
 #pragma unroll
         for (int e = 0; e < EV; e++) {
@@ -1100,14 +1158,16 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         } else {
           uni_stage_adjoint<EV>(p, Na, wmu, -p.kappa * wmu * 0.5 / sqrt(rvs[t - 1]), mup, sp, am, nmu, a_bar, nsb);
         }
-        for (int k = 0; k < Na; k++) gout[(size_t)(t - 1) * Na + k] = a_bar[k];
+        if (lead)
+          for (int k = 0; k < Na; k++) gout[(size_t)(t - 1) * Na + k] = a_bar[k];
         for (int e = 0; e < E; e++) s_mubar[e] = nmu[e];
         for (int e = 0; e < E * E; e++) s_sbar[e] = nsb[e];
       }
+      gstep++;
       __syncthreads();
       UNI_CLK(13);
     }
-    if (p.limit_change && tid < Na) {
+    if (p.limit_change && tid < Na && lead) {
       double cum = 0.0;
       for (int t = H - 1; t >= 0; t--) {
         cum += gout[(size_t)t * Na + tid];
@@ -1123,15 +1183,30 @@ template <int EV>
 cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem,
                                 cudaStream_t st) {
   cudaError_t e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (p.cluster > 1) {   // p.cluster consecutive CTAs form a thread-block cluster (grid is a multiple of it)
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
   if (bwd) {
     e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uniform_bwd_kernel<EV><<<grid, threads, smem, st>>>(p, grad);
+    e = cudaLaunchKernelEx(&cfg, uniform_bwd_kernel<EV>, p, grad);
   } else {
     e = cudaFuncSetAttribute(uniform_fwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uniform_fwd_kernel<EV><<<grid, threads, smem, st>>>(p);
+    e = cudaLaunchKernelEx(&cfg, uniform_fwd_kernel<EV>, p);
   }
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

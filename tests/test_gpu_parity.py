@@ -309,3 +309,29 @@ def test_uniform_path_large_state_dimension():
     np.testing.assert_allclose(got["cost"], want["cost"], rtol=0, atol=ATOL)
     np.testing.assert_allclose(got["grad"], want["grad"], rtol=0, atol=ATOL_GRAD)
     np.testing.assert_allclose(got["states_var_pred"], want["states_var_pred"], rtol=0, atol=ATOL)
+
+
+@pytest.mark.parametrize("kw", [dict(E=4, Na=2, N=500, H=6, B=1, ls=0.25), dict(E=3, Na=1, N=300, H=5, B=5, ls=0.5),
+                                dict(E=2, Na=1, N=200, H=7, B=20, ls=0.5, limit_action_change=True),
+                                dict(E=5, Na=2, N=260, H=4, B=2, ls=0.6, include_time_model=True)])
+def test_cluster_mode_matches_single_cta_mode(kw, monkeypatch):
+    """Small batches run with a thread-block cluster per candidate (sweep split over 2/4/8 CTAs, sums met in L2, one
+    cluster barrier per step).  Same numbers as the one-CTA-per-candidate path and as the oracle."""
+    cfg = make_workload(seed=11, **kw)
+    eng = make_engine(cfg)
+    assert eng.uses_uniform_path()
+    got = rollout(eng, cfg)                      # automatic: clusters (B * cluster <= number of SMs)
+    got2 = rollout(eng, cfg)                     # again: the rotating accumulators must come back clean
+    monkeypatch.setenv("GPMPC_UNI_CLUSTER", "1")
+    plain = rollout(eng, cfg)
+    monkeypatch.setenv("GPMPC_UNI_CLUSTER", "2")
+    two = rollout(eng, cfg)
+    monkeypatch.delenv("GPMPC_UNI_CLUSTER")
+    for other in (got2, plain, two):
+        for key in ("cost", "grad", "states_mu_pred", "states_var_pred", "rewards_trajectory", "rewards_traj_var"):
+            np.testing.assert_allclose(got[key], other[key], rtol=0, atol=1e-9, err_msg=key)
+    want = orc.evaluate_workload(cfg, candidates=[0])
+    np.testing.assert_allclose(got["cost"][:1], want["cost"], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(got["grad"][:1], want["grad"].reshape(1, -1), rtol=0, atol=ATOL_GRAD)
+    fwd_only = rollout(eng, cfg, need_grad=False)
+    np.testing.assert_allclose(fwd_only["cost"], got["cost"], rtol=0, atol=1e-9)
