@@ -308,11 +308,22 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
     *grid = 0;
     return GPMPC_OK;
   }
-  const int G = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, h->smem_optin);
+  int G = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, h->smem_optin);
   if (G < 1) return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
+  // Small batches of rollouts: a thread-block cluster shares each candidate, one output pair (a, b) per group, the
+  // groups dealt to the CTAs (rollout_kernel).  Worth it once the N^2 sweeps dominate (NP >= 128).
+  p.cluster = 1;
+  if (H > 0) {
+    const int P = h->E * (h->E + 1) / 2;
+    int c = 8;
+    while (c > 1 && (B * c > h->num_sms || P < c || h->NP < 128)) c /= 2;
+    if (const char* e = getenv("GPMPC_GEN_CLUSTER")) { int v = atoi(e); if (v == 1 || ((v == 2 || v == 4 || v == 8) && B * v <= h->num_sms && P >= v)) c = v; }
+    p.cluster = c;
+    if (c > 1) { G = 1; p.seg = 32; }   // one pair per group; finer work items (16 warps share one pair's sweep)
+  }
   p.group = G;
   *smem = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G, H, Na);
-  *grid = B < h->num_sms ? B : h->num_sms;
+  *grid = p.cluster > 1 ? B * p.cluster : (B < h->num_sms ? B : h->num_sms);
   cudaError_t ce = h->ws_kk.ensure(sizeof(double) * (size_t)(*grid) * h->E * h->NP);
   if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
   p.ws_kk = h->ws_kk.as<double>();
@@ -509,9 +520,27 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     }
     return GPMPC_OK;
   }
+  if (p.cluster > 1) {   // exchange buffers of the cluster path: (B, 2, 64) doubles, plain stores (no zeroing needed)
+    CU(h->ws_cl.ensure(sizeof(double) * (size_t)B * 2 * 64));
+    p.ws_cl = h->ws_cl.as<double>();
+  }
+  const bool dbg_gen = getenv("GPMPC_DEBUG_CLOCKS") != nullptr;   // tuning aid: per-phase cycles of CTA 0 on stderr
+  if (dbg_gen) {
+    CU(h->dbg_clk.ensure(sizeof(long long) * (16 + 4 * 2048)));
+    CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * 16, st));
+    p.dbg_clk = h->dbg_clk.as<long long>();
+  }
   if (h->timing) CU(cudaEventRecord(h->ev[0], st));
   CU(launch_rollout(E, want_grad, p, grid, smem, st));
   h->launches += 1;
+  if (dbg_gen) {
+    long long c[16];
+    CU(cudaMemcpyAsync(c, h->dbg_clk.ptr, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const long long ns = (long long)((B + grid / p.cluster - 1) / (grid / p.cluster)) * H;
+    fprintf(stderr, "[gpmpc general clocks/step, CTA 0, cluster %d, group %d] P0a %lld  P0b %lld  P1 %lld  P2 %lld  P2b %lld | per step over its pairs: P3 setup %lld  sweep %lld  reduce %lld  finalize+next %lld | exchange %lld  P4 %lld\n",
+            p.cluster, p.group, c[0] / ns, c[1] / ns, c[2] / ns, c[3] / ns, c[4] / ns, c[5] / ns, c[6] / ns, c[7] / ns, c[9] / ns, c[8] / ns, 0LL);
+  }
   if (h->timing) { CU(cudaEventRecord(h->ev[1], st)); h->ev_fwd = true; }
   h->ev_bwd = false;
   if (want_grad) {

@@ -183,6 +183,14 @@ __device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4
 }
 
 // ---------------------------------------------------------------------------------------------
+// Thread-block cluster helpers (small batches: several CTAs on neighbouring SMs share one candidate).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned uni_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void uni_cluster_sync() {   // all threads of all CTAs of the cluster; orders global memory too
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small dense SPD helpers (n <= 8), used once per step per GP / pair.
 // ---------------------------------------------------------------------------------------------
 // inv = a^-1, det = det(a) for symmetric positive definite a (n x n, row-major).  A non-positive

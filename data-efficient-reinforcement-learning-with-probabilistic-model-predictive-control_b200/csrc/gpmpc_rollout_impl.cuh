@@ -166,7 +166,7 @@ __device__ __forceinline__ double warp_reduce_multi(double (&v)[K2], int lane, i
 // The hot loop: one warp, rows {64 I + lane, 64 I + 32 + lane}, columns [jbeg, jend).
 //   t_ij = kap_i + kap_j + u_i . nu_j ;  w_ij = (beta_a,i beta_b,j - [a==b] iK_a,ij) exp(t_ij)
 // gp_model.py:161-175 (X, X2, Q, maha, k, L, beta L beta, iK * L) collapsed to one exponent.
-// Diagonal pairs (a == b) sweep only j >= i with weights {j>i: 1, j==i: 1/2}; the caller doubles.
+// Diagonal pairs (a == b) sweep only the tiles on or above the diagonal (diagonal tile: half weights); the caller doubles.
 // ---------------------------------------------------------------------------------------------
 template <int EV, bool GRAD, bool DIAG>
 __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* __restrict__ s_nu,
@@ -211,7 +211,9 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
 
   for (int j0 = jbeg; j0 < jend; j0 += 8) {
-    const bool masked = DIAG && (j0 < 64 * I + 64);
+    // diagonal pairs: the diagonal tile is swept in full with HALF weights instead of its upper triangle -- w is symmetric
+    // and every consumer of (rho, gam, xi) is invariant under that swap (see uni_bwd_item), so no element masks
+    const double wgt = (DIAG && j0 < 64 * I + 64) ? 0.5 : 1.0;
     double v[8];
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
@@ -235,12 +237,9 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
         t0 = fma(u0[e], nj[e], t0);
         t1 = fma(u1[e], nj[e], t1);
       }
+      if (DIAG) { c0 *= wgt; c1 *= wgt; }
       double w0 = c0 * exp2s(t0, s_tab);
       double w1 = c1 * exp2s(t1, s_tab);
-      if (masked) {
-        w0 = (j > i0) ? w0 : ((j == i0) ? 0.5 * w0 : 0.0);
-        w1 = (j > i1) ? w1 : ((j == i1) ? 0.5 * w1 : 0.0);
-      }
       rho0 += w0;
       rho1 += w1;
       if (GRAD) {
@@ -312,7 +311,15 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   const unsigned s_tab = exp2s_table_addr(s_tabp);
   const int nOut = L.nOut, PV = L.PV;
   const RecLayout RL = rec_layout(E, D);
-  const CostView cv{p.c_target, p.c_W, p.c_WT, p.c_smin, p.c_smax, p.kappa, p.use_constraints};
+  // cost description staged in shared memory (the stage cost is on the serial path of every step)
+  double* s_cst = sm + L.cst;
+  if (p.mode == 0) {
+    for (int i = tid; i < E + Na; i += NT) s_cst[i] = p.c_target[i];
+    for (int i = tid; i < (E + Na) * (E + Na); i += NT) s_cst[GPMPC_MAX_D + i] = p.c_W[i];
+    for (int i = tid; i < E * E; i += NT) s_cst[GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + i] = p.c_WT[i];
+  }
+  const CostView cv{s_cst, s_cst + GPMPC_MAX_D, s_cst + GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D, p.c_smin, p.c_smax,
+                    p.kappa, p.use_constraints};
 
   // ---- candidate-independent constants
   for (int o = tid; o < E * D; o += NT) s_il2[o] = p.il2[o];
@@ -334,9 +341,37 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
 
   // candidates are drawn from a global counter when the host provides one (rollouts; SM speeds differ by up to ~25 %,
   // see the uniform kernels), else dealt round-robin (single steps)
+  // Small batches: a thread-block cluster of C CTAs shares each candidate.  The output pairs (a, b) -- independent N^2
+  // sweeps -- are dealt to the CTAs (one pair per group, balanced by their cost); everything else is repeated by every
+  // CTA bitwise identically; the S_raw of the pairs are exchanged through L2 (two buffers alternating with the step)
+  // around ONE cluster barrier per horizon step; records of a pair are written by its owner, all other outputs by rank 0.
+  const int C = (p.mode == 0) ? p.cluster : 1;
+  const int crank = C > 1 ? (int)uni_cluster_rank() : 0, cid = blockIdx.x / C;
+  const bool lead = crank == 0;
+  int gstep = 0;
+  long long clk_ = clock64();
+#define GEN_CLK(k) do { if (p.dbg_clk && blockIdx.x == 0 && tid == 0) { const long long c_ = clock64(); p.dbg_clk[k] += c_ - clk_; clk_ = c_; } } while (0)
   __shared__ int s_next;
-  for (int cand = blockIdx.x;; cand += gridDim.x) {
-    if (p.queue) {
+  __shared__ double s_one;
+  if (tid == 0) s_one = 1.0;
+  __shared__ unsigned char s_owner[GPMPC_MAX_EV * (GPMPC_MAX_EV + 1) / 2];   // cluster rank that sweeps pair pr
+  if (tid == 0) {   // longest-processing-time deal: off-diagonal pairs sweep N^2 elements, diagonal ones half of that
+    int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pass = 0; pass < 2; pass++) {
+      int pr = 0;
+      for (int a = 0; a < E; a++)
+        for (int b = a; b < E; b++, pr++) {
+          if ((a == b) != (pass == 1)) continue;
+          int best = 0;
+          for (int c = 1; c < C; c++)
+            if (load[c] < load[best]) best = c;
+          load[best] += (a == b) ? 1 : 2;
+          s_owner[pr] = (unsigned char)best;
+        }
+    }
+  }
+  for (int cand = cid;; cand += gridDim.x / C) {
+    if (p.queue && C == 1) {
       if (tid == 0) s_next = atomicAdd(p.queue + 2, 1);
       __syncthreads();
       cand = s_next;
@@ -348,12 +383,12 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
       if (tid < E) {
         double v = p.obs_mu[(p.per_cand_init ? (size_t)cand * E : 0) + tid];
         s_mu[tid] = v;
-        p.states_mu[((size_t)cand * (H + 1)) * E + tid] = v;
+        if (lead) p.states_mu[((size_t)cand * (H + 1)) * E + tid] = v;
       }
       if (tid < E * E) {
         double v = p.obs_var[(p.per_cand_init ? (size_t)cand * E * E : 0) + tid];
         s_s[tid] = v;
-        p.states_var[((size_t)cand * (H + 1)) * E * E + tid] = v;
+        if (lead) p.states_var[((size_t)cand * (H + 1)) * E * E + tid] = v;
       }
       if (tid < Na) {  // action mapping (normalization_action_mapper.py:21-23 / derivative_action_mapper.py:28-35)
         double cum = 0.0;
@@ -370,7 +405,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
             am = raw;
           }
           s_am[t * Na + tid] = am;
-          p.actions_model[(size_t)cand * H * Na + t * Na + tid] = am;
+          if (lead) p.actions_model[(size_t)cand * H * Na + t * Na + tid] = am;
         }
       }
     } else {
@@ -388,13 +423,8 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         else v = (double)(p.iter_ctrl + t - 1);   // gp_model.py:101-102 (un-normalised time index)
         s_m[tid] = v;
       }
-      if (tid == 32 && p.mode == 0) {
-        double cmu, cvar;
-        stage_cost(cv, E, Na, s_mu, s_s, s_am + (t - 1) * Na, cmu, cvar);
-        s_r[t - 1] = -cmu;
-        s_rv[t - 1] = cvar;
-      }
       __syncthreads();
+      GEN_CLK(0);
       // ================================================================ P0b: small matrices
       if (tid < E) {
         const int a = tid;
@@ -411,6 +441,11 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         pair_matrices<EV>(s_s, s_Wd + pr * EV, Rinv, Qm, detR);
         for (int e = 0; e < EV * EV; e++) s_Q[pr * EV * EV + e] = Qm[e];
         s_detR[pr] = detR;
+      } else if (tid == 128 && p.mode == 0) {   // stage cost of the current state (serial, overlaps the matrix work)
+        double cmu, cvar;
+        stage_cost(cv, E, Na, s_mu, s_s, s_am + (t - 1) * Na, cmu, cvar);
+        s_r[t - 1] = -cmu;
+        s_rv[t - 1] = cvar;
       } else if (tid == 100) {
         double chk = 0.0;
         for (int d = 0; d < D; d++) chk += s_m[d];
@@ -418,7 +453,9 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         s_int[1] = isfinite(chk) ? 0 : 1;
       }
       __syncthreads();
+      GEN_CLK(1);
       // ================================================================ P1: nu, lb, kk  (gp_model.py:138-148,168)
+      for (int o = tid; o < E * nOut; o += NT) s_out[o] = 0.0;
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
@@ -456,30 +493,52 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         }
       }
       __syncthreads();
+      GEN_CLK(2);
       // ================================================================ P2: O(N) moment sums
-      for (int o = tid; o < E * nOut; o += NT) {
-        const int a = o / nOut, q = o - a * nOut;
-        const double* lb = s_lb + a * NP;
-        double acc = 0.0;
-        if (q == 0) {
-          for (int i = 0; i < N; i++) acc += lb[i];
-        } else if (q <= D) {
-          const int d1 = q - 1;
-          for (int i = 0; i < N; i++) acc = fma(lb[i], s_nu[i * DP + d1], acc);
-        } else if (q < 1 + D + EV * D) {
-          const int qq = q - 1 - D, e1 = qq / D, d1 = qq - e1 * D;
-          for (int i = 0; i < N; i++) acc = fma(lb[i] * s_nu[i * DP + e1], s_nu[i * DP + d1], acc);
-        } else {
-          const int qq = q - 1 - D - EV * D, e1 = qq / PV;
-          int kl = qq - e1 * PV, k1 = 0;
-          while (kl >= EV - k1) { kl -= EV - k1; k1++; }
-          const int l1 = k1 + kl;
-          for (int i = 0; i < N; i++)
-            acc = fma(lb[i] * s_nu[i * DP + e1], s_nu[i * DP + k1] * s_nu[i * DP + l1], acc);
+      // lane per output (all lanes read the SAME training point: multicast LDS, no bank conflicts), the 32-output groups
+      // x 4 slices of the training points dealt to the warps; the slice sums meet in s_out (zeroed in P1)
+      {
+        const int nTot = E * nOut, ngrp = (nTot + 31) >> 5, nsl = 4, slen = (N + nsl - 1) / nsl;
+        for (int task = tid >> 5; task < ngrp * nsl; task += NT >> 5) {
+          const int o = (task / nsl) * 32 + lane, sl = task % nsl;
+          const int ibeg = sl * slen, iend = min(N, ibeg + slen);
+          if (o < nTot) {
+            const int a = o / nOut, q = o - a * nOut;
+            const double* lb = s_lb + a * NP;
+            // value = lb_i * f1 * f2 * f3 with up to three factors nu_i[.]; an absent factor reads the constant 1.0
+            // (stride 0), so that all lanes run the same instruction stream whatever their output is
+            const double* b1 = &s_one; const double* b2 = &s_one; const double* b3 = &s_one;
+            int st1 = 0, st2 = 0, st3 = 0;
+            if (q == 0) {
+            } else if (q <= D) {
+              b1 = s_nu + (q - 1); st1 = DP;
+            } else if (q < 1 + D + EV * D) {
+              const int qq = q - 1 - D, e1 = qq / D;
+              b1 = s_nu + e1; st1 = DP;
+              b2 = s_nu + (qq - e1 * D); st2 = DP;
+            } else {
+              const int qq = q - 1 - D - EV * D, e1 = qq / PV;
+              int kl = qq - e1 * PV, k1 = 0;
+              while (kl >= EV - k1) { kl -= EV - k1; k1++; }
+              b1 = s_nu + e1; st1 = DP;
+              b2 = s_nu + k1; st2 = DP;
+              b3 = s_nu + (k1 + kl); st3 = DP;
+            }
+            double acc0 = 0.0, acc1 = 0.0;
+            int i = ibeg;
+            for (; i + 1 < iend; i += 2) {
+              const double f0 = lb[i] * b1[i * st1], f1 = lb[i + 1] * b1[(i + 1) * st1];
+              const double g0 = b2[i * st2] * b3[i * st3], g1 = b2[(i + 1) * st2] * b3[(i + 1) * st3];
+              acc0 = fma(f0, g0, acc0);
+              acc1 = fma(f1, g1, acc1);
+            }
+            if (i < iend) acc0 = fma(lb[i] * b1[i * st1], b2[i * st2] * b3[i * st3], acc0);
+            atomicAdd(s_out + o, acc0 + acc1);
+          }
         }
-        s_out[o] = acc;
       }
       __syncthreads();
+      GEN_CLK(3);
       // ================================================================ P2b: mean / V per GP (gp_model.py:152-153)
       if (tid < E) {
         const int a = tid;
@@ -502,7 +561,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
           if (p.stepV)
             for (int d = 0; d < D; d++) p.stepV[((size_t)cand * D + d) * E + a] = s_V[a * D + d];
         }
-        if (GRAD) {
+        if (GRAD && lead) {
           double* rec = p.records + ((size_t)cand * H + (t - 1)) * RL.size + RL.offGp + a * RL.gpStride;
           const double* Gam = out + 1 + D;            // [e][d]
           const double* T = out + 1 + D + EV * D;     // [e][kl]
@@ -528,8 +587,10 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         }
       }
       __syncthreads();
+      GEN_CLK(4);
       // ================================================================ P3: O(P N^2) covariance sums
       for (int g0 = 0; g0 < P; g0 += G) {
+        if (C > 1 && s_owner[g0] != crank) continue;    // another CTA of the cluster owns this pair (G == 1 in cluster mode)
         const int gn = min(G, P - g0);
         for (int o = tid; o < gn * NP; o += NT) {
           const int pl = o / NP, j = o - pl * NP;
@@ -560,6 +621,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         for (int o = tid; o < gn * L.paccN; o += NT) s_pacc[o] = 0.0;
         if (tid == 0) s_int[0] = 0;
         __syncthreads();
+        GEN_CLK(5);
         {
           const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg;
           const int nitems = gn * nrb * nseg;
@@ -592,6 +654,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
           }
         }
         __syncthreads();
+        GEN_CLK(6);
         if (GRAD) {
           // reduce (rho, gam, xi) over the training points into S_raw, dS/dm (D), dS/dQ (EV x EV)
           for (int pl = 0; pl < gn; pl++) {
@@ -640,6 +703,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
           }
           __syncthreads();
         }
+        GEN_CLK(7);
         if (tid < gn) {
           const int pl = tid, pr = g0 + pl, ab = s_int[2 + pr], a = ab >> 4, b = ab & 15;
           double* acc = s_pacc + pl * L.paccN;
@@ -667,6 +731,17 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         }
         __syncthreads();
       }
+      if (C > 1) {   // exchange the S_raw of the pairs: owners publish, cluster barrier, everybody reads all of them
+        double* ex = p.ws_cl + ((size_t)cid * 2 + (gstep & 1)) * 64;
+        for (int pr = tid; pr < P; pr += NT)
+          if (s_owner[pr] == crank) ex[pr] = s_Sraw[pr];
+        __threadfence();
+        uni_cluster_sync();
+        for (int pr = tid; pr < P; pr += NT) s_Sraw[pr] = __ldcg(ex + pr);
+        __syncthreads();
+      }
+      gstep++;
+      GEN_CLK(8);
       // ================================================================ P4: S, recurrence (gp_model.py:176-178, :105-108)
       if (tid == 0) {
         double S[GPMPC_MAX_EV * GPMPC_MAX_EV];
@@ -683,7 +758,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
           if (p.stepS)
             for (int e = 0; e < E * E; e++) p.stepS[(size_t)cand * E * E + e] = S[e];
         } else {
-          if (GRAD) {
+          if (GRAD && lead) {
             double* rec = p.records + ((size_t)cand * H + (t - 1)) * RL.size;
             for (int a = 0; a < E; a++) rec[RL.offM + a] = s_M[a];
             for (int a = 0; a < E; a++)
@@ -702,18 +777,19 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
             double v = s_mu[e] + s_M[e];
             if (bad) v = nan("");
             s_mu[e] = v;
-            p.states_mu[((size_t)cand * (H + 1) + t) * E + e] = v;
+            if (lead) p.states_mu[((size_t)cand * (H + 1) + t) * E + e] = v;
           }
           for (int e = 0; e < E * E; e++) {
             s_s[e] = sn[e];
-            p.states_var[((size_t)cand * (H + 1) + t) * E * E + e] = sn[e];
+            if (lead) p.states_var[((size_t)cand * (H + 1) + t) * E * E + e] = sn[e];
           }
         }
       }
       __syncthreads();
+      GEN_CLK(9);
     }  // steps
     // ================================================================== terminal cost + LCB (controller :270-276)
-    if (p.mode == 0 && tid == 0) {
+    if (p.mode == 0 && tid == 0 && lead) {
       double cmu, cvar;
       terminal_cost(cv, E, s_mu, s_s, cmu, cvar);
       s_r[H] = -cmu;
@@ -983,15 +1059,30 @@ __global__ void __launch_bounds__(128) backward_kernel(const BackwardParams p) {
 template <int EV>
 cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(ROLLOUT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (p.mode == 0 && p.cluster > 1) {   // p.cluster consecutive CTAs form a thread-block cluster
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
   if (grad) {
     e = cudaFuncSetAttribute(rollout_kernel<EV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_kernel<EV, true><<<grid, ROLLOUT_THREADS, smem, st>>>(p);
+    e = cudaLaunchKernelEx(&cfg, rollout_kernel<EV, true>, p);
   } else {
     e = cudaFuncSetAttribute(rollout_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_kernel<EV, false><<<grid, ROLLOUT_THREADS, smem, st>>>(p);
+    e = cudaLaunchKernelEx(&cfg, rollout_kernel<EV, false>, p);
   }
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -10,7 +10,7 @@ namespace gpmpc {
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
   int nu, grp, kap, gam, rho, xi, out, nOut, PV;
-  int m, s, mu, A, c, il2, s2, logs2, Q, Wd, detR, Sraw, M, V, pacc, paccN, am, r, rv, ints, tab, total;
+  int m, s, mu, A, c, il2, s2, logs2, Q, Wd, detR, Sraw, M, V, pacc, paccN, am, r, rv, ints, tab, cst, total;
 };
 
 HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G, int H, int Na) {
@@ -50,6 +50,7 @@ HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G
   L.ints = o; o += 2 + P;  // counter, bad flag, pair table (packed a*16+b)
   o = (o + 1) & ~1;
   L.tab = o; o += EXP2S_N;   // 2^(j/2048) for exp2s
+  L.cst = o; o += GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + GPMPC_MAX_EV * GPMPC_MAX_EV;   // cost: target, W, WT
   L.total = (o + 1) & ~1;
   return L;
 }

@@ -45,10 +45,6 @@ __device__ __forceinline__ int uni_next_candidate(const RolloutParams& p, int k,
 // sweep is split over all their warps, and the partial sums meet in L2 (float64 RED into a per-cluster accumulator,
 // rotating over three buffers so that zeroing never races with the next step) followed by ONE hardware cluster barrier
 // per horizon step.  Only the cluster's rank-0 CTA writes outputs.
-__device__ __forceinline__ unsigned uni_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void uni_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // float64 reduction at L2 without a return value (RED.E.ADD.F64: fire and forget)
 __device__ __forceinline__ void uni_red_add(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");

@@ -43,7 +43,9 @@ def controller_for(cfg):
 
 def main():
     for name, kw in (("C1 N=50 H=15", dict(name="C1")), ("C2 N=200 H=25", dict(name="C2", B=1)),
-                     ("C4b N=500 H=30", dict(name="C4b", B=1))):
+                     ("C4b N=500 H=30", dict(name="C4b", B=1)),
+                     ("C2 N=200 H=25, per-GP hyper-parameters", dict(name="C2", B=1, distinct_lengthscales=True)),
+                     ("C4b N=500 H=30, per-GP hyper-parameters", dict(name="C4b", B=1, distinct_lengthscales=True))):
         cfg = make_workload(kw.pop("name"), **kw)
         ctrl = controller_for(cfg)
         a = cfg["actions"][0].reshape(-1)
@@ -60,7 +62,7 @@ def main():
         eng.enable_timing(True)
         ctrl.compute_mean_lcb_trajectory(a, mu, var)
         torch.cuda.synchronize()
-        print("%-16s objective+gradient call %.3f ms  (kernels: fwd %.3f + reverse %.3f ms)" % (
+        print("%-42s objective+gradient call %.3f ms  (kernels: fwd %.3f + reverse %.3f ms)" % (
             name, dt * 1e3, eng.last_rollout_ms(), eng.last_backward_ms()), flush=True)
 
 
