@@ -131,7 +131,6 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
                                              int jbeg, int jend, int lane, double* s_part,
                                              unsigned s_tab) {
   constexpr int E = EV;
-  const int NP = p.NP;
   const int i0 = 64 * I + lane, i1 = i0 + 32;
   double u0[EV], u1[EV], bi0[E], bi1[E], kr0, kr1;
   {
@@ -741,7 +740,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
-  const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H, Dc = E + Na;
+  const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
   const bool premat = p.premat != 0;
   const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, premat);
   double* s_pre = sm + L.pre;
@@ -761,7 +760,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   int gstep = 0;
   const int warp = tid >> 5, nwarps = NT >> 5;
   double* s_wp = sm + L.wp; double* s_wp2 = s_wp + 8 * L.wplen;   // per-warp rows of the B1 / B3 point sums
-  double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q; double* s_misc = sm + L.misc;
+  double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   double* s2p = sm + L.small2;
   // small2 carve: mu_bar[E], s_bar[E2], Om[E2], Rinv[E2], Ub[E2], Vb[E2], hg[E + E2] (h_bar, g_bar), scal[16]
