@@ -60,10 +60,10 @@ constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forwar
 //   r_b,i += Eh_ij beta_b,j  (E FMAs),  tr += Eh_ij iK_ij  (1 FMA)   [gp_model.py:169-175 for all (a,b) at once]
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, int rlen, int j, double (&nu)[EV],
+__device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, int j, double (&nu)[EV],
                                              double& kap, double (&beta)[EV]) {
-  constexpr int RLEN = (EV + 1 + EV + 1) & ~1;   // hot part; rlen >= RLEN is the record stride (even)
-  const double2* r2 = reinterpret_cast<const double2*>(s_rec + (size_t)j * rlen);
+  constexpr int RLEN = 2 * EV + 2;   // record stride (UniLayout::rhot)
+  const double2* r2 = reinterpret_cast<const double2*>(s_rec + j * RLEN);
   double buf[RLEN];
 #pragma unroll
   for (int q = 0; q < RLEN / 2; q++) { const double2 v = r2[q]; buf[2 * q] = v.x; buf[2 * q + 1] = v.y; }
@@ -74,27 +74,30 @@ __device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, i
   for (int b = 0; b < EV; b++) beta[b] = buf[EV + 1 + b];
 }
 
-// columns [jbeg, jend) of the forward sweep for rows i0, i0 + 32:  r_b,i += Eh_ij beta_b,j ; TR: tr += Eh_ij iK_ij
-template <int EV, bool TR>
-__device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const double* __restrict__ s_rec, int rlen, int i0,
+// columns [jbeg, jend) of the forward sweep for the lane's rows i0, i0 + 1:  r_b,i += Eh'_ij beta_b,j ; tr_i += Eh'_ij iK_ij
+// with the ROW factor of the exponential taken out of the loop:  Eh_ij = e_i Eh'_ij ,  Eh'_ij = exp(kap_j + u_i . nu_j + d_i),
+// e_i = exp(max(kap_i, UNI_KAP_MIN)) applied by the caller to the finished row sums, d_i = kap_i - max(kap_i, UNI_KAP_MIN) the
+// residual shift of far-away rows (SH: some lane of the warp has d_i != 0; otherwise the add is not even issued).
+template <int EV, bool SH>
+__device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const double* __restrict__ s_rec, int i0,
                                              int jbeg, int jend, const double (&u0)[EV], const double (&u1)[EV],
-                                             double kr0, double kr1, double (&r0)[EV], double (&r1)[EV], double& trOut,
-                                             unsigned s_tab) {
+                                             double kr0, double kr1, double (&r0)[EV], double (&r1)[EV], double& trOut0,
+                                             double& trOut1, unsigned s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
-  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = column i
+  const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = columns i0, i0 + 1
   double tr = 0.0, tr2 = 0.0;
 #pragma unroll 2
   for (int j = jbeg; j < jend; j += 2) {   // 2 columns x 2 rows = 4 independent chains per warp
     double na[EV], nb[EV], ba[E], bb[E], ka, kb;
-    uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
-    uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
-    double k0a = 0.0, k1a = 0.0, k0b = 0.0, k1b = 0.0;
-    if (TR) {
-      k0a = __ldg(ik0); k1a = __ldg(ik0 + 32); k0b = __ldg(ik0 + NP); k1b = __ldg(ik0 + NP + 32);
-      ik0 += 2 * (size_t)NP;
-    }
-    double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, ex[4];
+    uni_load_rec<EV>(s_rec, j, na, ka, ba);
+    uni_load_rec<EV>(s_rec, j + 1, nb, kb, bb);
+    const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
+    const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
+    ik0 += 2 * (size_t)NP;
+    double t[4], ex[4];
+    if (SH) { t[0] = kr0 + ka; t[1] = kr1 + ka; t[2] = kr0 + kb; t[3] = kr1 + kb; }
+    else { t[0] = ka; t[1] = ka; t[2] = kb; t[3] = kb; }
     // serpentine order: every FMA shares one register operand with its predecessor (operand-reuse cache; a DFMA
     // with three fresh register operands issues at 2/3 rate on B200, tools/micro/dfma_operands.cu)
 #pragma unroll
@@ -104,7 +107,7 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
       t[3] = fma(u1[e], nb[e], t[3]);
       t[2] = fma(u0[e], nb[e], t[2]);
     }
-    exp2s_x4(t, ex, s_tab);
+    exp2b_x4<exp2b_log(EV)>(t, ex, s_tab);
 #pragma unroll
     for (int b = 0; b < E; b++) {
       if (b & 1) { r1[b] = fma(ex[1], ba[b], r1[b]); r0[b] = fma(ex[0], ba[b], r0[b]); }
@@ -115,28 +118,37 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
       if (b & 1) { r1[b] = fma(ex[3], bb[b], r1[b]); r0[b] = fma(ex[2], bb[b], r0[b]); }
       else       { r0[b] = fma(ex[2], bb[b], r0[b]); r1[b] = fma(ex[3], bb[b], r1[b]); }
     }
-    if (TR) {
-      tr = fma(ex[0], k0a, tr);
-      tr2 = fma(ex[1], k1a, tr2);
-      tr = fma(ex[2], k0b, tr);
-      tr2 = fma(ex[3], k1b, tr2);
-    }
+    tr = fma(ex[0], ika.x, tr);
+    tr2 = fma(ex[1], ika.y, tr2);
+    tr = fma(ex[2], ikb.x, tr);
+    tr2 = fma(ex[3], ikb.y, tr2);
   }
-  if (TR) trOut += tr + tr2;
+  trOut0 += tr;
+  trOut1 += tr2;
+}
+
+// Row factor of the sweeps (see uni_fwd_cols): kr (table units) -> e = exp(max(kr, kmin)), kr := residual shift.
+// kmin = -600 in natural units: with the total exponent <= 0, Eh' <= e^600 cannot overflow.
+template <int EV>
+__device__ __forceinline__ double uni_row_factor(double& kr, unsigned s_tab) {
+  constexpr int XL = exp2b_log(EV);
+  const double c = fmax(kr, -600.0 * Exp2B<XL>::SCALE);   // NaN -> kmin, and the residual keeps the NaN
+  kr -= c;
+  return exp2b<XL>(c, s_tab);
 }
 
 template <int EV>
-__device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
+__device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec,
                                              const double* __restrict__ Qm, const double* __restrict__ il2, int I,
                                              int jbeg, int jend, int lane, double* s_part,
                                              unsigned s_tab) {
   constexpr int E = EV;
-  const int i0 = 64 * I + lane, i1 = i0 + 32;
+  const int i0 = 64 * I + 2 * lane, i1 = i0 + 1;   // adjacent rows: one 16-byte load fetches both iK values of a column
   double u0[EV], u1[EV], bi0[E], bi1[E], kr0, kr1;
   {
     double n0[EV], n1[EV];
-    uni_load_rec<EV>(s_rec, rlen, i0, n0, kr0, bi0);
-    uni_load_rec<EV>(s_rec, rlen, i1, n1, kr1, bi1);
+    uni_load_rec<EV>(s_rec, i0, n0, kr0, bi0);
+    uni_load_rec<EV>(s_rec, i1, n1, kr1, bi1);
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       double q0 = 0.0, q1 = 0.0;
@@ -145,8 +157,8 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
         q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
         q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
       }
-      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2[e];   // exponent in table units (exp2s)
-      u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2[e];
+      u0[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q0 * il2[e];   // exponent in table units (exp2b)
+      u1[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q1 * il2[e];
     }
   }
   double r0[E], r1[E];
@@ -159,14 +171,20 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   // columns are halved before the columns above it are added.
   const int jd1 = 64 * I + 64;
   jend = min(jend, (p.N + 1) & ~1);   // zero-padded columns (beta = 0, iK = 0) contribute exact zeros: skip them
-  double trD = 0.0, trU = 0.0;
+  const double e0 = uni_row_factor<EV>(kr0, s_tab), e1 = uni_row_factor<EV>(kr1, s_tab);   // kr0, kr1 become residual shifts
+  const bool far = __any_sync(0xffffffffu, kr0 != 0.0 || kr1 != 0.0);
+  double trD0 = 0.0, trD1 = 0.0, trU0 = 0.0, trU1 = 0.0;
   if (jbeg < jd1) {
-    uni_fwd_cols<EV, true>(p, s_rec, rlen, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD, s_tab);
+    if (far) uni_fwd_cols<EV, true>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD0, trD1, s_tab);
+    else uni_fwd_cols<EV, false>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD0, trD1, s_tab);
 #pragma unroll
     for (int b = 0; b < E; b++) { r0[b] *= 0.5; r1[b] *= 0.5; }
   }
-  uni_fwd_cols<EV, true>(p, s_rec, rlen, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU, s_tab);
-  const double tr = fma(2.0, trU, trD);
+  if (far) uni_fwd_cols<EV, true>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU0, trU1, s_tab);
+  else uni_fwd_cols<EV, false>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU0, trU1, s_tab);
+  const double tr = e0 * fma(2.0, trU0, trD0) + e1 * fma(2.0, trU1, trD1);
+#pragma unroll
+  for (int b = 0; b < E; b++) { bi0[b] *= e0; bi1[b] *= e1; }   // the row factor, applied once to the finished row sums
   // S_ab += sum_i beta_a,i r_b,i  (a <= b), trace: halving reduction of the P + 1 lane partials, 16 at a time, into
   // this warp's private accumulator row (no shared-memory float64 atomics: those are CAS spin loops)
   constexpr int P1 = E * (E + 1) / 2 + 1, NCH = (P1 + 15) / 16;
@@ -203,21 +221,26 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
 // record's spare slot, nu of the action / time dimensions in its tail.  No shuffles, no atomics: the per-warp
 // partial rows s_wp[warp][o] are added up by the consumer (P4).
 template <int EV>
-__device__ __forceinline__ void uni_moments_slice(const double* __restrict__ s_rec, int rlen, int rhot, int nOut,
-                                                  int ibeg, int iend, int lane, double* __restrict__ s_wp_row) {
+__device__ __forceinline__ void uni_moments_slice(const double* __restrict__ s_rec, const double* __restrict__ s_tail,
+                                                  int tlen, int nOut, int ibeg, int iend, int lane,
+                                                  double* __restrict__ s_wp_row) {
+  constexpr int RLEN = 2 * EV + 2;
   const int nTot = EV * nOut;
   for (int ob = 0; ob < nTot; ob += 32) {
     const int o = ob + lane;
     const bool act = o < nTot;
     const int a = act ? o / nOut : 0, q = act ? o - a * nOut : 0, d = q - 1;
-    const int sb = EV + 1 + a, sd = (d < 0) ? 0 : (d < EV ? d : rhot + d - EV);   // slot of nu_d (tail: action / time dims)
+    const int sb = EV + 1 + a;
+    // nu_d of this lane's output: state dims in the hot record, action / time dims in the tail array
+    const double* fb = (d < EV) ? s_rec + (d < 0 ? 0 : d) : s_tail + (d - EV);
+    const int fs = (d < EV) ? RLEN : tlen;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int i0 = ibeg; i0 < iend; i0 += 4) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const double* r = s_rec + (i0 + k) * rlen;
+        const double* r = s_rec + (i0 + k) * RLEN;
         const double lb = r[sb] * r[2 * EV + 1];
-        const double f = (q == 0) ? 1.0 : r[sd];
+        const double f = (q == 0) ? 1.0 : fb[(i0 + k) * fs];
         acc[k] = fma(lb, f, acc[k]);
       }
     }
@@ -236,11 +259,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
   constexpr int P = E * (E + 1) / 2;
   const UniLayout L = make_uni_layout(EV, false, NP, DP, D, H, Na);
-  double* s_rec = sm + L.rec; double* s_out = sm + L.out;
+  double* s_rec = sm + L.rec; double* s_tail = sm + L.tail; double* s_out = sm + L.out;
   double* s_m = sm + L.m; double* s_s = sm + L.s; double* s_mu = sm + L.mu; double* s_A = sm + L.A;
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
-  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
+  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2b_lane_base(s_tabp);
   double* s_part = sm + L.part; double* s_wp = sm + L.wp; double* s_S = sm + L.S; double* s_cst = sm + L.cst;
   const int nOut = L.nOut, warp = tid >> 5, nwarps = NT >> 5;
   const UniRecLayout RL = uni_rec_layout(E);
@@ -252,7 +275,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
                     p.kappa, p.use_constraints};
   const double* il2 = p.il2;            // row 0 (all rows equal)
   const double s2 = p.s2[0];
-  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
+  for (int i = tid; i < exp2b_doubles(exp2b_log(EV)); i += NT) s_tabp[i] = p.exp2btab[i];
   __syncthreads();
 
   long long clk_ = clock64();
@@ -356,24 +379,24 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
           if (d < D) tail = fma(nu[d] * nu[d], il2[d], tail);
-        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
-        double* rec = s_rec + (size_t)i * L.rlen;
+        const double ei = (i < N) ? exp2b<exp2b_log(EV)>((-0.5 * Exp2B<exp2b_log(EV)>::SCALE) * (quad + tail), s_tab) : 0.0;
+        double* rec = s_rec + i * (2 * EV + 2);
 #pragma unroll
         for (int e = 0; e < EV; e++) rec[e] = nu[e];
-        rec[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;   // table units; log s2 factored out (s2^2 applied at the end)
+        rec[EV] = (i < N) ? Exp2B<exp2b_log(EV)>::SCALE * (-0.5 * (head + tail) + zqz) : 0.0;   // table units; log s2 factored out (s2^2 applied at the end)
 #pragma unroll
         for (int a = 0; a < E; a++) rec[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
         rec[2 * EV + 1] = ei;   // spare slot of the (even-length) record
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
-          if (d < D) rec[L.rhot + d - EV] = nu[d];
+          if (d < D) s_tail[i * L.tlen + d - EV] = nu[d];
       }
       __syncthreads();
       UNI_CLK(4);
       // ---- P1b: mean-part moments h_a, g_a (lane per output, warp per slice of points; summed over warps in P4)
       {
         const int per = NP / nwarps;
-        uni_moments_slice<EV>(s_rec, L.rlen, L.rhot, nOut, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
+        uni_moments_slice<EV>(s_rec, s_tail, L.tlen, nOut, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
       }
       UNI_CLK(1);
       // ---- P3: one sweep over the upper tile triangle for all pairs.  Static balanced split: row block I (64 rows)
@@ -388,7 +411,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
         while (c0 < c1) {
           while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
           const int ce = min(c1, base + cpt * (nrb - I));
-          uni_fwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base), lane,
+          uni_fwd_item<EV>(p, s_rec, s_Q, il2, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base), lane,
                            s_part + warp * L.partlen, s_tab);
           c0 = ce;
         }
@@ -527,14 +550,16 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 // Row and column sums leave the warp as float64 reductions into the CTA's global scratch (native RED.ADD.F64 at L2,
 // fire and forget); float64 atomics on shared memory are CAS spin loops and cost ~15 % of an item.
 // ---------------------------------------------------------------------------------------------
-// columns [jbeg, jend) (a multiple of 8) of the reverse sweep for rows i0, i0 + 32, with coefficient row vectors p0, p1
-// and trace weight wbar as given (the caller halves them on the diagonal tile)
-template <int EV>
-__device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const double* __restrict__ s_rec, int rlen, int i0,
+// columns [jbeg, jend) (a multiple of 8) of the reverse sweep for the lane's rows i0, i0 + 1, with coefficient row
+// vectors p0, p1 and trace weights wb0, wb1 as given: the caller folds the row factor e_i of the exponential into them
+// (and halves them on the diagonal tile), so w_ij = (p_i . beta_j - wb_i iK_ij) Eh'_ij needs no per-element row term
+// (SH: residual shifts kr0, kr1 of far-away rows, see uni_fwd_cols)
+template <int EV, bool SH>
+__device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const double* __restrict__ s_rec, int i0,
                                              int jbeg, int jend, const double (&u0)[EV], const double (&u1)[EV],
                                              double kr0, double kr1, const double (&p0)[EV], const double (&p1)[EV],
-                                             double wbar, double& rho0, double& rho1, double (&xi0)[EV], double (&xi1)[EV],
-                                             int lane, double* __restrict__ g_gam, unsigned s_tab) {
+                                             double wb0, double wb1, double& rho0, double& rho1, double (&xi0)[EV],
+                                             double (&xi1)[EV], int lane, double* __restrict__ g_gam, unsigned s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
   const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;
@@ -544,9 +569,11 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
     for (int jp = 0; jp < 4; jp++) {   // pairs of columns: 2 columns x 2 rows = 4 independent chains per warp
       const int j = j0 + 2 * jp;
       double na[EV], nb[EV], ba[E], bb[E], ka, kb;
-      uni_load_rec<EV>(s_rec, rlen, j, na, ka, ba);
-      uni_load_rec<EV>(s_rec, rlen, j + 1, nb, kb, bb);
-      double c[4] = {-wbar * __ldg(ik0), -wbar * __ldg(ik0 + 32), -wbar * __ldg(ik0 + NP), -wbar * __ldg(ik0 + NP + 32)};
+      uni_load_rec<EV>(s_rec, j, na, ka, ba);
+      uni_load_rec<EV>(s_rec, j + 1, nb, kb, bb);
+      const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
+      const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
+      double c[4] = {-wb0 * ika.x, -wb1 * ika.y, -wb0 * ikb.x, -wb1 * ikb.y};
       ik0 += 2 * (size_t)NP;
 #pragma unroll
       for (int b = 0; b < E; b++) {   // serpentine order (operand-reuse cache, see uni_fwd_cols)
@@ -555,7 +582,9 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
         c[3] = fma(p1[b], bb[b], c[3]);
         c[2] = fma(p0[b], bb[b], c[2]);
       }
-      double t[4] = {kr0 + ka, kr1 + ka, kr0 + kb, kr1 + kb}, w[4];
+      double t[4], w[4];
+      if (SH) { t[0] = kr0 + ka; t[1] = kr1 + ka; t[2] = kr0 + kb; t[3] = kr1 + kb; }
+      else { t[0] = ka; t[1] = ka; t[2] = kb; t[3] = kb; }
 #pragma unroll
       for (int e = 0; e < EV; e++) {
         t[0] = fma(u0[e], na[e], t[0]);
@@ -563,7 +592,7 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
         t[3] = fma(u1[e], nb[e], t[3]);
         t[2] = fma(u0[e], nb[e], t[2]);
       }
-      exp2s_x4(t, w, s_tab);
+      exp2b_x4<exp2b_log(EV)>(t, w, s_tab);
 #pragma unroll
       for (int q = 0; q < 4; q++) w[q] *= c[q];
       rho0 += w[0] + w[2];
@@ -591,19 +620,19 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
 // the sums (B3b) only need  g_i = rho_i + gam_i  and  sum_i z_i,k xi_i,l + xi_i,k z_i,l : both come out the same if the
 // diagonal tile is swept in full with HALF weights instead of its upper triangle -- no element masks anywhere.
 template <int EV>
-__device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec, int rlen,
+__device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const double* __restrict__ s_rec,
                                              const double* __restrict__ Qm, const double* __restrict__ il2,
                                              const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
                                              int lane, double* __restrict__ g_gam, double* __restrict__ g_rho,
                                              double* __restrict__ g_xi, unsigned s_tab) {
   constexpr int E = EV;
   const int NP = p.NP;
-  const int i0 = 64 * I + lane, i1 = i0 + 32;
+  const int i0 = 64 * I + 2 * lane, i1 = i0 + 1;   // adjacent rows (16-byte iK loads), as in the forward sweep
   double u0[EV], u1[EV], p0[E], p1[E], kr0, kr1;
   {
     double n0[EV], n1[EV], b0[E], b1[E];
-    uni_load_rec<EV>(s_rec, rlen, i0, n0, kr0, b0);
-    uni_load_rec<EV>(s_rec, rlen, i1, n1, kr1, b1);
+    uni_load_rec<EV>(s_rec, i0, n0, kr0, b0);
+    uni_load_rec<EV>(s_rec, i1, n1, kr1, b1);
 #pragma unroll
     for (int e = 0; e < EV; e++) {
       double q0 = 0.0, q1 = 0.0;
@@ -612,8 +641,8 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
         q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
         q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
       }
-      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2[e];   // exponent in table units (exp2s)
-      u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2[e];
+      u0[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q0 * il2[e];   // exponent in table units (exp2b)
+      u1[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q1 * il2[e];
     }
 #pragma unroll
     for (int a = 0; a < E; a++) {
@@ -629,16 +658,26 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
   const int jd1 = 64 * I + 64;
   jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns contribute exact zeros: skip them (8 columns per round)
+  // row factor e_i of the exponential (uni_fwd_cols) folded into the coefficient row vectors and the trace weights
+  const double e0 = uni_row_factor<EV>(kr0, s_tab), e1 = uni_row_factor<EV>(kr1, s_tab);   // kr0, kr1 become residual shifts
+  const bool far = __any_sync(0xffffffffu, kr0 != 0.0 || kr1 != 0.0);
+  const double wb0 = wbar * e0, wb1 = wbar * e1;
+#pragma unroll
+  for (int a = 0; a < E; a++) { p0[a] *= e0; p1[a] *= e1; }
   if (jbeg < jd1) {
 #pragma unroll
     for (int a = 0; a < E; a++) { p0[a] *= 0.5; p1[a] *= 0.5; }
-    uni_bwd_cols<EV>(p, s_rec, rlen, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, p0, p1, 0.5 * wbar, rho0, rho1, xi0, xi1,
-                     lane, g_gam, s_tab);
+    if (far) uni_bwd_cols<EV, true>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, p0, p1, 0.5 * wb0, 0.5 * wb1, rho0, rho1,
+                                    xi0, xi1, lane, g_gam, s_tab);
+    else uni_bwd_cols<EV, false>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, p0, p1, 0.5 * wb0, 0.5 * wb1, rho0, rho1,
+                                 xi0, xi1, lane, g_gam, s_tab);
 #pragma unroll
     for (int a = 0; a < E; a++) { p0[a] *= 2.0; p1[a] *= 2.0; }
   }
-  uni_bwd_cols<EV>(p, s_rec, rlen, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, p0, p1, wbar, rho0, rho1, xi0, xi1, lane,
-                   g_gam, s_tab);
+  if (far) uni_bwd_cols<EV, true>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, p0, p1, wb0, wb1, rho0, rho1, xi0, xi1,
+                                  lane, g_gam, s_tab);
+  else uni_bwd_cols<EV, false>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, p0, p1, wb0, wb1, rho0, rho1, xi0, xi1,
+                               lane, g_gam, s_tab);
   uni_red_add(g_rho + i0, rho0);
   uni_red_add(g_rho + i1, rho1);
 #pragma unroll
@@ -746,7 +785,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   double* s_pre = sm + L.pre;
   const int oA = 0, oQ = EV * EV, oRi = 2 * EV * EV, odS = 3 * EV * EV, oc = 4 * EV * EV, odet = oc + 1, odmu = oc + 2,
             oda = odmu + EV;
-  double* s_rec = sm + L.rec;
+  double* s_rec = sm + L.rec; double* s_tail = sm + L.tail;
   // global scratch of the sweep's row / column sums (L2 resident): gam[NP], rho[NP], xi[EV][NP] -- one per CTA, or three
   // per cluster (rotating with the step, see uni_cluster_sync) when p.cluster CTAs share a candidate
   const int C = p.cluster;
@@ -761,7 +800,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const int warp = tid >> 5, nwarps = NT >> 5;
   double* s_wp = sm + L.wp; double* s_wp2 = s_wp + 8 * L.wplen;   // per-warp rows of the B1 / B3 point sums
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q;
-  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
+  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2b_lane_base(s_tabp);
   double* s2p = sm + L.small2;
   // small2 carve: mu_bar[E], s_bar[E2], Om[E2], Rinv[E2], Ub[E2], Vb[E2], hg[E + E2] (h_bar, g_bar), scal[16]
   double* s_mubar = s2p; double* s_sbar = s_mubar + GPMPC_MAX_EV; double* s_Om = s_sbar + EV * EV;
@@ -771,7 +810,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const double* il2 = p.il2;
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
-  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
+  for (int i = tid; i < exp2b_doubles(exp2b_log(EV)); i += NT) s_tabp[i] = p.exp2btab[i];
   if (C == 1)
     for (int i = tid; i < NP * (2 + EV); i += NT) g_gam[i] = 0.0;   // B3 re-zeroes after every step (clusters: host memset)
   __syncthreads();
@@ -930,16 +969,16 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           an[d] = 0.0;
           if (d < D) { tail = fma(nu[d] * nu[d], il2[d], tail); an[d] = nu[d] * il2[d]; }
         }
-        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
-        double* rcd = s_rec + (size_t)i * L.rlen;
+        const double ei = (i < N) ? exp2b<exp2b_log(EV)>((-0.5 * Exp2B<exp2b_log(EV)>::SCALE) * (quad + tail), s_tab) : 0.0;
+        double* rcd = s_rec + i * (2 * EV + 2);
 #pragma unroll
         for (int e = 0; e < EV; e++) rcd[e] = nu[e];
-        rcd[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;
+        rcd[EV] = (i < N) ? Exp2B<exp2b_log(EV)>::SCALE * (-0.5 * (head + tail) + zqz) : 0.0;
 #pragma unroll
         for (int a = 0; a < E; a++) rcd[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
-          if (d < D) rcd[L.rhot + d - EV] = nu[d];
+          if (d < D) s_tail[i * L.tlen + d - EV] = nu[d];
         // mean part weight phi_i = sum_a e_i beta_a,i (h_bar_a + g_bar_a . nu_i^E), kept in the record's spare slot
         double phi = 0.0;
 #pragma unroll
@@ -983,7 +1022,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         while (c0 < c1) {
           while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
           const int ce = min(c1, base + cpt * (nrb - I));
-          uni_bwd_item<EV>(p, s_rec, L.rlen, s_Q, il2, s_Om, wbar, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base),
+          uni_bwd_item<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base),
                            lane, g_gam, g_rho, g_xi, s_tab);
           c0 = ce;
         }
@@ -1011,7 +1050,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
 #pragma unroll
       for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = 0.0;
       for (int i = tid; i < NP; i += NT) {
-        const double* rc = s_rec + (size_t)i * L.rlen;
+        const double* rc = s_rec + i * (2 * EV + 2);
         double xv[EV], z[EV];
         const double gv = __ldcg(g_gam + i), rv = __ldcg(g_rho + i);   // all loads first (the stores below may alias)
 #pragma unroll
@@ -1032,7 +1071,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
         }
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
-          if (d < D) vs[d] = fma(g, rc[L.rhot + d - EV], vs[d]);
+          if (d < D) vs[d] = fma(g, s_tail[i * L.tlen + d - EV], vs[d]);
         {
           int pr = 0;
 #pragma unroll

@@ -6,7 +6,7 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, rlen, rhot, pre, prelen, out, nOut, part, partlen, wp, wplen, S, cst;
+  int rec, tail, tlen, rhot, pre, prelen, out, nOut, part, partlen, wp, wplen, S, cst;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
 };
 
@@ -16,12 +16,13 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   UniLayout L;
   const int E = EV, P = E * (E + 1) / 2;
   int o = 0;
-  // hot-loop record per training point j: { nu_j[0..EV), kap_j, beta_j[0..E) } padded to an even length so that
-  // every lane fetches it with (rlen/2) broadcast LDS.128
-  // (followed by the action/time dims of nu, needed by the O(N) reductions that read the records)
-  L.rhot = (EV + 1 + E + 1) & ~1;
-  L.rlen = L.rhot + ((D - EV + 1) & ~1);
-  L.rec = o; o += NP * L.rlen;
+  // hot-loop record per training point j: { nu_j[0..EV), kap_j, beta_j[0..E), e_j } -- 2 EV + 2 doubles, a compile-time
+  // stride, so that every lane fetches it with (EV + 1) broadcast LDS.128 at immediate offsets from one running pointer.
+  // The action/time dims of nu, needed only by the O(N) reductions, live in a separate array (tlen per point).
+  L.rhot = 2 * EV + 2;
+  L.tlen = (D - EV + 1) & ~1;
+  L.rec = o; o += NP * L.rhot;
+  L.tail = o; o += NP * L.tlen;
   L.prelen = (4 * EV * EV + 2 + EV + Na + 1) & ~1;   // A, Q, Rinv, dS (E x E each), c, detR, dmu (E), da (Na)
   L.pre = o; if (bwd && premat) o += H * L.prelen;
   L.nOut = 1 + D;
@@ -49,7 +50,8 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.rv = o; o += H + 1;
   L.ints = o; o += 4;
   o = (o + 1) & ~1;
-  L.tab = o; o += EXP2S_N;   // 2^(j/2048) for exp2s
+  o = (o + 15) & ~15;       // 128-byte aligned: copy p of the table sits in bank pair p
+  L.tab = o; o += exp2b_doubles(exp2b_log(EV));   // bank-private tables of exp2b
   L.small2 = o; o += bwd ? (8 * EV * EV + 8 * GPMPC_MAX_D + E * E + 64) : 0;
   L.total = (o + 1) & ~1;
   return L;

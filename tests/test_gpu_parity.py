@@ -92,6 +92,21 @@ def test_cuda_matches_cpu_oracle(kw, path):
     np.testing.assert_allclose(got["rewards_traj_var"], want["rewards_traj_var"], rtol=0, atol=ATOL)
 
 
+@pytest.mark.parametrize("path", [0, 1])
+def test_far_rows_with_wide_input_distribution(path):
+    """Short lengthscale + very wide state distribution: some training points have a row exponent kap_i < -600 whose
+    row factor exp(kap_i) is taken out of the sweep; the uniform kernels then carry the residual shift per element
+    (uni_fwd_cols<SH=true>), and those rows still contribute (kap_i + kap_j + cross term ~ 0 for neighbours)."""
+    cfg = make_workload(E=2, Na=1, N=150, H=3, B=2, ls=0.02, seed=31, obs_var=4.0)
+    eng = make_engine(cfg, path)
+    want = orc.evaluate_workload(cfg)
+    got = rollout(eng, cfg)
+    np.testing.assert_allclose(got["cost"], want["cost"], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(got["grad"], want["grad"], rtol=0, atol=ATOL_GRAD)
+    np.testing.assert_allclose(got["states_mu_pred"], want["states_mu_pred"], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(got["states_var_pred"], want["states_var_pred"], rtol=0, atol=ATOL)
+
+
 @pytest.mark.parametrize("distinct", [False, True])
 def test_batched_equals_looped_and_is_order_independent(distinct):
     """B candidates in one call == B single-candidate calls: no cross-candidate arithmetic.  Not bit-for-bit:

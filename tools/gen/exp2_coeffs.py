@@ -30,3 +30,39 @@ for i in range(20001):
 print("max relative truncation error: %.3e  (Taylor: %.3e; half ulp = 1.11e-16)" % (float(worst), float(worst_taylor)))
 print("SCALE = T/ln2 = %.20e" % float(T / mp.log(2)))
 print("ln2/T        = %.20e" % float(k))
+
+
+def bank_private(T, deg):
+    """exp2b (csrc/gpmpc_common.cuh): T-entry table, one private copy per shared-memory bank pair, polynomial of degree
+    `deg` without constant term:  2^(f/T) - 1 ~= f (c1 + f (c2 + ... f c_deg)),  |f| <= 1/2.
+    The remainder is dominated by q f^(deg+1), q = k^(deg+1) / (deg+1)!, which c_(deg-1) absorbs: with m = deg - 1,
+    minimise max |f^m (d - q f^2)| on [0, F] -- the interior extremum (2 d / (m + 2)) f*^m at f*^2 = m d / ((m + 2) q)
+    equals minus the value at F."""
+    T = mp.mpf(T)
+    k = mp.log(2) / T
+    F = mp.mpf(1) / 2
+    m = deg - 1
+    q = k ** (deg + 1) / mp.factorial(deg + 1)
+    d = mp.findroot(lambda d: (2 * d / (m + 2)) * (m * d / ((m + 2) * q)) ** (mp.mpf(m) / 2) + F ** m * (d - q * F * F),
+                    q * F * F * mp.mpf("0.8"))
+    c = [k ** (i + 1) / mp.factorial(i + 1) for i in range(deg)]
+    c[m - 1] += d
+    cd = [float(x) for x in c]
+    for i, x in enumerate(cd):
+        print("b%d = %.20e  (%s)" % (i + 1, x, x.hex()))
+    worst = worst_t = mp.mpf(0)
+    for i in range(20001):
+        f = -F + mp.mpf(i) / 20000
+        exact = mp.power(2, f / T)
+        p = pt = mp.mpf(0)
+        for j in reversed(range(deg)):
+            p = f * (mp.mpf(cd[j]) + p)
+            pt = f * (k ** (j + 1) / mp.factorial(j + 1) + pt)
+        worst = max(worst, abs((1 + p) / exact - 1))
+        worst_t = max(worst_t, abs((1 + pt) / exact - 1))
+    print("degree %d, T = %d: max relative truncation error %.3e  (Taylor: %.3e)" % (deg, int(T), float(worst), float(worst_t)))
+    print("SCALE = T/ln2 = %.20e" % float(T / mp.log(2)))
+
+
+bank_private(256, 4)
+bank_private(128, 5)
