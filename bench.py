@@ -183,9 +183,8 @@ def fp64_report(uniform, E, N, preds, fwd_ms, bwd_ms, f_alg, peak):
     if uniform:
         tri = (NP // 64) * (NP // 64 + 1) // 2 * 64 * 64      # elements of the upper tile triangle (both sweeps)
         # (the row factor of the exponential is applied after the sweep: E exponent FMAs, no per-element add)
-        xp = 8 if E <= 5 else 9                               # exp2b: quartic (256-entry tables) / quintic (128)
-        fwd_ops = tri * (E + xp + E + 1)                      # exponent, exp2b, beta-weighted row sums, trace
-        bwd_ops = tri * (E + xp + (E + 1) + 3.06 + E)         # + coefficient, w, rho/col sums, xi
+        fwd_ops = tri * (E + 7 + E + 1)                       # exponent, exp2s, beta-weighted row sums, trace
+        bwd_ops = tri * (E + 7 + (E + 1) + 3.06 + E)          # + coefficient, w, rho/col sums, xi
     else:
         elems = E * NP * (NP + 64) // 2 + E * (E - 1) // 2 * NP * NP
         fwd_ops = elems * ((E + 1) + 7 + 2 + 1 + (E + 3.1))   # gradient mode: + rho/gamma/xi accumulation

@@ -136,22 +136,14 @@ int gpmpc_create(gpmpc_handle** out, int device) {
   for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
   {  // 2^(j/2048), rounded once from extended precision, stored pre-biased for exp2s: (j << 9) is subtracted from the
      // high word so that the kernels restore the entry and apply 2^(n >> 11) with one integer add (exp2s_entry)
-     // exp2b (uniform kernels): the same for 2^(j/256) and 2^(j/128), sixteen copies each -- entry j of copy p at
-     // double 16 j + p, so that copy p lives in shared-memory bank pair p; they follow the exp2s table in the buffer
-    constexpr int OFF8 = EXP2S_N, OFF7 = OFF8 + exp2b_doubles(8), TOTAL = OFF7 + exp2b_doubles(7);
-    static double tab[TOTAL];
-    auto entry = [](int j, int log) {
-      const double v = (double)exp2l((long double)j / (long double)(1 << log));
+    static double tab[EXP2S_N];
+    for (int j = 0; j < EXP2S_N; j++) {
+      const double v = (double)exp2l((long double)j / (long double)EXP2S_N);
       unsigned long long bits;
       memcpy(&bits, &v, sizeof(bits));
-      bits -= (unsigned long long)j << (32 + 20 - log);
-      double r;
-      memcpy(&r, &bits, sizeof(bits));
-      return r;
-    };
-    for (int j = 0; j < EXP2S_N; j++) tab[j] = entry(j, EXP2S_LOG);
-    for (int j = 0; j < 256; j++) for (int c = 0; c < 16; c++) tab[OFF8 + 16 * j + c] = entry(j, 8);
-    for (int j = 0; j < 128; j++) for (int c = 0; c < 16; c++) tab[OFF7 + 16 * j + c] = entry(j, 7);
+      bits -= (unsigned long long)j << (32 + 20 - EXP2S_LOG);
+      memcpy(&tab[j], &bits, sizeof(bits));
+    }
     if (h->exp2tab.ensure(sizeof(tab)) != cudaSuccess ||
         cudaMemcpy(h->exp2tab.ptr, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess) {
       cudaGetLastError();
@@ -311,7 +303,6 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
                        int* grid, bool uniform = false) {
   p.x = h->x.as<double>(); p.beta = h->beta.as<double>(); p.iK = h->iK.as<double>();
   p.il2 = h->il2.as<double>(); p.s2 = h->s2.as<double>(); p.exp2tab = h->exp2tab.as<double>();
-  p.exp2btab = p.exp2tab + EXP2S_N + (exp2b_log(EV) == 8 ? 0 : exp2b_doubles(8));
   p.N = h->N; p.NP = h->NP; p.D = h->D; p.DP = h->DP; p.E = h->E; p.Na = Na;
   p.B = B; p.H = H;
   p.betaT = h->betaT.as<double>();

@@ -80,7 +80,7 @@ __device__ __forceinline__ void exp_tab_x4(const double (&x)[4], double (&res)[4
 #pragma unroll
   for (int c = 0; c < 4; c++) kd[c] = __fma_rn(x[c], INV, SHIFT);
 #pragma unroll
-  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }
+  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }   // (an I2F.F64 instead of this add is slower)
 #pragma unroll
   for (int c = 0; c < 4; c++) r[c] = __fma_rn(kd[c], -2.16608493792591616511e-02, x[c]);
 #pragma unroll
@@ -171,112 +171,13 @@ __device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4
 #pragma unroll
   for (int c = 0; c < 4; c++) kd[c] = x[c] + SHIFT;
 #pragma unroll
-  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }
+  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }   // (an I2F.F64 instead of this add is slower)
 #pragma unroll
   for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_entry(tab_s, n[c]); }
 #pragma unroll
   for (int c = 0; c < 4; c++) p[c] = __fma_rn(GPMPC_EXP2S_C3, f[c], GPMPC_EXP2S_C2);
 #pragma unroll
   for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], f[c], GPMPC_EXP2S_C1);
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] *= f[c];
-#pragma unroll
-  for (int c = 0; c < 4; c++) res[c] = __fma_rn(t[c], p[c], t[c]);
-}
-
-// ---------------------------------------------------------------------------------------------
-// exp2b: the exponential of the uniform-kernel sweeps.  Those sweeps are bound by the shared-memory data pipe (ncu:
-// l1tex__data_pipe_lsu_wavefronts 86 % of peak in the forward kernel), and the per-lane lookup into one shared
-// 2048-entry table (exp2s) costs ~6 wavefronts per warp: the 16 lanes of a half-warp hit random bank pairs.  exp2b
-// keeps SIXTEEN copies of a smaller table, copy p living entirely in bank pair p (entry j of copy p at double
-// 16 j + p), and lane l only reads copy l & 15: every lookup is conflict-free (2 wavefronts, one per half-warp).
-//   LOG = 8: 256 entries (32 KB), quartic  -- 8 float64 operations; state dimensions <= 5 (two CTAs per SM still fit)
-//   LOG = 7: 128 entries (16 KB), quintic  -- 9 float64 operations; larger state dimensions (one CTA per SM, big records)
-// Same structure as exp2s otherwise: exponent in table units t2 = x * 2^LOG / ln 2, n = rint(t2) by a magic-number add,
-// pre-biased entries (the high word of entry j carries -(j << (20 - LOG))), clamp of deep underflow on the high word.
-// Coefficients: tools/gen/exp2_coeffs.py (truncation error 5.0e-18 / 1.5e-19).
-// ---------------------------------------------------------------------------------------------
-template <int LOG> struct Exp2B;
-template <> struct Exp2B<8> {
-  static constexpr double SCALE = 3.69329930467574627073e+02;   // 256 / ln 2
-  static constexpr unsigned HI_MIN = 0xC10FF000u;               // high word of -(1022 * 256).0
-  static constexpr int DEG = 4;
-  static constexpr double C1 = 2.70760617406228627432e-03, C2 = 3.66556559691010622906e-06, C3 = 3.30830294402499521092e-09,
-                          C4 = 2.23939519087515698716e-12, C5 = 0.0;
-};
-template <> struct Exp2B<7> {
-  static constexpr double SCALE = 1.84664965233787313537e+02;   // 128 / ln 2
-  static constexpr unsigned HI_MIN = 0xC0FFF000u;               // high word of -(1022 * 128).0
-  static constexpr int DEG = 5;
-  static constexpr double C1 = 5.41521234812457254865e-03, C2 = 1.46622623876404249162e-05, C3 = 2.64664214443309703440e-08,
-                          C4 = 3.58303308827120037297e-11, C5 = 3.88057615678653915067e-14;
-};
-HD constexpr int exp2b_log(int EV) { return EV <= 5 ? 8 : 7; }
-HD constexpr int exp2b_doubles(int LOG) { return 16 << LOG; }   // 16 bank-private copies
-
-// this lane's table copy: 32-bit shared-window address of its entry 0
-__device__ __forceinline__ unsigned exp2b_lane_base(const double* tab) {
-  return (unsigned)__cvta_generic_to_shared(tab) + 8u * (threadIdx.x & 15u);
-}
-template <int LOG>
-__device__ __forceinline__ double exp2b_clamp(double t2) {
-  const unsigned h = min((unsigned)__double2hiint(t2), Exp2B<LOG>::HI_MIN);
-  return __hiloint2double((int)h, __double2loint(t2));
-}
-template <int LOG>
-__device__ __forceinline__ double exp2b_entry(unsigned tb, int n) {   // 2^(n / 2^LOG)
-  const double raw = exp2s_lds(tb + ((n & ((1 << LOG) - 1)) << 7));
-  return __hiloint2double(__double2hiint(raw) + (n << (20 - LOG)), __double2loint(raw));
-}
-template <int LOG>
-__device__ __forceinline__ double exp2b_poly(double f) {   // 2^(f / 2^LOG) - 1
-  using C = Exp2B<LOG>;
-  double p;
-  if (C::DEG == 5) { p = __fma_rn(C::C5, f, C::C4); p = __fma_rn(p, f, C::C3); }
-  else p = __fma_rn(C::C4, f, C::C3);
-  p = __fma_rn(p, f, C::C2);
-  p = __fma_rn(p, f, C::C1);
-  return p * f;
-}
-template <int LOG>
-__device__ __forceinline__ double exp2b(double t2, unsigned tb) {
-  const double SHIFT = 6755399441055744.0;
-  t2 = exp2b_clamp<LOG>(t2);
-  double kd = t2 + SHIFT;
-  const int n = __double2loint(kd);
-  kd -= SHIFT;
-  const double f = t2 - kd;
-  const double t = exp2b_entry<LOG>(tb, n);
-  return __fma_rn(t, exp2b_poly<LOG>(f), t);
-}
-// Four at once, stage by stage (4 independent float64 operations per stage)
-template <int LOG>
-__device__ __forceinline__ void exp2b_x4(const double (&xin)[4], double (&res)[4], unsigned tb) {
-  using C = Exp2B<LOG>;
-  const double SHIFT = 6755399441055744.0;
-  double x[4], kd[4], f[4], p[4], t[4];
-  int n[4];
-#pragma unroll
-  for (int c = 0; c < 4; c++) x[c] = exp2b_clamp<LOG>(xin[c]);
-#pragma unroll
-  for (int c = 0; c < 4; c++) kd[c] = x[c] + SHIFT;
-#pragma unroll
-  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }
-#pragma unroll
-  for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2b_entry<LOG>(tb, n[c]); }
-  if (C::DEG == 5) {
-#pragma unroll
-    for (int c = 0; c < 4; c++) p[c] = __fma_rn(C::C5, f[c], C::C4);
-#pragma unroll
-    for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], f[c], C::C3);
-  } else {
-#pragma unroll
-    for (int c = 0; c < 4; c++) p[c] = __fma_rn(C::C4, f[c], C::C3);
-  }
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], f[c], C::C2);
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], f[c], C::C1);
 #pragma unroll
   for (int c = 0; c < 4; c++) p[c] *= f[c];
 #pragma unroll

@@ -13,7 +13,6 @@ struct RolloutParams {
   const double* il2;    // (E, D)  1 / lengthscale^2
   const double* s2;     // (E)     outputscale
   const double* exp2tab; // (2048)  2^(j/2048), correctly rounded, pre-biased (general path, exp2s)
-  const double* exp2btab; // (16 x 256 | 16 x 128)  bank-private tables of the uniform kernels (exp2b), chosen by E
   int N, NP, D, DP, E, Na;
   // ---- candidates
   int B, H, mode;            // mode 0: rollout, 1: single moment-matching step on given inputs

@@ -107,7 +107,7 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
       t[3] = fma(u1[e], nb[e], t[3]);
       t[2] = fma(u0[e], nb[e], t[2]);
     }
-    exp2b_x4<exp2b_log(EV)>(t, ex, s_tab);
+    exp2s_x4(t, ex, s_tab);
 #pragma unroll
     for (int b = 0; b < E; b++) {
       if (b & 1) { r1[b] = fma(ex[1], ba[b], r1[b]); r0[b] = fma(ex[0], ba[b], r0[b]); }
@@ -129,12 +129,10 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
 
 // Row factor of the sweeps (see uni_fwd_cols): kr (table units) -> e = exp(max(kr, kmin)), kr := residual shift.
 // kmin = -600 in natural units: with the total exponent <= 0, Eh' <= e^600 cannot overflow.
-template <int EV>
 __device__ __forceinline__ double uni_row_factor(double& kr, unsigned s_tab) {
-  constexpr int XL = exp2b_log(EV);
-  const double c = fmax(kr, -600.0 * Exp2B<XL>::SCALE);   // NaN -> kmin, and the residual keeps the NaN
+  const double c = fmax(kr, -600.0 * GPMPC_EXP2S_SCALE);   // NaN -> kmin, and the residual keeps the NaN
   kr -= c;
-  return exp2b<XL>(c, s_tab);
+  return exp2s(c, s_tab);
 }
 
 template <int EV>
@@ -157,8 +155,8 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
         q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
         q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
       }
-      u0[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q0 * il2[e];   // exponent in table units (exp2b)
-      u1[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q1 * il2[e];
+      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2[e];   // exponent in table units (exp2s)
+      u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2[e];
     }
   }
   double r0[E], r1[E];
@@ -171,7 +169,7 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   // columns are halved before the columns above it are added.
   const int jd1 = 64 * I + 64;
   jend = min(jend, (p.N + 1) & ~1);   // zero-padded columns (beta = 0, iK = 0) contribute exact zeros: skip them
-  const double e0 = uni_row_factor<EV>(kr0, s_tab), e1 = uni_row_factor<EV>(kr1, s_tab);   // kr0, kr1 become residual shifts
+  const double e0 = uni_row_factor(kr0, s_tab), e1 = uni_row_factor(kr1, s_tab);   // kr0, kr1 become residual shifts
   const bool far = __any_sync(0xffffffffu, kr0 != 0.0 || kr1 != 0.0);
   double trD0 = 0.0, trD1 = 0.0, trU0 = 0.0, trU1 = 0.0;
   if (jbeg < jd1) {
@@ -263,7 +261,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
   double* s_m = sm + L.m; double* s_s = sm + L.s; double* s_mu = sm + L.mu; double* s_A = sm + L.A;
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
-  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2b_lane_base(s_tabp);
+  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   double* s_part = sm + L.part; double* s_wp = sm + L.wp; double* s_S = sm + L.S; double* s_cst = sm + L.cst;
   const int nOut = L.nOut, warp = tid >> 5, nwarps = NT >> 5;
   const UniRecLayout RL = uni_rec_layout(E);
@@ -275,7 +273,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
                     p.kappa, p.use_constraints};
   const double* il2 = p.il2;            // row 0 (all rows equal)
   const double s2 = p.s2[0];
-  for (int i = tid; i < exp2b_doubles(exp2b_log(EV)); i += NT) s_tabp[i] = p.exp2btab[i];
+  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
   __syncthreads();
 
   long long clk_ = clock64();
@@ -379,11 +377,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
           if (d < D) tail = fma(nu[d] * nu[d], il2[d], tail);
-        const double ei = (i < N) ? exp2b<exp2b_log(EV)>((-0.5 * Exp2B<exp2b_log(EV)>::SCALE) * (quad + tail), s_tab) : 0.0;
+        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
         double* rec = s_rec + i * (2 * EV + 2);
 #pragma unroll
         for (int e = 0; e < EV; e++) rec[e] = nu[e];
-        rec[EV] = (i < N) ? Exp2B<exp2b_log(EV)>::SCALE * (-0.5 * (head + tail) + zqz) : 0.0;   // table units; log s2 factored out (s2^2 applied at the end)
+        rec[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;   // table units; log s2 factored out (s2^2 applied at the end)
 #pragma unroll
         for (int a = 0; a < E; a++) rec[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
         rec[2 * EV + 1] = ei;   // spare slot of the (even-length) record
@@ -592,7 +590,7 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
         t[3] = fma(u1[e], nb[e], t[3]);
         t[2] = fma(u0[e], nb[e], t[2]);
       }
-      exp2b_x4<exp2b_log(EV)>(t, w, s_tab);
+      exp2s_x4(t, w, s_tab);
 #pragma unroll
       for (int q = 0; q < 4; q++) w[q] *= c[q];
       rho0 += w[0] + w[2];
@@ -641,8 +639,8 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
         q0 = fma(Qm[e * EV + f], n0[f] * il2[f], q0);
         q1 = fma(Qm[e * EV + f], n1[f] * il2[f], q1);
       }
-      u0[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q0 * il2[e];   // exponent in table units (exp2b)
-      u1[e] = (2.0 * Exp2B<exp2b_log(EV)>::SCALE) * q1 * il2[e];
+      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2[e];   // exponent in table units (exp2s)
+      u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2[e];
     }
 #pragma unroll
     for (int a = 0; a < E; a++) {
@@ -659,7 +657,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   const int jd1 = 64 * I + 64;
   jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns contribute exact zeros: skip them (8 columns per round)
   // row factor e_i of the exponential (uni_fwd_cols) folded into the coefficient row vectors and the trace weights
-  const double e0 = uni_row_factor<EV>(kr0, s_tab), e1 = uni_row_factor<EV>(kr1, s_tab);   // kr0, kr1 become residual shifts
+  const double e0 = uni_row_factor(kr0, s_tab), e1 = uni_row_factor(kr1, s_tab);   // kr0, kr1 become residual shifts
   const bool far = __any_sync(0xffffffffu, kr0 != 0.0 || kr1 != 0.0);
   const double wb0 = wbar * e0, wb1 = wbar * e1;
 #pragma unroll
@@ -800,7 +798,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const int warp = tid >> 5, nwarps = NT >> 5;
   double* s_wp = sm + L.wp; double* s_wp2 = s_wp + 8 * L.wplen;   // per-warp rows of the B1 / B3 point sums
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q;
-  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2b_lane_base(s_tabp);
+  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
   double* s2p = sm + L.small2;
   // small2 carve: mu_bar[E], s_bar[E2], Om[E2], Rinv[E2], Ub[E2], Vb[E2], hg[E + E2] (h_bar, g_bar), scal[16]
   double* s_mubar = s2p; double* s_sbar = s_mubar + GPMPC_MAX_EV; double* s_Om = s_sbar + EV * EV;
@@ -810,7 +808,7 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
   const double* il2 = p.il2;
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
-  for (int i = tid; i < exp2b_doubles(exp2b_log(EV)); i += NT) s_tabp[i] = p.exp2btab[i];
+  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
   if (C == 1)
     for (int i = tid; i < NP * (2 + EV); i += NT) g_gam[i] = 0.0;   // B3 re-zeroes after every step (clusters: host memset)
   __syncthreads();
@@ -969,11 +967,11 @@ __global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd
           an[d] = 0.0;
           if (d < D) { tail = fma(nu[d] * nu[d], il2[d], tail); an[d] = nu[d] * il2[d]; }
         }
-        const double ei = (i < N) ? exp2b<exp2b_log(EV)>((-0.5 * Exp2B<exp2b_log(EV)>::SCALE) * (quad + tail), s_tab) : 0.0;
+        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
         double* rcd = s_rec + i * (2 * EV + 2);
 #pragma unroll
         for (int e = 0; e < EV; e++) rcd[e] = nu[e];
-        rcd[EV] = (i < N) ? Exp2B<exp2b_log(EV)>::SCALE * (-0.5 * (head + tail) + zqz) : 0.0;
+        rcd[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;
 #pragma unroll
         for (int a = 0; a < E; a++) rcd[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
 #pragma unroll

@@ -50,8 +50,7 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.rv = o; o += H + 1;
   L.ints = o; o += 4;
   o = (o + 1) & ~1;
-  o = (o + 15) & ~15;       // 128-byte aligned: copy p of the table sits in bank pair p
-  L.tab = o; o += exp2b_doubles(exp2b_log(EV));   // bank-private tables of exp2b
+  L.tab = o; o += EXP2S_N;   // 2^(j/2048) for exp2s (pre-biased entries)
   L.small2 = o; o += bwd ? (8 * EV * EV + 8 * GPMPC_MAX_D + E * E + 64) : 0;
   L.total = (o + 1) & ~1;
   return L;
