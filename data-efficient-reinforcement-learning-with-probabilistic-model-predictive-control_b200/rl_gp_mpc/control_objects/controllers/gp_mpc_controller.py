@@ -15,6 +15,8 @@ import numpy as np
 import torch
 from scipy.optimize import minimize
 
+from .batched_optim import minimize_box_adam, minimize_box_lbfgs
+
 from rl_gp_mpc.config_classes.total_config import Config
 from rl_gp_mpc.control_objects.actions_mappers.action_init_functions import (
     generate_mpc_action_init_frompreviousiter, generate_mpc_action_init_random)
@@ -131,7 +133,8 @@ class GpMpcController(BaseControllerObject):
         self.transition_model.prepare_inference(x_mem, y_mem)
 
     def _get_optimal_actions_batched(self, state_mu, state_var):
-        """B candidate action sequences optimised at once on the device (box-projected Adam on the LCB objective).
+        """B candidate action sequences optimised at once on the device (batched_optim.py: projected L-BFGS, or
+        projected Adam with ControllerConfig(batched_method="adam")) on the LCB objective.
 
         Replaces the serial restart loop of the reference (gp_mpc_controller.py:125-148): candidate 0 is the shifted
         previous solution (when init_from_previous_actions), the others are uniform random restarts; each iteration
@@ -144,28 +147,19 @@ class GpMpcController(BaseControllerObject):
         if ctl.init_from_previous_actions and self.actions_mpc_previous_iter is not None:
             warm = generate_mpc_action_init_frompreviousiter(self.actions_mpc_previous_iter, dim_action=na)
             x[0] = torch.as_tensor(warm, dtype=torch.float64, device=dev)
-        m = torch.zeros_like(x)
-        v = torch.zeros_like(x)
-        best_cost = torch.full((nb,), float("inf"), dtype=torch.float64, device=dev)
-        best_x = x.clone()
-        b1, b2, eps = 0.9, 0.999, 1e-8
-        for k in range(1, int(ctl.batched_iters) + 1):
-            out = self._rollout(x, state_mu, state_var, need_grad=True)
-            cost, grad = out["cost"], out["grad"]
-            ok = torch.isfinite(cost)
-            better = ok & (cost < best_cost)
+
+        def fun(xb):
+            out = self._rollout(xb, state_mu, state_var, need_grad=True, need_traj=False)
+            return out["cost"], out["grad"]
+
+        if getattr(ctl, "batched_method", "lbfgs") == "adam":
+            best_x, best_cost, x_last = minimize_box_adam(fun, x, ctl.batched_iters, lr=ctl.batched_lr)
+            cost = self._rollout(x_last, state_mu, state_var, need_grad=False, need_traj=False)["cost"]
+            better = torch.isfinite(cost) & (cost < best_cost)
             best_cost = torch.where(better, cost, best_cost)
-            best_x[better] = x[better]
-            grad = torch.nan_to_num(grad, nan=0.0, posinf=0.0, neginf=0.0)
-            m.mul_(b1).add_(grad, alpha=1 - b1)
-            v.mul_(b2).addcmul_(grad, grad, value=1 - b2)
-            step = (m / (1 - b1 ** k)) / ((v / (1 - b2 ** k)).sqrt() + eps)
-            x = (x - ctl.batched_lr * step).clamp_(0.0, 1.0)
-        out = self._rollout(x, state_mu, state_var, need_grad=False)
-        cost = out["cost"]
-        better = torch.isfinite(cost) & (cost < best_cost)
-        best_cost = torch.where(better, cost, best_cost)
-        best_x[better] = x[better]
+            best_x = torch.where(better[:, None], x_last, best_x)
+        else:
+            best_x, best_cost = minimize_box_lbfgs(fun, x, ctl.batched_iters)
         idx = int(torch.argmin(best_cost).item())
         final = self._rollout(best_x[idx:idx + 1], state_mu, state_var, need_grad=False)   # side effects of the winner
         self._store_side_effects(final, 0)
@@ -255,7 +249,7 @@ class GpMpcController(BaseControllerObject):
             self.transition_model.set_cost(self.config.reward)
             self._cost_bound = True
 
-    def _rollout(self, actions_mpc, obs_mu, obs_var, need_grad=True):
+    def _rollout(self, actions_mpc, obs_mu, obs_var, need_grad=True, need_traj=True):
         self._bind_cost()
         am = self.actions_mapper
         limit = bool(self.config.actions.limit_action_change)
@@ -263,7 +257,7 @@ class GpMpcController(BaseControllerObject):
             actions_mpc, obs_mu, obs_var, self.config.controller.len_horizon, iter_ctrl=self.iter_ctrl,
             limit_action_change=limit,
             max_change=self.config.actions.max_change_action_norm if limit else None,
-            action_prev=am.action_model_previous_iter if limit else None, need_grad=need_grad)
+            action_prev=am.action_model_previous_iter if limit else None, need_grad=need_grad, need_traj=need_traj)
 
     def _store_side_effects(self, out, idx):
         self.cost_traj_mean_lcb = -out["cost"][idx].cpu()

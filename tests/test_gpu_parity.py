@@ -247,7 +247,8 @@ def test_controller_api_drop_in():
     assert info.predicted_states.shape == (cfg["H"] + 1, 3) and np.isfinite(info.lower_bound_mean_predicted_cost)
 
 
-def test_batched_on_device_optimizer_beats_serial_restarts():
+@pytest.mark.parametrize("method,iters", [("lbfgs", 15), ("adam", 40)])
+def test_batched_on_device_optimizer_beats_serial_restarts(method, iters):
     """B candidates optimised simultaneously (one batched rollout per iteration) reach a cost at
     least as good as the reference-style serial scipy L-BFGS-B restarts from the same warm start."""
     from rl_gp_mpc import GpMpcController
@@ -285,7 +286,7 @@ def test_batched_on_device_optimizer_beats_serial_restarts():
     serial = controller(restarts_optim=2)
     a_serial = serial.get_action(obs)
     cost_serial = serial.last_optim_cost
-    batched = controller(batched_candidates=256, batched_iters=40, batched_lr=0.05)
+    batched = controller(batched_candidates=256, batched_iters=iters, batched_lr=0.05, batched_method=method)
     a_batched = batched.get_action(obs)
     cost_batched = batched.last_optim_cost
     assert abs(cost_batched + batched.cost_traj_mean_lcb.item()) < 1e-8      # side effects describe the winner

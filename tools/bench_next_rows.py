@@ -27,7 +27,7 @@ from rl_gp_mpc.config_classes.training_config import TrainingConfig  # noqa: E40
 from rl_gp_mpc.control_objects.models.gp_model import GpStateTransitionModel  # noqa: E402
 
 
-def controller(cfg, batched=0, restarts=2):
+def controller(cfg, batched=0, restarts=2, method="lbfgs", iters=30):
     E, Na, H = cfg["E"], cfg["Na"], cfg["H"]
     r = cfg["reward"]
     config = Config(
@@ -38,7 +38,7 @@ def controller(cfg, batched=0, restarts=2):
                                    exploration_factor=r["exploration_factor"]),
         actions_config=ActionsConfig(),
         controller_config=ControllerConfig(len_horizon=H, restarts_optim=restarts, batched_candidates=batched,
-                                           batched_iters=30),
+                                           batched_iters=iters, batched_method=method),
         training_config=TrainingConfig(training_frequency=10 ** 9),
         model_config=ModelConfig(gp_init={"noise_covar.noise": list(cfg["noise"]),
                                           "base_kernel.lengthscale": [list(v) for v in cfg["lengthscale"]],
@@ -61,7 +61,10 @@ def main():
         cfg = make_workload(name, B=1)
         obs = cfg["mu0"]
         for label, kw in (("scipy L-BFGS-B, 2 restarts", dict(batched=0, restarts=2)),
-                          ("batched on device, 256 candidates x 30 iterations", dict(batched=256))):
+                          ("batched on device, Adam, 256 candidates x 30 iterations", dict(batched=256, method="adam")),
+                          ("batched on device, L-BFGS, 256 candidates x 15 iterations", dict(batched=256, iters=15)),
+                          ("batched on device, L-BFGS, 64 candidates x 15 iterations", dict(batched=64, iters=15)),
+                          ("batched on device, L-BFGS, 16 candidates x 15 iterations", dict(batched=16, iters=15))):
             ctrl = controller(cfg, **kw)
             ctrl.get_action(obs)         # warm-up (first call: library load, allocations)
             t0 = time.perf_counter()
@@ -72,7 +75,7 @@ def main():
                 ctrl.get_action(obs)
                 costs.append(ctrl.last_optim_cost)
             dt = (time.perf_counter() - t0) / reps
-            print("N1 %-4s N=%d H=%d  %-50s %8.1f ms per control step, objective reached %.6f" % (
+            print("N1 %-4s N=%d H=%d  %-62s %8.1f ms per control step, objective reached %.6f" % (
                 name, cfg["N"], cfg["H"], label, dt * 1e3, float(np.mean(costs))), flush=True)
     # N2: hyper-parameter fit on the device objective
     for name in ("C2", "C4b"):
