@@ -13,100 +13,6 @@
 #define HD __host__ __device__ __forceinline__
 
 // ---------------------------------------------------------------------------------------------
-// exp for the N^2 loop.  Arguments are <= log(s2_a s2_b) (bounded above) and may be very
-// negative.  Cody-Waite reduction by ln2 + degree-12 polynomial, 2^k applied through the exponent
-// field.  ~1 ulp on [-708, 40]; returns 0 below -708.  NaN inputs are screened per step by the
-// caller (a NaN candidate is poisoned explicitly), so no NaN handling is needed here.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double exp_fast(double x) {
-  const double L2E = 1.4426950408889634074;
-  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52
-  double kd = __fma_rn(x, L2E, SHIFT);
-  int k = __double2loint(kd);
-  kd -= SHIFT;
-  double r = __fma_rn(kd, -6.93147180369123816490e-01, x);
-  r = __fma_rn(kd, -1.90821492927058770002e-10, r);
-  double p = 2.08767569878680989792e-09;            // 1/12!
-  p = __fma_rn(p, r, 2.50521083854417187751e-08);   // 1/11!
-  p = __fma_rn(p, r, 2.75573192239858906526e-07);   // 1/10!
-  p = __fma_rn(p, r, 2.75573192239858906526e-06);   // 1/9!
-  p = __fma_rn(p, r, 2.48015873015873015873e-05);   // 1/8!
-  p = __fma_rn(p, r, 1.98412698412698412698e-04);   // 1/7!
-  p = __fma_rn(p, r, 1.38888888888888888889e-03);   // 1/6!
-  p = __fma_rn(p, r, 8.33333333333333333333e-03);   // 1/5!
-  p = __fma_rn(p, r, 4.16666666666666666667e-02);   // 1/4!
-  p = __fma_rn(p, r, 1.66666666666666666667e-01);   // 1/3!
-  p = __fma_rn(p, r, 0.5);
-  p = __fma_rn(p, r, 1.0);
-  p = __fma_rn(p, r, 1.0);
-  int hi = __double2hiint(p) + (k << 20);
-  double res = __hiloint2double(hi, __double2loint(p));
-  return (k < -1021) ? 0.0 : res;
-}
-
-// Table variant used by the hot loops: x = (32 k + j) ln2/32 + r, |r| <= ln2/64,
-//   exp(x) = 2^k * T[j] * (1 + r + ... + r^6/720),   T[j] = 2^(j/32) in shared memory (32 doubles).
-// 11 float64 ops + one LDS instead of 16; max relative error 2.2e-16 (validated against 40-digit
-// arithmetic over [-60, 1]); same domain/underflow behaviour as exp_fast.
-__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
-  const double INV = 4.61662413084468283841e+01;   // 32 / ln2
-  const double SHIFT = 6755399441055744.0;
-  double kd = __fma_rn(x, INV, SHIFT);
-  int n = __double2loint(kd);
-  kd -= SHIFT;
-  double r = __fma_rn(kd, -2.16608493792591616511e-02, x);   // ln2/32 hi (30 bits)
-  r = __fma_rn(kd, -1.32391292681540124659e-11, r);          // ln2/32 lo
-  double p = 1.38888888888888888889e-03;
-  p = __fma_rn(p, r, 8.33333333333333333333e-03);
-  p = __fma_rn(p, r, 4.16666666666666666667e-02);
-  p = __fma_rn(p, r, 1.66666666666666666667e-01);
-  p = __fma_rn(p, r, 0.5);
-  p = __fma_rn(p, r, 1.0);
-  p *= r;
-  n = max(n, -32704);                              // k >= -1022: deep underflow collapses to ~2e-308 (one IMNMX)
-  const double t = tab[n & 31];
-  const double res = __fma_rn(t, p, t);
-  const int hi = __double2hiint(res) + (int)(((unsigned)n & 0xFFFFFFE0u) << 15);   // += k << 20
-  return __hiloint2double(hi, __double2loint(res));
-}
-
-// Four exponentials evaluated stage by stage (4 independent FMAs per stage).  Measured on B200: the FP64 pipe
-// needs ~4 independent dependent-chains PER WARP to saturate (DFMA latency 8.3 clk; 4 warps x 1 chain reach only
-// 65 % of peak, 4 warps x 4 chains 92 % -- tools/micro/dfma_latency.cu), so the hot loops feed it 4 elements at once.
-__device__ __forceinline__ void exp_tab_x4(const double (&x)[4], double (&res)[4], const double* __restrict__ tab) {
-  const double INV = 4.61662413084468283841e+01, SHIFT = 6755399441055744.0;
-  double kd[4], r[4], p[4], t[4];
-  int n[4];
-#pragma unroll
-  for (int c = 0; c < 4; c++) kd[c] = __fma_rn(x[c], INV, SHIFT);
-#pragma unroll
-  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }   // (an I2F.F64 instead of this add is slower)
-#pragma unroll
-  for (int c = 0; c < 4; c++) r[c] = __fma_rn(kd[c], -2.16608493792591616511e-02, x[c]);
-#pragma unroll
-  for (int c = 0; c < 4; c++) r[c] = __fma_rn(kd[c], -1.32391292681540124659e-11, r[c]);
-#pragma unroll
-  for (int c = 0; c < 4; c++) { n[c] = max(n[c], -32704); t[c] = tab[n[c] & 31]; }
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] = __fma_rn(1.38888888888888888889e-03, r[c], 8.33333333333333333333e-03);
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 4.16666666666666666667e-02);
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 1.66666666666666666667e-01);
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 0.5);
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], r[c], 1.0);
-#pragma unroll
-  for (int c = 0; c < 4; c++) p[c] *= r[c];
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    const double v = __fma_rn(t[c], p[c], t[c]);
-    const int hi = __double2hiint(v) + (int)(((unsigned)n[c] & 0xFFFFFFE0u) << 15);
-    res[c] = __hiloint2double(hi, __double2loint(v));
-  }
-}
-
 // Hot-loop exponential, 7 float64 operations + 5 integer/LDS instructions.  The caller passes the exponent already
 // in table units, t2 = x * 2048 / ln 2 (the scale is folded into the per-row / per-column terms when they are built,
 // so it costs nothing per element):
@@ -161,7 +67,7 @@ __device__ __forceinline__ double exp2s(double t2, unsigned tab_s) {
   return __fma_rn(t, p, t);
 }
 
-// Four at once, stage by stage (4 independent float64 operations per stage, see exp_tab_x4).
+// Four at once, stage by stage (4 independent float64 operations per stage).
 __device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4], unsigned tab_s) {
   const double SHIFT = 6755399441055744.0;
   double x[4], kd[4], f[4], p[4], t[4];
