@@ -2,6 +2,7 @@
 run_env) against this backend.  The environment and the recorder are host code (CPU tests); the closed loop needs the
 CUDA engine (gpu test)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -125,3 +126,80 @@ def test_run_env_closes_the_loop_on_process_control(tmp_path, include_time_model
     assert os.path.isfile(os.path.join(str(tmp_path), "run_history.npz"))
     assert any(m == "append" for m, _ in modes), modes          # the memory grew one point at a time
     assert max(n for _, n in modes) >= 6
+
+
+def test_classic_control_stand_ins_follow_the_published_dynamics():
+    """Pendulum-v0 / MountainCarContinuous-v0 stand-ins (used by examples/pendulum, examples/mountain_car without gym)."""
+    from rl_gp_mpc.envs.classic_control import MountainCarContinuous, Pendulum
+    p = Pendulum(seed=0)
+    obs = p.reset()
+    assert obs.shape == (3,) and abs(obs[0] ** 2 + obs[1] ** 2 - 1.0) < 1e-12
+    assert np.all(p.observation_space.high == np.array([1, 1, 8], np.float32)) and p.action_space.high[0] == 2
+    p.state = np.array([np.pi, 0.0])                       # hanging down, at rest, no torque: stays there
+    obs, rew, done, _ = p.step([0.0])
+    np.testing.assert_allclose(p.state, [np.pi, 0.0], atol=1e-12)
+    assert not done and abs(rew + np.pi ** 2) < 1e-12
+    p.state = np.array([0.5, 1.0])                         # one Euler step by hand, torque clipped at 2
+    obs, rew, _, _ = p.step([5.0])
+    thdot = 1.0 + (-15.0 * np.sin(0.5 + np.pi) + 3.0 * 2.0) * 0.05
+    np.testing.assert_allclose(p.state, [0.5 + thdot * 0.05, thdot], atol=1e-12)
+    assert abs(rew + (0.25 + 0.1 + 0.001 * 4.0)) < 1e-12
+    np.testing.assert_allclose(obs, [np.cos(p.state[0]), np.sin(p.state[0]), thdot], atol=1e-12)
+    p.state = np.array([0.0, 7.99])
+    p.step([2.0])
+    assert p.state[1] <= 8.0                               # speed limit
+    m = MountainCarContinuous(seed=0)
+    obs = m.reset()
+    assert -0.6 <= obs[0] <= -0.4 and obs[1] == 0.0
+    m.state = np.array([-0.5, 0.0])
+    obs, rew, done, _ = m.step([1.0])
+    v = 0.0015 - 0.0025 * np.cos(-1.5)
+    np.testing.assert_allclose(obs, [-0.5 + v, v], atol=1e-15)
+    assert not done and abs(rew + 0.1) < 1e-15
+    m.state = np.array([-1.2, -0.05])                      # inelastic left wall
+    obs, _, _, _ = m.step([-1.0])
+    assert obs[0] == -1.2 and obs[1] == 0.0
+    m.state = np.array([0.44, 0.07])
+    obs, rew, done, _ = m.step([1.0])
+    assert done and abs(rew - 99.9) < 1e-12
+    m.state = np.array([-0.5, 0.0])                        # full throttle alone never climbs out (the point of the task)
+    top = max(m.step([1.0])[0][0] for _ in range(300))
+    assert top < 0.45
+
+
+def test_example_configs_carry_the_reference_values():
+    """examples/pendulum and examples/mountain_car: dimensions and hyper-parameters of BASELINE.json configs C1-C3."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for rel, dims, horizon, maxfun in (("examples/pendulum/config_pendulum.py", 3, 15, 4),
+                                       ("examples/mountain_car/config_mountaincar.py", 2, 10, 8)):
+        spec = importlib.util.spec_from_file_location("cfg_" + str(dims), os.path.join(root, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        cfg = mod.get_config()
+        assert cfg.controller.len_horizon == horizon and cfg.controller.actions_optimizer_params["maxfun"] == maxfun
+        assert len(cfg.model.gp_init["noise_covar.noise"]) == dims
+        assert float(np.asarray(cfg.model.gp_init["outputscale"]).reshape(-1)[0]) == 5e-2
+        assert float(np.asarray(cfg.model.gp_init["base_kernel.lengthscale"]).reshape(-1)[0]) == 0.5
+        assert cfg.reward.target_state_norm.shape[-1] == dims
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("example", ["pendulum", "mountain_car"])
+def test_examples_close_the_loop_on_the_stand_in_environments(tmp_path, example):
+    import importlib.util
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    name = {"pendulum": "run_pendulum", "mountain_car": "run_mountaincar"}[example]
+    sys.path.insert(0, os.path.join(root, "examples", example))
+    try:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "examples", example, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        np.random.seed(5)
+        torch.manual_seed(5)
+        costs = getattr(mod, name)(num_steps=14, random_actions_init=8, num_repeat_actions=1, len_horizon=6, seed=5,
+                                   folder_save=str(tmp_path))
+    finally:
+        sys.path.pop(0)
+    assert costs.shape == (14,) and np.all(np.isfinite(costs)) and np.all(costs >= 0)
