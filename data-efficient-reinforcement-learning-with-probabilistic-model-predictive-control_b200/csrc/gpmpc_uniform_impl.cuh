@@ -54,6 +54,11 @@ constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forwar
 #ifndef UNI_MINB
 #define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
 #endif
+// The forward kernel is built twice for state dimensions <= 5: MAXT = 256 (two CTAs per SM, <= 128 registers; also the
+// thread-block-cluster launches) and MAXT = 128 with three CTAs per SM (<= 168 registers): with the larger register
+// budget ptxas hoists the record / iK loads of a loop body to its top and interleaves the stages of both column pairs
+// (forward 60.6 -> 57.9 ms at the headline shape).  The host picks it when three CTAs fit the shared memory.
+#define UNI_FWD_MINCTAS(EV, MAXT) ((MAXT) == 128 && (EV) <= 5 ? 3 : UNI_MINB(EV))
 
 // ---------------------------------------------------------------------------------------------
 // forward hot loop: full sweep, rows {64 I + lane, +32}, columns [jbeg, jend)
@@ -249,8 +254,8 @@ __device__ __forceinline__ void uni_moments_slice(const double* __restrict__ s_r
 // ---------------------------------------------------------------------------------------------
 // uniform forward kernel (value + small per-step record when p.records != NULL)
 // ---------------------------------------------------------------------------------------------
-template <int EV>
-__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_fwd_kernel(const RolloutParams p) {
+template <int EV, int MAXT>
+__global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_kernel(const RolloutParams p) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -1234,9 +1239,16 @@ cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, 
     if (e != cudaSuccess) return e;
     e = cudaLaunchKernelEx(&cfg, uniform_bwd_kernel<EV>, p, grad);
   } else {
-    e = cudaFuncSetAttribute(uniform_fwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaLaunchKernelEx(&cfg, uniform_fwd_kernel<EV>, p);
+    if (EV <= 5 && threads <= 128) {   // three-CTAs-per-SM build (see UNI_FWD_MINCTAS)
+      constexpr int T = EV <= 5 ? 128 : UNIFORM_MAX_THREADS;   // (no extra instantiation for the larger state dims)
+      e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaLaunchKernelEx(&cfg, uniform_fwd_kernel<EV, T>, p);
+    } else {
+      e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaLaunchKernelEx(&cfg, uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, p);
+    }
   }
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
