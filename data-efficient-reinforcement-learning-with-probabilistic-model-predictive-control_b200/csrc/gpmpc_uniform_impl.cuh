@@ -59,6 +59,15 @@ constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forwar
 // budget ptxas hoists the record / iK loads of a loop body to its top and interleaves the stages of both column pairs
 // (forward 60.6 -> 57.9 ms at the headline shape).  The host picks it when three CTAs fit the shared memory.
 #define UNI_FWD_MINCTAS(EV, MAXT) ((MAXT) == 128 && (EV) <= 5 ? 3 : UNI_MINB(EV))
+// tuning hook (tools/variants.sh): launch bounds of the reverse-sweep kernel, e.g. -DUNI_BWD_MAXT=128 -DUNI_BWD_MINCTAS_ALL=3
+#ifndef UNI_BWD_MAXT
+#define UNI_BWD_MAXT UNIFORM_MAX_THREADS
+#endif
+#ifdef UNI_BWD_MINCTAS_ALL
+#define UNI_BWD_MINCTAS(EV) UNI_BWD_MINCTAS_ALL
+#else
+#define UNI_BWD_MINCTAS(EV) UNI_MINB(EV)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // forward hot loop: full sweep, rows {64 I + lane, +32}, columns [jbeg, jend)
@@ -778,7 +787,7 @@ __device__ inline void uni_stage_adjoint(const RolloutParams& p, int Na, double 
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__global__ void __launch_bounds__(UNIFORM_MAX_THREADS, UNI_MINB(EV)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
+__global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
