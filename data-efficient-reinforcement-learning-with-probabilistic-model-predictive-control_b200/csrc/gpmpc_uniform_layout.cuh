@@ -34,7 +34,11 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.wplen = bwd ? (D + P) : (E * L.nOut);
   L.wp = o; o += (bwd ? 16 : 8) * L.wplen;   // reverse sweep: two sets (B1, B3)
   L.S = o; o += 2 * E * E;          // S and s V^T of the recurrence stage
-  L.cst = o; o += GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + GPMPC_MAX_EV * GPMPC_MAX_EV;   // target, W, WT
+  L.cst = o;                        // target, W, WT (read from shared memory by the forward kernel only)
+#ifdef GPMPC_BWD_NO_CST              // tuning variant (tools/variants.sh build-all): 2.7 KB less for the reverse sweep
+  if (!bwd)
+#endif
+  o += GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + GPMPC_MAX_EV * GPMPC_MAX_EV;
   L.m = o; o += GPMPC_MAX_D;
   L.s = o; o += EV * EV;
   L.mu = o; o += GPMPC_MAX_EV;
