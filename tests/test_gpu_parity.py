@@ -3,7 +3,7 @@ reference's own code, (b) the CPU oracle on seeded workloads, (c) size-independe
 
 Tolerance (float64 path, stated per north_star): absolute 1e-8 on costs / states / variances / rewards and
 1e-7 on gradients and V, for training sets with cond(K + noise I) up to ~1e7 (the reference's hyper-parameter
-regime, noise 1e-5).  Measured errors on B200 are 1e-11 or better (profiles/parity_r01.txt)."""
+regime, noise 1e-5).  Measured errors on B200 are 1e-11 or better (smoke: profiles/r01_s8_smoke.txt)."""
 import numpy as np
 import pytest
 import torch
