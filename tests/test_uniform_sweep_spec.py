@@ -103,9 +103,13 @@ def _case(ls, obs_var, seed, N=150, E=2, Na=1):
     return d, m, s
 
 
-def test_uniform_sweep_matches_the_pairwise_formula():
+import pytest
+
+
+@pytest.mark.parametrize("E,Na,N", [(2, 1, 150), (1, 1, 64), (3, 2, 70), (4, 2, 129)])
+def test_uniform_sweep_matches_the_pairwise_formula(E, Na, N):
     tab = prebiased_table()
-    d, m, s = _case(ls=0.3, obs_var=1e-3, seed=1)
+    d, m, s = _case(ls=0.3, obs_var=1e-3, seed=1, N=N, E=E, Na=Na)
     ref = step_forward(d, m, s)["Sraw"]
     got, far = uniform_sweep(d, m, s, tab)
     assert not far
