@@ -127,3 +127,51 @@ def test_far_rows_keep_their_contribution_through_the_residual_shift():
     got = got * d.s2[0] ** 2
     iu = np.triu_indices(d.E)
     np.testing.assert_allclose(got[iu], ref[iu], rtol=0, atol=1e-9 * max(1.0, np.abs(ref).max()))
+
+
+def test_reverse_sweep_sums_over_the_tile_triangle_equal_the_full_symmetric_sums():
+    """uniform_bwd_kernel sweeps w_ij = (beta_i^T Om beta_j - wbar iK_ij) Eh_ij over the tiles on or above the diagonal
+    (diagonal tile in full, half weight), with the row factor e_i folded into the coefficient row vector and the trace
+    weight.  Its consumers only use  g_i = rho_i + gam_i  and the (i <-> j)-symmetric contraction of xi with z, which
+    must equal the full row sums and HALF the full symmetric contraction (B4 doubles it)."""
+    tab = prebiased_table()
+    d, m, s = _case(ls=0.3, obs_var=2e-3, seed=7, N=150, E=3, Na=1)
+    E, N = d.E, d.N
+    NP = (N + 63) // 64 * 64
+    rng = np.random.default_rng(3)
+    Om = rng.standard_normal((E, E)); Om = Om + Om.T                    # adjoint of S_raw (symmetric)
+    wbar = float(np.trace(Om))
+    il2 = d.il2[0, :E]
+    nu = np.zeros((NP, E)); nu[:N] = (d.x - m)[:, :E]
+    tail = np.zeros(NP); tail[:N] = (((d.x - m)[:, E:]) ** 2 * d.il2[0, E:]).sum(1)
+    beta = np.zeros((NP, E)); beta[:N] = d.beta.T
+    iK = np.zeros((NP, NP)); iK[:N, :N] = d.iK[0]
+    Q = 0.5 * np.linalg.solve(s * (2.0 * il2)[None, :] + np.eye(E), s)
+    z = nu * il2
+    kap = SCALE * (-0.5 * ((nu ** 2 * il2).sum(1) + tail) + np.einsum("ie,ef,if->i", z, Q, z)); kap[N:] = 0.0
+    u = 2.0 * SCALE * (z @ Q) * il2
+    # full symmetric reference
+    Eh = np.exp((kap[:, None] + kap[None, :] + u @ nu.T) / SCALE)
+    w = (beta @ Om @ beta.T - wbar * iK) * Eh
+    assert np.abs(w - w.T).max() <= 1e-9 * np.abs(w).max()
+    g_full = w.sum(1)
+    sym_full = np.einsum("ij,ik,jl->kl", w, z, z); sym_full = sym_full + sym_full.T
+    # tile-triangle sweep with the row factor folded in
+    e = exp2s(np.maximum(kap, -600.0 * SCALE), tab)
+    resid = kap - np.maximum(kap, -600.0 * SCALE)
+    rho = np.zeros(NP); gam = np.zeros(NP); xi = np.zeros((NP, E))
+    nrb = NP // 64
+    for I in range(nrb):
+        rows = slice(64 * I, 64 * I + 64)
+        p = (beta[rows] @ Om) * e[rows][:, None]                        # coefficient row vectors, row factor folded in
+        wb = wbar * e[rows]
+        for J in range(I, nrb):
+            cols = slice(64 * J, 64 * J + 64)
+            half = 0.5 if J == I else 1.0
+            c = half * (p @ beta[cols].T - wb[:, None] * iK[rows, cols])
+            wt = c * exp2s(kap[cols][None, :] + u[rows] @ nu[cols].T + resid[rows][:, None], tab)
+            rho[rows] += wt.sum(1); gam[cols] += wt.sum(0); xi[rows] += wt @ nu[cols]
+    scale = np.abs(g_full).max()
+    np.testing.assert_allclose(rho + gam, g_full, rtol=0, atol=1e-10 * scale)
+    X = z.T @ (xi * il2)
+    np.testing.assert_allclose(2.0 * (X + X.T), sym_full, rtol=0, atol=1e-10 * np.abs(sym_full).max())
