@@ -8,7 +8,7 @@ bench.py's cpu_baseline / --impl reference legs may import it; the product path
 Pinned by: tests/golden/*.npz, produced by oracle/make_golden.py from the
 reference's own code imported verbatim from /root/reference (oracle/
 ref_loader.py; gpytorch replaced by oracle/gpytorch_shim, whose only arithmetic
-is the RBF Gram matrix).  tests/test_oracle_vs_reference.py checks every function
+is the RBF Gram matrix).  tests/test_oracle_vs_golden.py checks every function
 here against those vectors.  The reference itself has no tests / golden vectors
 for this path ("parity unpinned" by the reference); and the
 Gram matrix follows gpytorch's published formula, not an executed gpytorch.
