@@ -47,7 +47,7 @@ struct gpmpc_handle {
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
   DevBuf dbg_clk, ws_uni, queue, ws_cl;
-  DevBuf ws_kk, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
+  DevBuf ws_kk, ws_gam, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
   long long launches = 0;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -132,7 +132,7 @@ int gpmpc_create(gpmpc_handle** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return GPMPC_ERR_CUDA; }
   h->num_sms = prop.multiProcessorCount;
-  h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->smem_optin = prop.sharedMemPerBlockOptin - GPMPC_STATIC_SMEM;   // budget of the DYNAMIC allocation (static: exp table)
   for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
   {  // 2^(j/2048), rounded once from extended precision, stored pre-biased for exp2s: (j << 9) is subtracted from the
      // high word so that the kernels restore the entry and apply 2^(n >> 11) with one integer add (exp2s_entry)
@@ -161,7 +161,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
-                   &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->t_mu, &h->t_var,
+                   &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->ws_gam, &h->t_mu, &h->t_var,
                    &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue, &h->ws_cl};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
@@ -300,7 +300,7 @@ int gpmpc_set_cost(gpmpc_handle* h, const double* target, const double* W, const
 }
 
 static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int B, int H, int Na, size_t* smem,
-                       int* grid, bool uniform = false) {
+                       int* grid, int* threads, bool uniform = false) {
   p.x = h->x.as<double>(); p.beta = h->beta.as<double>(); p.iK = h->iK.as<double>();
   p.il2 = h->il2.as<double>(); p.s2 = h->s2.as<double>(); p.exp2tab = h->exp2tab.as<double>();
   p.N = h->N; p.NP = h->NP; p.D = h->D; p.DP = h->DP; p.E = h->E; p.Na = Na;
@@ -313,27 +313,53 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
     p.seg = 32;   // forward sweep: columns per chunk of the static tile-triangle split (divides 64)
     *smem = 0;
     *grid = 0;
+    *threads = 0;
     return GPMPC_OK;
   }
-  int G = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, h->smem_optin);
-  if (G < 1) return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
-  // Small batches of rollouts: a thread-block cluster shares each candidate, one output pair (a, b) per group, the
-  // groups dealt to the CTAs (rollout_kernel).  Worth it once the N^2 sweeps dominate (NP >= 128).
+  // Launch plan of the general kernel: G = output pairs per N^2 phase (their column terms live in shared memory).  Two
+  // CTAs per SM (half of the kernel's thread budget each) when that costs no extra phase -- one CTA's serial small-matrix
+  // phases then overlap the other's sweep -- else one CTA with all the threads.
+  const size_t half_sm = (size_t)(227 * 1024) / 2 - 1024 - GPMPC_STATIC_SMEM;
+  const int P = h->E * (h->E + 1) / 2;
+  const int maxt = rollout_max_threads(EV);
+  const int G1 = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, maxt / 32, h->smem_optin);
+  const int G2 = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, maxt / 64, half_sm < h->smem_optin ? half_sm : h->smem_optin);
+  if (G1 < 1) return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
+  // measured at the headline shape (profiles/r02a_general_launch_plans.txt): 1 x 384 threads 237.6 k predictions/s,
+  // 2 x 192 219.2 k, 2 x 128 223.3 k; the 128-register build: 1 x 512 236.5 k, 2 x 256 233.1 k -> one CTA per SM
+  int ctas = 1;
+  if (const char* e = getenv("GPMPC_GEN_CTAS")) { int v = atoi(e); if (v == 1 || (v == 2 && G2 >= 1 && maxt / 2 >= 128)) ctas = v; }
+  // Small batches of rollouts: a thread-block cluster shares each candidate, its output pairs (a, b) dealt to the CTAs
+  // (rollout_kernel).  Worth it once the N^2 sweeps dominate (NP >= 128).
   p.cluster = 1;
   if (H > 0) {
-    const int P = h->E * (h->E + 1) / 2;
     int c = 8;
     while (c > 1 && (B * c > h->num_sms || P < c || h->NP < 128)) c /= 2;
     if (const char* e = getenv("GPMPC_GEN_CLUSTER")) { int v = atoi(e); if (v == 1 || ((v == 2 || v == 4 || v == 8) && B * v <= h->num_sms && P >= v)) c = v; }
     p.cluster = c;
-    if (c > 1) { G = 1; p.seg = 32; }   // one pair per group; finer work items (16 warps share one pair's sweep)
+    if (c > 1) ctas = 1;
   }
+  if (B <= h->num_sms) ctas = 1;       // nothing to overlap with: give the candidate all the threads
+  const int G = ctas == 2 ? G2 : G1;
   p.group = G;
-  *smem = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G, H, Na);
-  *grid = p.cluster > 1 ? B * p.cluster : (B < h->num_sms ? B : h->num_sms);
+  *threads = maxt / ctas;
+  if (const char* e = getenv("GPMPC_GEN_THREADS")) { int v = atoi(e); if (v >= 128 && v <= maxt / ctas && v % 32 == 0) *threads = v; }
+  p.seg = 32;                          // columns per chunk of the static split of the sweeps (divides 64)
+  {  // small training sets / clusters: finer chunks so that every warp gets a run
+    const int nrb = h->NP / 64, nw = *threads / 32;
+    while (p.seg > 8 && (64 / p.seg) * nrb * (nrb + 1) / 2 * ((P + p.cluster - 1) / p.cluster) < 2 * nw) p.seg /= 2;
+  }
+  if (const char* e = getenv("GPMPC_GEN_SEG")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) p.seg = v; }
+  *smem = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G, H, Na, *threads / 32);
+  *grid = p.cluster > 1 ? B * p.cluster : (B < h->num_sms * ctas ? B : h->num_sms * ctas);
   cudaError_t ce = h->ws_kk.ensure(sizeof(double) * (size_t)(*grid) * h->E * h->NP);
   if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
   p.ws_kk = h->ws_kk.as<double>();
+  if (grad) {
+    ce = h->ws_gam.ensure(sizeof(double) * (size_t)(*grid) * G * h->NP);
+    if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
+    p.ws_gam = h->ws_gam.as<double>();
+  }
   return GPMPC_OK;
 }
 
@@ -347,13 +373,13 @@ int gpmpc_predict_step(gpmpc_handle* h, const double* input_mu, const double* in
   CU(cudaSetDevice(h->device));
   RolloutParams p;
   memset(&p, 0, sizeof(p));
-  size_t smem; int grid;
-  int rc = fill_common(h, p, EV, false, B, 0, 1, &smem, &grid);
+  size_t smem; int grid, threads;
+  int rc = fill_common(h, p, EV, false, B, 0, 1, &smem, &grid, &threads);
   if (rc) return rc;
   p.mode = 1;
   p.obs_mu = input_mu; p.obs_var = input_var;
   p.stepM = M; p.stepS = S; p.stepV = V;
-  CU(launch_rollout(EV, false, p, grid, smem, st));
+  CU(launch_rollout(EV, false, p, grid, threads, smem, st));
   h->launches += 1;
   return GPMPC_OK;
 }
@@ -378,9 +404,9 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
   const bool want_grad = grad != nullptr;
   RolloutParams p;
   memset(&p, 0, sizeof(p));
-  size_t smem; int grid;
+  size_t smem; int grid, threads;
   const bool use_uniform = h->uniform && h->path_mode == 0;
-  int rc = fill_common(h, p, E, want_grad, B, H, Na, &smem, &grid, use_uniform);
+  int rc = fill_common(h, p, E, want_grad, B, H, Na, &smem, &grid, &threads, use_uniform);
   if (rc) return rc;
   p.mode = 0;
   p.include_time = include_time; p.iter_ctrl = iter_ctrl; p.per_cand_init = per_candidate_init ? 1 : 0;
@@ -399,8 +425,8 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
   if (!actions_model) { CU(h->t_am.ensure(sizeof(double) * (size_t)B * H * Na)); actions_model = h->t_am.as<double>(); }
   p.cost = cost; p.states_mu = states_mu; p.states_var = states_var; p.rewards = rewards; p.rewards_var = rewards_var;
   p.actions_model = actions_model;
-  const RecLayout RL = rec_layout(E, D);
-  if (want_grad) {
+  if (want_grad && !use_uniform) {   // general-path records (the uniform path sizes its own, 12x smaller, layout below)
+    const RecLayout RL = rec_layout(E, D);
     CU(h->records.ensure(sizeof(double) * (size_t)B * H * RL.size));
     p.records = h->records.as<double>();
   }
@@ -421,7 +447,8 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false);
     {  // precomputed per-step matrices: only if they do not cost a resident CTA (or the launch itself)
       const size_t with = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true);
-      const size_t lim = smb <= 112 * 1024 ? 112 * 1024 : h->smem_optin;
+      const size_t two = 112 * 1024 - GPMPC_STATIC_SMEM;   // two CTAs per SM
+      const size_t lim = smb <= two ? two : h->smem_optin;
       p.premat = with <= lim ? 1 : 0;
       if (const char* e = getenv("GPMPC_UNI_PREMAT")) p.premat = (atoi(e) != 0 && with <= lim) ? 1 : 0;
       if (p.premat) smb = with;
@@ -431,13 +458,13 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     // several small CTAs per SM so that one CTA's serial small-matrix phases overlap another's N^2 sweep
     auto plan = [&](size_t sm, int* thr, int* grd, const char* env_thr, const char* env_ctas, bool fwd) {
       const size_t per_sm = 227 * 1024;
-      int fit = (int)(per_sm / (sm + 1024));
+      int fit = (int)(per_sm / (sm + GPMPC_STATIC_SMEM + 1024));
       if (fit < 1) fit = 1;
       int ctas = fit > 2 ? 2 : fit;      // tuned on B200: 2 CTAs x 256 threads per SM (16 warps, <= 128 registers)
       *thr = 256;
       // forward kernel, state dimensions <= 5: 3 CTAs x 128 threads with <= 168 registers when they fit (57.9 vs 60.6 ms)
       if (fwd && E <= 5 && fit >= 3) { ctas = 3; *thr = 128; }
-      if (const char* e = getenv(env_thr)) { int v = atoi(e); if (v == 128 || v == 256) *thr = v; }   // tuning aid
+      if (const char* e = getenv(env_thr)) { int v = atoi(e); if (v == 128 || v == 256 || (!fwd && v == 192)) *thr = v; }   // tuning aid
       if (const char* e = getenv(env_ctas)) { int v = atoi(e); if (v >= 1 && v <= fit) ctas = v; }
       if (E > 5) { *thr = 256; ctas = 1; }   // large state dims: 255-register kernels, one CTA per SM
       if (ctas * (*thr) > 512) ctas = 512 / (*thr);
@@ -536,17 +563,24 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
   const bool dbg_gen = getenv("GPMPC_DEBUG_CLOCKS") != nullptr;   // tuning aid: per-phase cycles of CTA 0 on stderr
   if (dbg_gen) {
     CU(h->dbg_clk.ensure(sizeof(long long) * (16 + 4 * 2048)));
-    CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * 16, st));
+    CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * 64, st));
     p.dbg_clk = h->dbg_clk.as<long long>();
   }
   if (h->timing) CU(cudaEventRecord(h->ev[0], st));
-  CU(launch_rollout(E, want_grad, p, grid, smem, st));
+  CU(launch_rollout(E, want_grad, p, grid, threads, smem, st));
   h->launches += 1;
   if (dbg_gen) {
-    long long c[16];
+    long long c[64];
     CU(cudaMemcpyAsync(c, h->dbg_clk.ptr, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const long long ns = (long long)((B + grid / p.cluster - 1) / (grid / p.cluster)) * H;
+    {  // per-warp duration of the sweep: the static split's balance
+      long long mn = c[32], mx = c[32];
+      for (int w = 0; w < threads / 32; w++) { if (c[32 + w] < mn) mn = c[32 + w]; if (c[32 + w] > mx) mx = c[32 + w]; }
+      fprintf(stderr, "[gpmpc general sweep per warp, CTA 0, %d warps] fastest %lld  slowest %lld clocks/step:", threads / 32, mn / ns, mx / ns);
+      for (int w = 0; w < threads / 32; w++) fprintf(stderr, " %lld", c[32 + w] / ns);
+      fprintf(stderr, "\n");
+    }
     fprintf(stderr, "[gpmpc general clocks/step, CTA 0, cluster %d, group %d] P0a %lld  P0b %lld  P1 %lld  P2 %lld  P2b %lld | per step over its pairs: P3 setup %lld  sweep %lld  reduce %lld  finalize+next %lld | exchange %lld  P4 %lld\n",
             p.cluster, p.group, c[0] / ns, c[1] / ns, c[2] / ns, c[3] / ns, c[4] / ns, c[5] / ns, c[6] / ns, c[7] / ns, c[9] / ns, c[8] / ns, 0LL);
   }

@@ -33,13 +33,24 @@ constexpr int EXP2S_N = 1 << EXP2S_LOG;
 #define GPMPC_EXP2S_C3 6.46152867293236580665e-12
 #define GPMPC_EXP2S_HI_MIN 0xC13FF000u                 /* high word of -(1022 * 2048).0 */
 
-__device__ __forceinline__ unsigned exp2s_table_addr(const double* tab) {   // 32-bit shared-window address
-  return (unsigned)__cvta_generic_to_shared(tab);
-}
-__device__ __forceinline__ double exp2s_lds(unsigned addr) {
-  double v;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
+// The table lives in STATIC shared memory, as the first member of the only static shared object of the kernels.  On
+// sm_100a user shared memory starts GPMPC_SS_OFFSET = 1 KB into the CTA's window (the first KB is reserved by the system)
+// and, in a thread-block cluster, the window of CTA rank r starts at r << 24; with both known a lookup is
+//   SHL (n << 3), LOP3 ((. & mask) | rank bits), LDS.64 [R + 0x400]
+// -- two integer instructions per exp instead of three with a run-time table base (the sweeps are issue-bound, every
+// instruction counts: profiles/r02_micro_gen_loop.txt).  exp2s_fill checks the assumed offset at kernel start (trap).
+#define GPMPC_SS_OFFSET 1024
+struct __align__(16) GpmpcStaticSmem {
+  double tab[EXP2S_N];      // 2^(j/2048), pre-biased (gpmpc_api.cu)
+  double one;               // the constant 1.0 (rollout_kernel: stride-0 factor of the moment sums)
+  int next;                 // hand-over slot of the dynamic candidate queue
+  int pad;
+  unsigned char owner[GPMPC_MAX_PAIRS + 4];   // cluster rank that sweeps pair pr (rollout_kernel)
+};
+__shared__ GpmpcStaticSmem gpmpc_ss;
+__device__ __forceinline__ void exp2s_fill(const double* __restrict__ tab_global, int tid, int nthreads) {   // + __syncthreads()
+  if (tid == 0 && ((unsigned)__cvta_generic_to_shared(&gpmpc_ss) & 0xffffffu) != GPMPC_SS_OFFSET) __trap();   // see exp2s_entry
+  for (int i = tid; i < EXP2S_N; i += nthreads) gpmpc_ss.tab[i] = tab_global[i];
 }
 __device__ __forceinline__ double exp2s_clamp(double t2) {
   const unsigned h = min((unsigned)__double2hiint(t2), GPMPC_EXP2S_HI_MIN);
@@ -48,19 +59,21 @@ __device__ __forceinline__ double exp2s_clamp(double t2) {
 // The table is stored PRE-BIASED: entry j holds the bit pattern of 2^(j/2048) with (j << 9) subtracted from its high
 // word (gpmpc_api.cu).  Adding (n << 9) = ((n >> 11) << 20) + ((n & 2047) << 9) to the high word of entry n & 2047 then
 // restores the mantissa AND applies 2^(n >> 11) through the exponent field in ONE integer instruction (no masks).
-__device__ __forceinline__ double exp2s_entry(unsigned tab_s, int n) {   // 2^(n / 2048)
-  const double raw = exp2s_lds(tab_s + ((n << 3) & (8 * EXP2S_N - 8)));
+__device__ __forceinline__ double exp2s_entry(int n) {   // 2^(n / 2048)
+  const unsigned rank_bits = (unsigned)__cvta_generic_to_shared(&gpmpc_ss) - GPMPC_SS_OFFSET;   // loop invariant (r << 24)
+  double raw;
+  asm("ld.shared.f64 %0, [%1 + 1024];" : "=d"(raw) : "r"(((n << 3) & (8 * EXP2S_N - 8)) | rank_bits));
   return __hiloint2double(__double2hiint(raw) + (n << (20 - EXP2S_LOG)), __double2loint(raw));
 }
 
-__device__ __forceinline__ double exp2s(double t2, unsigned tab_s) {
+__device__ __forceinline__ double exp2s(double t2) {
   const double SHIFT = 6755399441055744.0;
   t2 = exp2s_clamp(t2);
   double kd = t2 + SHIFT;
   const int n = __double2loint(kd);
   kd -= SHIFT;
   const double f = t2 - kd;
-  const double t = exp2s_entry(tab_s, n);
+  const double t = exp2s_entry(n);
   double p = __fma_rn(GPMPC_EXP2S_C3, f, GPMPC_EXP2S_C2);
   p = __fma_rn(p, f, GPMPC_EXP2S_C1);
   p *= f;
@@ -68,7 +81,7 @@ __device__ __forceinline__ double exp2s(double t2, unsigned tab_s) {
 }
 
 // Four at once, stage by stage (4 independent float64 operations per stage).
-__device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4], unsigned tab_s) {
+__device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4]) {
   const double SHIFT = 6755399441055744.0;
   double x[4], kd[4], f[4], p[4], t[4];
   int n[4];
@@ -79,7 +92,35 @@ __device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4
 #pragma unroll
   for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }   // (an I2F.F64 instead of this add is slower)
 #pragma unroll
-  for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_entry(tab_s, n[c]); }
+  for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_entry(n[c]); }
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = __fma_rn(GPMPC_EXP2S_C3, f[c], GPMPC_EXP2S_C2);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] = __fma_rn(p[c], f[c], GPMPC_EXP2S_C1);
+#pragma unroll
+  for (int c = 0; c < 4; c++) p[c] *= f[c];
+#pragma unroll
+  for (int c = 0; c < 4; c++) res[c] = __fma_rn(t[c], p[c], t[c]);
+}
+
+// exp2s_x4 with a SIGN per pair of results: res[0], res[1] = +-exp(xin[0]), +-exp(xin[1]) (sign a), res[2], res[3] (sign b).
+// The sign costs nothing per element: the caller passes the magic constant of the range reduction as
+//   sh = SHIFT + (negative ? 2^22 : 0)      (exp2s_shift: high word 0x43380000, low word 0 or 0x400000)
+// so that n = lo(x + sh) carries bit 22; the table index (n & 2047) ignores it, and in the one integer add that applies
+// 2^(n >> 11) to the table entry, (n << 9) moves it to bit 31 -- the sign bit of the result.  x itself is not touched.
+__device__ __forceinline__ double exp2s_shift(int lo_word) { return __hiloint2double(0x43380000, lo_word); }
+#define GPMPC_EXP2S_NEG_LO 0x00400000
+__device__ __forceinline__ void exp2s_x4_signed(const double (&xin)[4], double (&res)[4], double sha, double shb) {
+  double x[4], kd[4], f[4], p[4], t[4];
+  int n[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) x[c] = exp2s_clamp(xin[c]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) kd[c] = x[c] + (c < 2 ? sha : shb);
+#pragma unroll
+  for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= (c < 2 ? sha : shb); }
+#pragma unroll
+  for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_entry(n[c]); }
 #pragma unroll
   for (int c = 0; c < 4; c++) p[c] = __fma_rn(GPMPC_EXP2S_C3, f[c], GPMPC_EXP2S_C2);
 #pragma unroll

@@ -1,7 +1,7 @@
 // Instantiation unit: rollout / reverse-sweep kernels for EV = 7.
 #include "gpmpc_uniform_impl.cuh"
 namespace gpmpc {
-template cudaError_t launch_rollout_inst<7>(bool, const RolloutParams&, int, size_t, cudaStream_t);
+template cudaError_t launch_rollout_inst<7>(bool, const RolloutParams&, int, int, size_t, cudaStream_t);
 template cudaError_t launch_backward_inst<7>(const BackwardParams&, cudaStream_t);
 template cudaError_t launch_uniform_inst<7>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t);
 }  // namespace gpmpc

@@ -35,6 +35,7 @@ struct RolloutParams {
   double* stepM; double* stepS; double* stepV;   // mode 1 outputs (may be NULL)
   double* records;     // (B, H, rec.size) gradient-mode records (NULL in value mode)
   double* ws_kk;       // (gridDim.x, E, NP) per-CTA scratch
+  double* ws_gam;      // general kernel, gradient mode: (gridDim.x, group, NP) column sums of the sweeps (RED at L2)
   // ---- launch geometry
   int group;           // pairs per N^2 phase
   int seg;             // columns per work item
@@ -59,9 +60,15 @@ struct BackwardParams {
   double* grad;        // (B, H*Na)
 };
 
-size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na);
-int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, size_t smem_limit);
-cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st);
+size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na, int nwarps);
+int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, int nwarps, size_t smem_limit);
+cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, int threads, size_t smem, cudaStream_t st);
+// Launch bounds of rollout_kernel<EV, .> = threads per SM of its launch plans: state dimensions <= 5 are built for 384
+// threads (<= 168 registers: two CTAs of 192 threads, or one of 384), larger ones for 256 threads (full register file).
+#ifndef GEN_MAXT
+#define GEN_MAXT(EV) ((EV) <= 5 ? 384 : 256)
+#endif
+inline int rollout_max_threads(int EV) { return GEN_MAXT(EV); }
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
 size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat);
 cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
@@ -76,7 +83,8 @@ cudaError_t launch_mll(const double* x, const double* y, const double* ls, const
                        cudaStream_t st, long long* launches);
 cudaError_t launch_il2(const double* ls, double* il2, int n, cudaStream_t st);
 
-constexpr int ROLLOUT_THREADS = 512;
+// static shared memory of the rollout kernels: the 16 KB table of exp2s (gpmpc_common.cuh) + a few scalars
+constexpr size_t GPMPC_STATIC_SMEM = 16 * 1024 + 128;   // sizeof(GpmpcStaticSmem) rounded up
 constexpr int UNIFORM_MAX_THREADS = 256;   // uniform kernels: __launch_bounds__(256, 2) -> <= 128 registers
 
 }  // namespace gpmpc

@@ -5,41 +5,41 @@
 
 namespace gpmpc {
 
-size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na) {
-  SmemLayout L = make_layout(EV, grad, NP, DP, D, E, group, H, Na);
+size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na, int nwarps) {
+  SmemLayout L = make_layout(EV, grad, NP, DP, D, E, group, H, Na, nwarps);
   return (size_t)L.total * sizeof(double);
 }
 
-int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, size_t smem_limit) {
+int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, int nwarps, size_t smem_limit) {
   const int P = E * (E + 1) / 2;
   int best = 0;
   for (int g = 1; g <= P; g++) {
-    if (rollout_smem_bytes(EV, grad, NP, DP, D, E, g, H, Na) <= smem_limit) best = g;
+    if (rollout_smem_bytes(EV, grad, NP, DP, D, E, g, H, Na, nwarps) <= smem_limit) best = g;
   }
   return best;
 }
 
 
 template <int EV> cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
-template <int EV> cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st);
+template <int EV> cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, int threads, size_t smem, cudaStream_t st);
 template <int E> cudaError_t launch_backward_inst(const BackwardParams& p, cudaStream_t st);
 #define GPMPC_DECL(n)                                                                                             \
-  extern template cudaError_t launch_rollout_inst<n>(bool, const RolloutParams&, int, size_t, cudaStream_t);      \
+  extern template cudaError_t launch_rollout_inst<n>(bool, const RolloutParams&, int, int, size_t, cudaStream_t);      \
   extern template cudaError_t launch_backward_inst<n>(const BackwardParams&, cudaStream_t);                       \
   extern template cudaError_t launch_uniform_inst<n>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t);
 GPMPC_DECL(1) GPMPC_DECL(2) GPMPC_DECL(3) GPMPC_DECL(4) GPMPC_DECL(5) GPMPC_DECL(6) GPMPC_DECL(7) GPMPC_DECL(8)
 #undef GPMPC_DECL
 
-cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, int threads, size_t smem, cudaStream_t st) {
   switch (EV) {
-    case 1: return launch_rollout_inst<1>(grad, p, grid, smem, st);
-    case 2: return launch_rollout_inst<2>(grad, p, grid, smem, st);
-    case 3: return launch_rollout_inst<3>(grad, p, grid, smem, st);
-    case 4: return launch_rollout_inst<4>(grad, p, grid, smem, st);
-    case 5: return launch_rollout_inst<5>(grad, p, grid, smem, st);
-    case 6: return launch_rollout_inst<6>(grad, p, grid, smem, st);
-    case 7: return launch_rollout_inst<7>(grad, p, grid, smem, st);
-    case 8: return launch_rollout_inst<8>(grad, p, grid, smem, st);
+    case 1: return launch_rollout_inst<1>(grad, p, grid, threads, smem, st);
+    case 2: return launch_rollout_inst<2>(grad, p, grid, threads, smem, st);
+    case 3: return launch_rollout_inst<3>(grad, p, grid, threads, smem, st);
+    case 4: return launch_rollout_inst<4>(grad, p, grid, threads, smem, st);
+    case 5: return launch_rollout_inst<5>(grad, p, grid, threads, smem, st);
+    case 6: return launch_rollout_inst<6>(grad, p, grid, threads, smem, st);
+    case 7: return launch_rollout_inst<7>(grad, p, grid, threads, smem, st);
+    case 8: return launch_rollout_inst<8>(grad, p, grid, threads, smem, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -136,6 +136,31 @@ __device__ __forceinline__ double col_reduce8(const double (&v)[8], int lane, in
   return c;
 }
 
+// The same column sums through a per-warp shared-memory scratch (COLRED_WARP doubles): every lane stores its 8 values
+// (rows of 80 bytes: conflict-free 16-byte stores), lane (g, c) = (lane >> 3, lane & 7) adds column c of source lanes
+// 8 g .. 8 g + 7 (the groups of a half-warp read rows 12 apart: conflict-free), two shuffle rounds finish.  30 instructions
+// instead of the ~105 of the transpose-reduce (18 SHFL + 28 FSEL + moves): the sweeps are issue-bound, every instruction
+// counts (profiles/r02_micro_gen_loop.txt).  On return every lane holds the total of column lane & 7.
+constexpr int COLRED_STRIDE = 10;
+constexpr int COLRED_WARP = 32 * COLRED_STRIDE;
+__device__ __forceinline__ double col_reduce8s(const double (&v)[8], int lane, double* __restrict__ scr) {
+  double2* w = reinterpret_cast<double2*>(scr + lane * COLRED_STRIDE);
+#pragma unroll
+  for (int q = 0; q < 4; q++) w[q] = make_double2(v[2 * q], v[2 * q + 1]);
+  __syncwarp();
+  const int c = lane & 7, g = lane >> 3;
+  const double* ra = scr + (8 * g + 4 * (g & 1)) * COLRED_STRIDE + c;
+  const double* rb = scr + (8 * g + 4 - 4 * (g & 1)) * COLRED_STRIDE + c;
+  double s0 = ra[0] + ra[COLRED_STRIDE], s1 = ra[2 * COLRED_STRIDE] + ra[3 * COLRED_STRIDE];
+  s0 += rb[0] + rb[COLRED_STRIDE];
+  s1 += rb[2 * COLRED_STRIDE] + rb[3 * COLRED_STRIDE];
+  double s = s0 + s1;
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  __syncwarp();   // the scratch is rewritten by the next round
+  return s;
+}
+
 // Sums of K2 (power of two, <= 32) per-lane values over the 32 lanes with K2 - 1 + log2(32 / K2) shuffles instead
 // of 5 K2 (halving exchange: at offset 16, 8, ... every lane keeps one half of its values and sends the other half).
 // On return value number `idx` is complete in every lane that shares `idx`; lanes with (lane & (32 / K2 - 1)) == 0
@@ -163,28 +188,201 @@ __device__ __forceinline__ double warp_reduce_multi(double (&v)[K2], int lane, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// The hot loop: one warp, rows {64 I + lane, 64 I + 32 + lane}, columns [jbeg, jend).
-//   t_ij = kap_i + kap_j + u_i . nu_j ;  w_ij = (beta_a,i beta_b,j - [a==b] iK_a,ij) exp(t_ij)
-// gp_model.py:161-175 (X, X2, Q, maha, k, L, beta L beta, iK * L) collapsed to one exponent.
-// Diagonal pairs (a == b) sweep only the tiles on or above the diagonal (diagonal tile: half weights); the caller doubles.
+// float64 reduction at L2 without a return value (RED.E.ADD.F64: fire and forget); float64 atomics on shared memory
+// are CAS spin loops, so sums that several warps contribute to per element leave the SM this way
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void uni_red_add(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+// Row factor of the sweeps: the per-row term kap_i of the exponent never enters the element loops,
+//   exp(kap_i + kap_j + u_i . nu_j) = e_i * exp(kap_j + u_i . nu_j) ,   e_i = exp(max(kap_i, kmin)),
+// and e_i multiplies the finished row sums (or is folded into the row's coefficients).  kr (table units) -> e, kr := the
+// residual shift kap_i - max(kap_i, kmin), non-zero only for rows far away from the input mean (their warps run the
+// loop variant with the extra add, SH).  kmin = -600 in natural units: with the total exponent bounded above by
+// log(s2_a s2_b) (+ log|beta|), the remaining factor cannot overflow.
+__device__ __forceinline__ double uni_row_factor(double& kr) {
+  const double c = fmax(kr, -600.0 * GPMPC_EXP2S_SCALE);   // NaN -> kmin, and the residual keeps the NaN
+  kr -= c;
+  return exp2s(c);
+}
+
+// Warp totals of PV "pair" values (k <= l, row-major) and up to GPMPC_MAX_D "single" values that every lane has summed
+// over its own rows / columns: halving exchanges, 16 values per round (16 shuffles instead of 80), then ONE shared-memory
+// atomicAdd per value and warp into acc[o]: o < D singles, o = D + pr pairs.  (A few hundred per step: the CAS loop of
+// the float64 shared atomic does not matter here, unlike per-element sums.)
+template <int PV>
+__device__ __forceinline__ void gen_warp_sums_add(const double (&vp)[PV], const double (&vs)[GPMPC_MAX_D], int D, int lane,
+                                                  double* __restrict__ acc) {
+  constexpr int NCH = (PV + GPMPC_MAX_D + 15) / 16;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) {
+    if (16 * ch < PV + D) {   // warp-uniform: rounds that hold only unused single slots are skipped
+      double v16[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int sl = 16 * ch + k;
+        v16[k] = (sl < PV) ? vp[sl < PV ? sl : 0] : ((sl - PV < GPMPC_MAX_D) ? vs[(sl - PV >= 0 && sl - PV < GPMPC_MAX_D) ? sl - PV : 0] : 0.0);
+      }
+      int idx;
+      const double tot = warp_reduce_multi<16>(v16, lane, idx);
+      const int sl = 16 * ch + idx;
+      if ((lane & 1) == 0) {
+        if (sl < PV) atomicAdd(acc + D + sl, tot);
+        else if (sl - PV < D) atomicAdd(acc + (sl - PV), tot);
+      }
+    }
+  }
+}
+
+// nu_j[0 .. EV) of one training point as 16-byte shared-memory loads (rows of s_nu start 16-byte aligned: DP is even)
+template <int EV>
+__device__ __forceinline__ void gen_load_nu(const double* __restrict__ row, double (&nu)[EV]) {
+  const double2* r2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+  for (int q = 0; q < (EV + 1) / 2; q++) {
+    const double2 v = r2[q];
+    nu[2 * q] = v.x;
+    if (2 * q + 1 < EV) nu[2 * q + 1] = v.y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The hot loop of the general path (per-GP hyper-parameters): one warp, one output pair (a, b), lane = two ADJACENT rows
+// i0 = 64 I + 2 lane, i0 + 1, columns [jbeg, jend) two at a time (4 independent chains per warp).
+//   t_ij = kap_i + kap_j + u_i . nu_j ;  w_ij = (beta_a,i beta_b,j - [a==b] iK_a,ij) exp(t_ij)
+// gp_model.py:161-175 (X, X2, Q, maha, k, L, beta L beta, iK * L) collapsed to one exponent per element.
+//  * row factor e_i = exp(kap_i) outside the loop (uni_row_factor);
+//  * off-diagonal pairs: log|beta_b,j| is part of the column term kap'_j and the sign of beta_b,j rides in its lowest
+//    mantissa bit (one integer XOR on the result), so the element costs no multiplication by the coefficient:
+//    rho'_i = sum_j +-exp(kap'_j + u_i . nu_j), xi'_i likewise, and the row factor be_i = beta_a,i e_i multiplies the
+//    finished sums;  E + 7 + 1 float64 instructions per element (value), + E + 1.6 with the gradient sums;
+//  * diagonal pairs: c_ij = be_i beta_j - e_i iK_ij (both iK values of a column with one 16-byte load), upper tile
+//    triangle only, the diagonal tile in full with HALF weights (w is symmetric and every consumer of (rho, gam, xi) is
+//    invariant under that swap, see uni_bwd_item) -- no element masks;
+//  * gradient sums: rows rho_i, xi_i = sum_j w_ij nu_j stay in registers (folded into the pair's accumulators by
+//    gen_item); column sums gam_j by an 8-column transpose-reduce and a float64 RED at L2 (per-CTA scratch).
+// ---------------------------------------------------------------------------------------------
+#ifndef GEN_IK_PREFETCH
+#define GEN_IK_PREFETCH 1
+#endif
+template <int EV, bool GRAD, bool DIAG, bool SH>
+__device__ __forceinline__ void gen_cols(const double* __restrict__ s_nu, int DP, const double* __restrict__ s_kp,
+                                         const double* __restrict__ beta_b, const double* __restrict__ ik0, int NP,
+                                         int jbeg, int jend, const double (&u0)[EV], const double (&u1)[EV],
+                                         double kr0, double kr1, double cb0, double cb1, double ce0, double ce1,
+                                         double& rho0, double& rho1, double (&xi0)[EV], double (&xi1)[EV], int lane,
+                                         double* __restrict__ g_gam, double* __restrict__ scr) {
+  const double* __restrict__ pn = s_nu + (size_t)jbeg * DP;
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    double v[8];
+#if GEN_IK_PREFETCH
+    // diagonal pairs: the iK rows of the NEXT round of 8 columns -> L1 (they come from L2, ~700 clocks away, and the three
+    // warps of a sub-partition cannot hide that: a diagonal chunk took 1.42x an off-diagonal one instead of the 1.19x of
+    // its instruction count)
+    if (DIAG && j0 + 8 < jend) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) asm volatile("prefetch.global.L1 [%0];" ::"l"(ik0 + (size_t)(8 + q) * NP));
+    }
+#endif
+#pragma unroll
+    for (int jp = 0; jp < 4; jp++) {
+      const int j = j0 + 2 * jp;
+      double na[EV], nb[EV];
+      gen_load_nu<EV>(pn, na);
+      gen_load_nu<EV>(pn + DP, nb);
+      pn += 2 * DP;
+      // column record {kap'_j, magic constant of the exp's range reduction carrying the sign of beta_b,j}
+      const double2 ca = *reinterpret_cast<const double2*>(s_kp + 2 * j);
+      const double2 cb = *reinterpret_cast<const double2*>(s_kp + 2 * j + 2);
+      double t[4], w[4];
+      if (SH) { t[0] = kr0 + ca.x; t[1] = kr1 + ca.x; t[2] = kr0 + cb.x; t[3] = kr1 + cb.x; }
+      else { t[0] = ca.x; t[1] = ca.x; t[2] = cb.x; t[3] = cb.x; }
+      // serpentine order: every FMA shares one register operand with its predecessor (operand-reuse cache; a DFMA with
+      // three fresh register operands issues at 2/3 rate on B200, tools/micro/dfma_operands.cu)
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+        t[0] = fma(u0[e], na[e], t[0]);
+        t[1] = fma(u1[e], na[e], t[1]);
+        t[3] = fma(u1[e], nb[e], t[3]);
+        t[2] = fma(u0[e], nb[e], t[2]);
+      }
+      if (DIAG) {
+        exp2s_x4(t, w);
+      } else {   // sign of beta_b,j through the magic constant of the range reduction (exp2s_x4_signed): no per-element cost
+        exp2s_x4_signed(t, w, ca.y, cb.y);
+      }
+      if (DIAG) {
+        const double2 bb2 = __ldg(reinterpret_cast<const double2*>(beta_b + j));
+        const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
+        const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
+        ik0 += 2 * (size_t)NP;
+        double c[4] = {-ce0 * ika.x, -ce1 * ika.y, -ce0 * ikb.x, -ce1 * ikb.y};
+        c[0] = fma(cb0, bb2.x, c[0]);
+        c[1] = fma(cb1, bb2.x, c[1]);
+        c[3] = fma(cb1, bb2.y, c[3]);
+        c[2] = fma(cb0, bb2.y, c[2]);
+        if (GRAD) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) w[q] *= c[q];
+          rho0 += w[0] + w[2];
+          rho1 += w[1] + w[3];
+        } else {
+          rho0 = fma(c[0], w[0], rho0);
+          rho1 = fma(c[1], w[1], rho1);
+          rho0 = fma(c[2], w[2], rho0);
+          rho1 = fma(c[3], w[3], rho1);
+        }
+      } else {
+        rho0 += w[0] + w[2];
+        rho1 += w[1] + w[3];
+      }
+      if (GRAD) {
+#pragma unroll
+        for (int e = 0; e < EV; e++) {
+          if (e & 1) { xi1[e] = fma(w[1], na[e], xi1[e]); xi0[e] = fma(w[0], na[e], xi0[e]); }
+          else       { xi0[e] = fma(w[0], na[e], xi0[e]); xi1[e] = fma(w[1], na[e], xi1[e]); }
+        }
+#pragma unroll
+        for (int e = 0; e < EV; e++) {
+          if (e & 1) { xi1[e] = fma(w[3], nb[e], xi1[e]); xi0[e] = fma(w[2], nb[e], xi0[e]); }
+          else       { xi0[e] = fma(w[2], nb[e], xi0[e]); xi1[e] = fma(w[3], nb[e], xi1[e]); }
+        }
+        if (DIAG) { v[2 * jp] = w[0] + w[1]; v[2 * jp + 1] = w[2] + w[3]; }
+        else { v[2 * jp] = fma(cb0, w[0], cb1 * w[1]); v[2 * jp + 1] = fma(cb0, w[2], cb1 * w[3]); }
+      }
+    }
+    if (GRAD) {
+      const double tot = col_reduce8s(v, lane, scr);
+      if (lane < 8) uni_red_add(g_gam + j0 + lane, tot);
+    }
+  }
+}
+
+// One run of columns [jbeg, jend) (multiples of 8; diagonal pairs: jbeg >= 64 I) of row block I of pair (a, b): row
+// set-up, the column loops, and -- everything downstream being linear in (rho_i, xi_i) -- the fold of the lane's
+// partial row sums straight into the pair's accumulators  acc[0] = S_raw, acc[1 .. 1+D) = dS/dm (rho part),
+// acc[1+D ..) = upper triangle of dS/dQ (rho and xi parts); the gam parts follow after the sweep (rollout_kernel).
 template <int EV, bool GRAD, bool DIAG>
-__device__ __forceinline__ void pair_item(const RolloutParams& p, const double* __restrict__ s_nu,
-                                          const double* __restrict__ s_kapj, const double* __restrict__ Qm,
-                                          const double* __restrict__ il2a, const double* __restrict__ il2b,
-                                          const double* __restrict__ kka, const double* __restrict__ beta_a,
-                                          const double* __restrict__ beta_b, const double* __restrict__ iKa,
-                                          int I, int jbeg, int jend, int lane, double* s_gam, double* s_rho,
-                                          double* s_xi, double* s_acc, unsigned s_tab) {
-  const int NP = p.NP, DP = p.DP;
-  const int i0 = 64 * I + lane, i1 = i0 + 32;
+__device__ __forceinline__ void gen_item(const RolloutParams& p, const double* __restrict__ s_nu,
+                                         const double* __restrict__ s_kp, const double* __restrict__ Qm,
+                                         const double* __restrict__ il2a, const double* __restrict__ il2b,
+                                         const double* __restrict__ kka, const double* __restrict__ beta_a,
+                                         const double* __restrict__ beta_b, const double* __restrict__ iKa, int I,
+                                         int jbeg, int jend, int lane, double* __restrict__ g_gam,
+                                         double* __restrict__ acc, double* __restrict__ scr) {
+  constexpr int PV = EV * (EV + 1) / 2;
+  const int NP = p.NP, DP = p.DP, D = p.D;
+  const int i0 = 64 * I + 2 * lane, i1 = i0 + 1;
+  const double* __restrict__ n0p = s_nu + (size_t)i0 * DP;
+  const double* __restrict__ n1p = n0p + DP;
   double u0[EV], u1[EV], kr0, kr1;
   {
     double z0[EV], z1[EV];
 #pragma unroll
     for (int e = 0; e < EV; e++) {
-      z0[e] = s_nu[i0 * DP + e] * il2a[e];
-      z1[e] = s_nu[i1 * DP + e] * il2a[e];
+      z0[e] = n0p[e] * il2a[e];
+      z1[e] = n1p[e] * il2a[e];
     }
     kr0 = kka[i0];
     kr1 = kka[i1];
@@ -198,95 +396,96 @@ __device__ __forceinline__ void pair_item(const RolloutParams& p, const double* 
       }
       kr0 = fma(z0[e], q0, kr0);
       kr1 = fma(z1[e], q1, kr1);
-      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2b[e];   // exponent in table units (exp2s; s_kapj is scaled too)
+      u0[e] = (2.0 * GPMPC_EXP2S_SCALE) * q0 * il2b[e];   // exponent in table units (exp2s; s_kp is scaled too)
       u1[e] = (2.0 * GPMPC_EXP2S_SCALE) * q1 * il2b[e];
     }
     kr0 *= GPMPC_EXP2S_SCALE;
     kr1 *= GPMPC_EXP2S_SCALE;
   }
-  const double bi0 = __ldg(beta_a + i0), bi1 = __ldg(beta_a + i1);
-  double rho0 = 0.0, rho1 = 0.0;
-  double xi0[EV], xi1[EV];
+  const double e0 = uni_row_factor(kr0), e1 = uni_row_factor(kr1);   // kr0, kr1 become residual shifts
+  const bool far = __any_sync(0xffffffffu, kr0 != 0.0 || kr1 != 0.0);
+  const double be0 = __ldg(beta_a + i0) * e0, be1 = __ldg(beta_a + i1) * e1;
+  double rho0 = 0.0, rho1 = 0.0, xi0[EV], xi1[EV];
 #pragma unroll
   for (int e = 0; e < EV; e++) { xi0[e] = 0.0; xi1[e] = 0.0; }
-
-  for (int j0 = jbeg; j0 < jend; j0 += 8) {
-    // diagonal pairs: the diagonal tile is swept in full with HALF weights instead of its upper triangle -- w is symmetric
-    // and every consumer of (rho, gam, xi) is invariant under that swap (see uni_bwd_item), so no element masks
-    const double wgt = (DIAG && j0 < 64 * I + 64) ? 0.5 : 1.0;
-    double v[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int j = j0 + jj;
-      double nj[EV];
-#pragma unroll
-      for (int e = 0; e < EV; e++) nj[e] = s_nu[j * DP + e];
-      const double kj = s_kapj[j];
-      const double bj = __ldg(beta_b + j);
-      double c0, c1;
-      if (DIAG) {
-        c0 = fma(bi0, bj, -__ldg(iKa + (size_t)j * NP + i0));
-        c1 = fma(bi1, bj, -__ldg(iKa + (size_t)j * NP + i1));
-      } else {
-        c0 = bi0 * bj;
-        c1 = bi1 * bj;
-      }
-      double t0 = kr0 + kj, t1 = kr1 + kj;
-#pragma unroll
-      for (int e = 0; e < EV; e++) {
-        t0 = fma(u0[e], nj[e], t0);
-        t1 = fma(u1[e], nj[e], t1);
-      }
-      if (DIAG) { c0 *= wgt; c1 *= wgt; }
-      double w0 = c0 * exp2s(t0, s_tab);
-      double w1 = c1 * exp2s(t1, s_tab);
-      rho0 += w0;
-      rho1 += w1;
-      if (GRAD) {
-#pragma unroll
-        for (int e = 0; e < EV; e++) {
-          xi0[e] = fma(w0, nj[e], xi0[e]);
-          xi1[e] = fma(w1, nj[e], xi1[e]);
-        }
-        v[jj] = w0 + w1;
-      }
-    }
-    if (GRAD) {
-      int col;
-      double tot = col_reduce8(v, lane, col);
-      if ((lane & 3) == 0) atomicAdd(s_gam + j0 + col, tot);
-    }
-  }
-  if (GRAD) {
-    atomicAdd(s_rho + i0, rho0);
-    atomicAdd(s_rho + i1, rho1);
-#pragma unroll
-    for (int e = 0; e < EV; e++) {
-      atomicAdd(s_xi + i0 * EV + e, xi0[e]);
-      atomicAdd(s_xi + i1 * EV + e, xi1[e]);
+  jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns contribute (numerically) nothing: skip them
+  if (DIAG) {
+    // two column segments: the diagonal tile (half weights) and the tiles above it; ONE inlined instance of the loops
+    // (the sweeps' code has to stay resident in the instruction caches of all warps, whatever variant they run)
+    const int jd1 = 64 * I + 64;
+#pragma unroll 1
+    for (int seg = 0; seg < 2; seg++) {
+      const int jb = seg == 0 ? jbeg : max(jbeg, jd1), je = seg == 0 ? min(jend, jd1) : jend;
+      if (jb >= je) continue;
+      const double wg = seg == 0 ? 0.5 : 1.0;
+      const double* ikp = iKa + (size_t)jb * NP + i0;   // row j of the symmetric iK, lane = columns i0, i0 + 1
+      if (far) gen_cols<EV, GRAD, true, true>(s_nu, DP, s_kp, beta_b, ikp, NP, jb, je, u0, u1, kr0, kr1, wg * be0, wg * be1,
+                                              wg * e0, wg * e1, rho0, rho1, xi0, xi1, lane, g_gam, scr);
+      else gen_cols<EV, GRAD, true, false>(s_nu, DP, s_kp, beta_b, ikp, NP, jb, je, u0, u1, kr0, kr1, wg * be0, wg * be1,
+                                           wg * e0, wg * e1, rho0, rho1, xi0, xi1, lane, g_gam, scr);
     }
   } else {
-    double tot = warp_sum(rho0 + rho1);
-    if (lane == 0) atomicAdd(s_acc, tot);
+    if (far) gen_cols<EV, GRAD, false, true>(s_nu, DP, s_kp, nullptr, nullptr, NP, jbeg, jend, u0, u1, kr0, kr1, be0, be1, 0.0, 0.0,
+                                             rho0, rho1, xi0, xi1, lane, g_gam, scr);
+    else gen_cols<EV, GRAD, false, false>(s_nu, DP, s_kp, nullptr, nullptr, NP, jbeg, jend, u0, u1, kr0, kr1, be0, be1, 0.0, 0.0,
+                                          rho0, rho1, xi0, xi1, lane, g_gam, scr);
+    rho0 *= be0;
+    rho1 *= be1;
+    if (GRAD) {
+#pragma unroll
+      for (int e = 0; e < EV; e++) { xi0[e] *= be0; xi1[e] *= be1; }
+    }
+  }
+  {
+    const double tot = warp_sum(rho0 + rho1);
+    if (lane == 0) atomicAdd(acc, tot);
+  }
+  if (GRAD) {
+    double vs[GPMPC_MAX_D], vp[PV];
+#pragma unroll
+    for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = (d < D) ? (rho0 * n0p[d < D ? d : 0] + rho1 * n1p[d < D ? d : 0]) * il2a[d < D ? d : 0] : 0.0;
+    double za0[EV], za1[EV], xs0[EV], xs1[EV];
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      za0[e] = n0p[e] * il2a[e];
+      za1[e] = n1p[e] * il2a[e];
+      xs0[e] = xi0[e] * il2b[e];
+      xs1[e] = xi1[e] * il2b[e];
+    }
+    int pr = 0;
+#pragma unroll
+    for (int k = 0; k < EV; k++) {
+      const double rk0 = rho0 * za0[k], rk1 = rho1 * za1[k];
+#pragma unroll
+      for (int l = k; l < EV; l++) {
+        double a0 = fma(rk0, za0[l], za0[k] * xs0[l]);
+        a0 = fma(za0[l], xs0[k], a0);
+        double a1 = fma(rk1, za1[l], za1[k] * xs1[l]);
+        a1 = fma(za1[l], xs1[k], a1);
+        vp[pr++] = a0 + a1;
+      }
+    }
+    gen_warp_sums_add<PV>(vp, vs, D, lane, acc + 1);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
+// Launch plans (host: gpmpc_api.cu; GEN_MAXT in gpmpc_internal.h): state dimensions <= 5: 384 threads per SM with <= 168 registers
+// -- two CTAs of 192 threads when the shared memory allows two per SM (one CTA's serial phases then overlap the other's
+// sweep), else one of 384; larger state dimensions: one CTA of 256 threads with the full register file.
 template <int EV, bool GRAD>
-__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const RolloutParams p) {
+__global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutParams p) {
   extern __shared__ __align__(16) double sm[];
-  const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x, warp = tid >> 5, nwarps = NT >> 5;
   const int E = p.E, D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
   const int P = E * (E + 1) / 2, G = p.group;
-  const SmemLayout L = make_layout(EV, GRAD, NP, DP, D, E, G, (p.mode == 0) ? H : 0, Na);
+  const SmemLayout L = make_layout(EV, GRAD, NP, DP, D, E, G, (p.mode == 0) ? H : 0, Na, nwarps);
   double* s_nu = sm + L.nu;
   double* s_lb = sm + L.grp;  // aliases the group arrays (only live in P1/P2)
   double* s_kap = sm + L.kap;
-  double* s_gam = sm + L.gam;
-  double* s_rho = sm + L.rho;
-  double* s_xi = sm + L.xi;
+  double* s_colred = sm + L.colred + warp * COLRED_WARP;   // this warp's scratch of the column-sum reduction (gradient mode)
   double* s_out = sm + L.out;
   double* s_m = sm + L.m;
   double* s_s = sm + L.s;
@@ -307,8 +506,6 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   double* s_r = sm + L.r;
   double* s_rv = sm + L.rv;
   int* s_int = reinterpret_cast<int*>(sm + L.ints);  // [0] counter, [1] bad flag, [2..] pair table
-  double* s_tabp = sm + L.tab;
-  const unsigned s_tab = exp2s_table_addr(s_tabp);
   const int nOut = L.nOut, PV = L.PV;
   const RecLayout RL = rec_layout(E, D);
   // cost description staged in shared memory (the stage cost is on the serial path of every step)
@@ -324,7 +521,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   // ---- candidate-independent constants
   for (int o = tid; o < E * D; o += NT) s_il2[o] = p.il2[o];
   if (tid < E) { s_s2[tid] = p.s2[tid]; s_logs2[tid] = log(p.s2[tid]); }
-  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
+  exp2s_fill(p.exp2tab, tid, NT);
   if (tid == 0) {
     int pr = 0;
     for (int a = 0; a < E; a++)
@@ -337,6 +534,11 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
     s_Wd[o] = s_il2[(ab >> 4) * D + e] + s_il2[(ab & 15) * D + e];
   }
   double* kk = p.ws_kk + (size_t)blockIdx.x * E * NP;
+  // column sums gam_j of the sweeps (float64 RED at L2), one row per pair of the group; zero on entry and re-zeroed
+  // by their consumer after every step
+  double* g_gam = GRAD ? p.ws_gam + (size_t)blockIdx.x * G * NP : nullptr;
+  if (GRAD)
+    for (int o = tid; o < G * NP; o += NT) g_gam[o] = 0.0;
   __syncthreads();
 
   // candidates are drawn from a global counter when the host provides one (rollouts; SM speeds differ by up to ~25 %,
@@ -351,10 +553,10 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   int gstep = 0;
   long long clk_ = clock64();
 #define GEN_CLK(k) do { if (p.dbg_clk && blockIdx.x == 0 && tid == 0) { const long long c_ = clock64(); p.dbg_clk[k] += c_ - clk_; clk_ = c_; } } while (0)
-  __shared__ int s_next;
-  __shared__ double s_one;
+  int& s_next = gpmpc_ss.next;
+  double& s_one = gpmpc_ss.one;
   if (tid == 0) s_one = 1.0;
-  __shared__ unsigned char s_owner[GPMPC_MAX_EV * (GPMPC_MAX_EV + 1) / 2];   // cluster rank that sweeps pair pr
+  unsigned char* s_owner = gpmpc_ss.owner;   // cluster rank that sweeps pair pr
   if (tid == 0) {   // longest-processing-time deal: off-diagonal pairs sweep N^2 elements, diagonal ones half of that
     int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int pass = 0; pass < 2; pass++) {
@@ -441,7 +643,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
         pair_matrices<EV>(s_s, s_Wd + pr * EV, Rinv, Qm, detR);
         for (int e = 0; e < EV * EV; e++) s_Q[pr * EV * EV + e] = Qm[e];
         s_detR[pr] = detR;
-      } else if (tid == 128 && p.mode == 0) {   // stage cost of the current state (serial, overlaps the matrix work)
+      } else if (tid == 96 && p.mode == 0) {   // stage cost of the current state (serial, overlaps the matrix work)
         double cmu, cvar;
         stage_cost(cv, E, Na, s_mu, s_s, s_am + (t - 1) * Na, cmu, cvar);
         s_r[t - 1] = -cmu;
@@ -485,7 +687,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
             if (d < D) tail = fma(nu[d] * nu[d], la[d], tail);
           double lb = 0.0, kv = 0.0;
           if (i < N) {
-            lb = __ldg(p.beta + (size_t)a * NP + i) * exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab);
+            lb = __ldg(p.beta + (size_t)a * NP + i) * exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail));
             kv = s_logs2[a] - 0.5 * (head + tail);
           }
           s_lb[a * NP + i] = lb;
@@ -589,12 +791,16 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
       __syncthreads();
       GEN_CLK(4);
       // ================================================================ P3: O(P N^2) covariance sums
+      // Groups of G pairs (all of them when their column terms fit the shared memory).  Per group: column terms kap'_j
+      // per pair -> ONE sweep phase over the chunks of all its pairs (static weighted split into contiguous runs per warp)
+      // -> column-sum (gam) parts of the gradient -> per-pair finalisation.  Cluster mode: a CTA handles the pairs it owns.
       for (int g0 = 0; g0 < P; g0 += G) {
-        if (C > 1 && s_owner[g0] != crank) continue;    // another CTA of the cluster owns this pair (G == 1 in cluster mode)
         const int gn = min(G, P - g0);
         for (int o = tid; o < gn * NP; o += NT) {
           const int pl = o / NP, j = o - pl * NP;
-          const int pr = g0 + pl, b = s_int[2 + pr] & 15;
+          const int pr = g0 + pl;
+          if (C > 1 && s_owner[pr] != crank) continue;
+          const int ab = s_int[2 + pr], a = ab >> 4, b = ab & 15;
           double kap = 0.0;
           if (j < N) {
             const double* Qm = s_Q + pr * EV * EV;
@@ -610,101 +816,130 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
               kap = fma(z[e], r, kap);
             }
           }
-          s_kap[o] = GPMPC_EXP2S_SCALE * kap;
-          if (GRAD) {
-            s_gam[o] = 0.0;
-            s_rho[o] = 0.0;
-#pragma unroll
-            for (int e = 0; e < EV; e++) s_xi[(size_t)o * EV + e] = 0.0;
+          if (a != b) {
+            // off-diagonal pairs: the coefficient beta_b,j moves into the exponent (log|beta|) and its sign into the magic
+            // constant of the exp's range reduction (gen_cols, exp2s_x4_signed); padded columns get exp(-huge) = 0
+            const double bj = (j < N) ? __ldg(p.beta + (size_t)b * NP + j) : 0.0;
+            kap = (j < N) ? GPMPC_EXP2S_SCALE * (kap + log(fabs(bj))) : -1.0e300;
+            s_kap[2 * o + 1] = exp2s_shift(bj < 0.0 ? GPMPC_EXP2S_NEG_LO : 0);
+          } else {
+            kap *= GPMPC_EXP2S_SCALE;
           }
+          s_kap[2 * o] = kap;
         }
         for (int o = tid; o < gn * L.paccN; o += NT) s_pacc[o] = 0.0;
-        if (tid == 0) s_int[0] = 0;
         __syncthreads();
         GEN_CLK(5);
+        const long long sw0_ = p.dbg_clk ? clock64() : 0;
         {
-          const int nrb = NP / 64, nseg = (NP + p.seg - 1) / p.seg;
-          const int nitems = gn * nrb * nseg;
-          for (;;) {
-            int item = 0;
-            if (lane == 0) item = atomicAdd(&s_int[0], 1);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= nitems) break;
-            // longest row sweeps (small I) first within each pair
-            const int pl = item / (nrb * nseg);
-            const int rem = item - pl * nrb * nseg;
-            const int I = rem / nseg, js = rem - I * nseg;
-            const int pr = g0 + pl, ab = s_int[2 + pr], a = ab >> 4, b = ab & 15;
-            int jbeg = js * p.seg;
-            const int jend = min(NP, jbeg + p.seg);
-            const double* Qm = s_Q + pr * EV * EV;
-            if (a == b) {
-              if (jend <= 64 * I) continue;
-              jbeg = max(jbeg, 64 * I);
-              pair_item<EV, GRAD, true>(p, s_nu, s_kap + pl * NP, Qm, s_il2 + a * D, s_il2 + b * D, kk + a * NP,
-                                        p.beta + (size_t)a * NP, p.beta + (size_t)b * NP,
-                                        p.iK + (size_t)a * NP * NP, I, jbeg, jend, lane, s_gam + pl * NP,
-                                        s_rho + pl * NP, s_xi + (size_t)pl * NP * EV, s_pacc + pl * L.paccN, s_tab);
-            } else {
-              pair_item<EV, GRAD, false>(p, s_nu, s_kap + pl * NP, Qm, s_il2 + a * D, s_il2 + b * D, kk + a * NP,
-                                         p.beta + (size_t)a * NP, p.beta + (size_t)b * NP, nullptr, I, jbeg, jend,
-                                         lane, s_gam + pl * NP, s_rho + pl * NP, s_xi + (size_t)pl * NP * EV,
-                                         s_pacc + pl * L.paccN, s_tab);
+          // chunks of CH columns x 64 rows: an off-diagonal pair has nrb * (NP / CH) of them (row-major), a diagonal pair
+          // cpt (nrb - I) per row block I (upper tile triangle).  A diagonal chunk takes ~1.4x as long as an off-diagonal
+          // one (iK stream from L2 on top of 3 more float64 instructions per element; measured per warp,
+          // profiles/r02c_general_sweep_per_warp.txt), so the two kinds are split SEPARATELY: every warp gets an equal
+          // contiguous run of the diagonal pairs' chunks and one of the off-diagonal pairs' chunks -- balanced whatever the
+          // cost ratio; even warps start with their diagonal run, odd warps with the off-diagonal one (mixed L2 traffic).
+          const int CH = p.seg, nrb = NP / 64, cpr = NP / CH, cpt = 64 / CH;
+          const int nOff = nrb * cpr, nDia = cpt * nrb * (nrb + 1) / 2;
+#pragma unroll 1
+          for (int ph = 0; ph < 2; ph++) {
+            const bool dia = ((ph ^ warp) & 1) == 0;
+            const int n = dia ? nDia : nOff;
+            int cnt = 0;
+            for (int pl = 0; pl < gn; pl++) {
+              const int pr = g0 + pl, ab = s_int[2 + pr];
+              if (C > 1 && s_owner[pr] != crank) continue;
+              cnt += (((ab >> 4) == (ab & 15)) == dia) ? 1 : 0;
+            }
+            const int T = cnt * n;
+            const int clo = (int)((long long)T * warp / nwarps), chi = (int)((long long)T * (warp + 1) / nwarps);
+            int cw = 0;
+            for (int pl = 0; pl < gn; pl++) {
+              const int pr = g0 + pl, ab = s_int[2 + pr], a = ab >> 4, b = ab & 15;
+              if ((C > 1 && s_owner[pr] != crank) || ((a == b) != dia)) continue;
+              int c0 = max(clo, cw) - cw;
+              const int c1 = min(chi, cw + n) - cw;
+              cw += n;
+              if (c0 >= c1) continue;
+              const double* Qm = s_Q + pr * EV * EV;
+              if (dia) {
+                int I = 0, base = 0;
+                while (c0 < c1) {
+                  while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
+                  const int ce = min(c1, base + cpt * (nrb - I));
+                  gen_item<EV, GRAD, true>(p, s_nu, s_kap + 2 * pl * NP, Qm, s_il2 + a * D, s_il2 + b * D, kk + a * NP,
+                                           p.beta + (size_t)a * NP, p.beta + (size_t)b * NP, p.iK + (size_t)a * NP * NP, I,
+                                           64 * I + CH * (c0 - base), 64 * I + CH * (ce - base), lane, g_gam + pl * NP,
+                                           s_pacc + pl * L.paccN, s_colred);
+                  c0 = ce;
+                }
+              } else {
+                while (c0 < c1) {
+                  const int I = c0 / cpr, ce = min(c1, (I + 1) * cpr);
+                  gen_item<EV, GRAD, false>(p, s_nu, s_kap + 2 * pl * NP, Qm, s_il2 + a * D, s_il2 + b * D, kk + a * NP,
+                                            p.beta + (size_t)a * NP, p.beta + (size_t)b * NP, nullptr, I, CH * (c0 - I * cpr),
+                                            CH * (ce - I * cpr), lane, g_gam + pl * NP, s_pacc + pl * L.paccN, s_colred);
+                  c0 = ce;
+                }
+              }
             }
           }
         }
+        if (p.dbg_clk && blockIdx.x == 0 && lane == 0) p.dbg_clk[32 + warp] += clock64() - sw0_;   // tuning aid: this warp's share of the sweep
+        if (GRAD) __threadfence();   // the column sums are reductions at L2: make them visible before they are loaded below
         __syncthreads();
         GEN_CLK(6);
         if (GRAD) {
-          // reduce (rho, gam, xi) over the training points into S_raw, dS/dm (D), dS/dQ (EV x EV)
-          for (int pl = 0; pl < gn; pl++) {
+          // column-sum parts: S_raw += sum_j gam_j (diagonal pairs), dS/dm += sum_j gam_j lb nu_j, dS/dQ += sum_j gam_j zb zb^T
+          // (L2 loads: the sums were formed by reductions at L2; the scratch is re-zeroed for the next step)
+          // one warp per pair (round-robin), lanes over the training points: ONE warp-level reduction per pair
+          constexpr int PVc = EV * (EV + 1) / 2;
+          for (int pl = warp; pl < gn; pl += nwarps) {
             const int pr = g0 + pl, ab = s_int[2 + pr], a = ab >> 4, b = ab & 15;
-            const double* la = s_il2 + a * D;
+            if (C > 1 && s_owner[pr] != crank) continue;
             const double* lbv = s_il2 + b * D;
-            double accS = 0.0, gm[GPMPC_MAX_D], gQ[EV * EV];
+            double accG = 0.0, vs[GPMPC_MAX_D], vp[PVc];
 #pragma unroll
-            for (int d = 0; d < GPMPC_MAX_D; d++) gm[d] = 0.0;
+            for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = 0.0;
 #pragma unroll
-            for (int e = 0; e < EV * EV; e++) gQ[e] = 0.0;
-            for (int i = tid; i < N; i += NT) {
-              const double rho = s_rho[pl * NP + i], gam = s_gam[pl * NP + i];
-              accS += (a == b) ? (rho + gam) : rho;
-              double za[EV], zb[EV], xs[EV];
+            for (int e = 0; e < PVc; e++) vp[e] = 0.0;
+            double* gp = g_gam + pl * NP;
+            for (int j0 = lane; j0 < NP; j0 += 128) {
+              double gam4[4];
 #pragma unroll
-              for (int d = 0; d < GPMPC_MAX_D; d++)
-                if (d < D) {
-                  double nud = s_nu[i * DP + d];
-                  gm[d] = fma(rho * la[d] + gam * lbv[d], nud, gm[d]);
+              for (int q = 0; q < 4; q++) gam4[q] = (j0 + 32 * q < NP) ? __ldcg(gp + j0 + 32 * q) : 0.0;   // NP is a multiple of 64
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const int j = j0 + 32 * q;
+                if (j >= NP) continue;
+                gp[j] = 0.0;
+                const double gam = gam4[q];
+                accG += gam;
+                const double* nj = s_nu + j * DP;
+                double zb[EV];
+#pragma unroll
+                for (int d = 0; d < GPMPC_MAX_D; d++)
+                  if (d < D) vs[d] = fma(gam * lbv[d], nj[d], vs[d]);
+#pragma unroll
+                for (int e = 0; e < EV; e++) zb[e] = nj[e] * lbv[e];
+                int q2 = 0;
+#pragma unroll
+                for (int k = 0; k < EV; k++) {
+                  const double gk = gam * zb[k];
+#pragma unroll
+                  for (int l = k; l < EV; l++) { vp[q2] = fma(gk, zb[l], vp[q2]); q2++; }
                 }
-#pragma unroll
-              for (int e = 0; e < EV; e++) {
-                double nue = s_nu[i * DP + e];
-                za[e] = nue * la[e];
-                zb[e] = nue * lbv[e];
-                xs[e] = s_xi[((size_t)pl * NP + i) * EV + e] * lbv[e];
               }
-#pragma unroll
-              for (int e = 0; e < EV; e++)
-#pragma unroll
-                for (int f = 0; f < EV; f++)
-                  gQ[e * EV + f] += rho * za[e] * za[f] + gam * zb[e] * zb[f] + za[e] * xs[f] + za[f] * xs[e];
             }
-            accS = warp_sum(accS);
-            if (lane == 0) atomicAdd(s_pacc + pl * L.paccN, accS);
-            for (int d = 0; d < D; d++) {
-              double v = warp_sum(gm[d]);
-              if (lane == 0) atomicAdd(s_pacc + pl * L.paccN + 1 + d, v);
+            if (a == b) {
+              accG = warp_sum(accG);
+              if (lane == 0) atomicAdd(s_pacc + pl * L.paccN, accG);
             }
-#pragma unroll
-            for (int e = 0; e < EV * EV; e++) {
-              double v = warp_sum(gQ[e]);
-              if (lane == 0) atomicAdd(s_pacc + pl * L.paccN + 1 + D + e, v);
-            }
+            gen_warp_sums_add<PVc>(vp, vs, D, lane, s_pacc + pl * L.paccN + 1);
           }
           __syncthreads();
         }
         GEN_CLK(7);
-        if (tid < gn) {
+        if (tid < gn && (C == 1 || s_owner[g0 + tid] == crank)) {
           const int pl = tid, pr = g0 + pl, ab = s_int[2 + pr], a = ab >> 4, b = ab & 15;
           double* acc = s_pacc + pl * L.paccN;
           double Sr = acc[0];
@@ -726,7 +961,14 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
             rec[0] = Sr;
             rec[1] = s_detR[pr];
             for (int d = 0; d < D; d++) rec[2 + d] = acc[1 + d];
-            for (int e = 0; e < EV * EV; e++) rec[2 + D + e] = acc[1 + D + e];
+            int q = 0;                                   // dS/dQ is accumulated as its upper triangle (it is symmetric)
+            for (int k = 0; k < EV; k++)
+              for (int l = k; l < EV; l++) {
+                const double v = acc[1 + D + q];
+                q++;
+                rec[2 + D + k * EV + l] = v;
+                rec[2 + D + l * EV + k] = v;
+              }
           }
         }
         __syncthreads();
@@ -1057,11 +1299,11 @@ __global__ void __launch_bounds__(128) backward_kernel(const BackwardParams p) {
 // per-EV launchers; each gpmpc_inst_evN.cu instantiates one EV so that the build parallelises
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, int threads, size_t smem, cudaStream_t st) {
   cudaError_t e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(ROLLOUT_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

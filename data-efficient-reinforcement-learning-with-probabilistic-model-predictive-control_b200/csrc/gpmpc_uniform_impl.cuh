@@ -45,12 +45,16 @@ __device__ __forceinline__ int uni_next_candidate(const RolloutParams& p, int k,
 // sweep is split over all their warps, and the partial sums meet in L2 (float64 RED into a per-cluster accumulator,
 // rotating over three buffers so that zeroing never races with the next step) followed by ONE hardware cluster barrier
 // per horizon step.  Only the cluster's rank-0 CTA writes outputs.
-// float64 reduction at L2 without a return value (RED.E.ADD.F64: fire and forget)
-__device__ __forceinline__ void uni_red_add(double* addr, double v) {
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
-}
+// (uni_red_add, the float64 reduction at L2 without a return value, lives in gpmpc_rollout_impl.cuh)
 constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forward sweep (P + 1 <= 37 used)
 
+// column sums of the reverse sweep: 0 = shuffle transpose-reduce (col_reduce8), 1 = through a per-warp shared-memory
+// scratch (col_reduce8s).  The scratch version wins in the general kernel (3 warps per sub-partition, shared-memory pipe at
+// ~50 %) and loses here (27.5 -> 30.4 ms at B=2368: the records of this kernel already load the pipe, and the 20 KB of
+// scratch cost the precomputed per-step matrices their place): profiles/r02c_*.  NB: a -D must reach the host code too.
+#ifndef UNI_BWD_COLRED_SMEM
+#define UNI_BWD_COLRED_SMEM 0
+#endif
 #ifndef UNI_MINB
 #define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
 #endif
@@ -96,7 +100,7 @@ template <int EV, bool SH>
 __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const double* __restrict__ s_rec, int i0,
                                              int jbeg, int jend, const double (&u0)[EV], const double (&u1)[EV],
                                              double kr0, double kr1, double (&r0)[EV], double (&r1)[EV], double& trOut0,
-                                             double& trOut1, unsigned s_tab) {
+                                             double& trOut1) {
   constexpr int E = EV;
   const int NP = p.NP;
   const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;   // row j of the symmetric iK, lane = columns i0, i0 + 1
@@ -121,7 +125,7 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
       t[3] = fma(u1[e], nb[e], t[3]);
       t[2] = fma(u0[e], nb[e], t[2]);
     }
-    exp2s_x4(t, ex, s_tab);
+    exp2s_x4(t, ex);
 #pragma unroll
     for (int b = 0; b < E; b++) {
       if (b & 1) { r1[b] = fma(ex[1], ba[b], r1[b]); r0[b] = fma(ex[0], ba[b], r0[b]); }
@@ -141,19 +145,11 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
   trOut1 += tr2;
 }
 
-// Row factor of the sweeps (see uni_fwd_cols): kr (table units) -> e = exp(max(kr, kmin)), kr := residual shift.
-// kmin = -600 in natural units: with the total exponent <= 0, Eh' <= e^600 cannot overflow.
-__device__ __forceinline__ double uni_row_factor(double& kr, unsigned s_tab) {
-  const double c = fmax(kr, -600.0 * GPMPC_EXP2S_SCALE);   // NaN -> kmin, and the residual keeps the NaN
-  kr -= c;
-  return exp2s(c, s_tab);
-}
-
+// Row factor of the sweeps (see uni_fwd_cols): uni_row_factor in gpmpc_rollout_impl.cuh.
 template <int EV>
 __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const double* __restrict__ s_rec,
                                              const double* __restrict__ Qm, const double* __restrict__ il2, int I,
-                                             int jbeg, int jend, int lane, double* s_part,
-                                             unsigned s_tab) {
+                                             int jbeg, int jend, int lane, double* s_part) {
   constexpr int E = EV;
   const int i0 = 64 * I + 2 * lane, i1 = i0 + 1;   // adjacent rows: one 16-byte load fetches both iK values of a column
   double u0[EV], u1[EV], bi0[E], bi1[E], kr0, kr1;
@@ -183,17 +179,17 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   // columns are halved before the columns above it are added.
   const int jd1 = 64 * I + 64;
   jend = min(jend, (p.N + 1) & ~1);   // zero-padded columns (beta = 0, iK = 0) contribute exact zeros: skip them
-  const double e0 = uni_row_factor(kr0, s_tab), e1 = uni_row_factor(kr1, s_tab);   // kr0, kr1 become residual shifts
+  const double e0 = uni_row_factor(kr0), e1 = uni_row_factor(kr1);   // kr0, kr1 become residual shifts
   const bool far = __any_sync(0xffffffffu, kr0 != 0.0 || kr1 != 0.0);
   double trD0 = 0.0, trD1 = 0.0, trU0 = 0.0, trU1 = 0.0;
   if (jbeg < jd1) {
-    if (far) uni_fwd_cols<EV, true>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD0, trD1, s_tab);
-    else uni_fwd_cols<EV, false>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD0, trD1, s_tab);
+    if (far) uni_fwd_cols<EV, true>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD0, trD1);
+    else uni_fwd_cols<EV, false>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, r0, r1, trD0, trD1);
 #pragma unroll
     for (int b = 0; b < E; b++) { r0[b] *= 0.5; r1[b] *= 0.5; }
   }
-  if (far) uni_fwd_cols<EV, true>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU0, trU1, s_tab);
-  else uni_fwd_cols<EV, false>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU0, trU1, s_tab);
+  if (far) uni_fwd_cols<EV, true>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU0, trU1);
+  else uni_fwd_cols<EV, false>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, r0, r1, trU0, trU1);
   const double tr = e0 * fma(2.0, trU0, trD0) + e1 * fma(2.0, trU1, trD1);
 #pragma unroll
   for (int b = 0; b < E; b++) { bi0[b] *= e0; bi1[b] *= e1; }   // the row factor, applied once to the finished row sums
@@ -275,7 +271,7 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
   double* s_m = sm + L.m; double* s_s = sm + L.s; double* s_mu = sm + L.mu; double* s_A = sm + L.A;
   double* s_Q = sm + L.Q; double* s_misc = sm + L.misc; double* s_M = sm + L.M; double* s_V = sm + L.V;
   double* s_acc = sm + L.acc; double* s_am = sm + L.am; double* s_r = sm + L.r; double* s_rv = sm + L.rv;
-  int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
+  int* s_int = reinterpret_cast<int*>(sm + L.ints);
   double* s_part = sm + L.part; double* s_wp = sm + L.wp; double* s_S = sm + L.S; double* s_cst = sm + L.cst;
   const int nOut = L.nOut, warp = tid >> 5, nwarps = NT >> 5;
   const UniRecLayout RL = uni_rec_layout(E);
@@ -287,7 +283,7 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
                     p.kappa, p.use_constraints};
   const double* il2 = p.il2;            // row 0 (all rows equal)
   const double s2 = p.s2[0];
-  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
+  exp2s_fill(p.exp2tab, tid, NT);
   __syncthreads();
 
   long long clk_ = clock64();
@@ -391,7 +387,7 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
           if (d < D) tail = fma(nu[d] * nu[d], il2[d], tail);
-        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
+        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail)) : 0.0;
         double* rec = s_rec + i * (2 * EV + 2);
 #pragma unroll
         for (int e = 0; e < EV; e++) rec[e] = nu[e];
@@ -424,7 +420,7 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
           while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
           const int ce = min(c1, base + cpt * (nrb - I));
           uni_fwd_item<EV>(p, s_rec, s_Q, il2, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base), lane,
-                           s_part + warp * L.partlen, s_tab);
+                           s_part + warp * L.partlen);
           c0 = ce;
         }
       }
@@ -571,7 +567,8 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
                                              int jbeg, int jend, const double (&u0)[EV], const double (&u1)[EV],
                                              double kr0, double kr1, const double (&p0)[EV], const double (&p1)[EV],
                                              double wb0, double wb1, double& rho0, double& rho1, double (&xi0)[EV],
-                                             double (&xi1)[EV], int lane, double* __restrict__ g_gam, unsigned s_tab) {
+                                             double (&xi1)[EV], int lane, double* __restrict__ g_gam,
+                                             double* __restrict__ scr) {
   constexpr int E = EV;
   const int NP = p.NP;
   const double* __restrict__ ik0 = p.iK + (size_t)jbeg * NP + i0;
@@ -604,7 +601,7 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
         t[3] = fma(u1[e], nb[e], t[3]);
         t[2] = fma(u0[e], nb[e], t[2]);
       }
-      exp2s_x4(t, w, s_tab);
+      exp2s_x4(t, w);
 #pragma unroll
       for (int q = 0; q < 4; q++) w[q] *= c[q];
       rho0 += w[0] + w[2];
@@ -622,9 +619,14 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
       v[2 * jp] = w[0] + w[1];
       v[2 * jp + 1] = w[2] + w[3];
     }
+#if UNI_BWD_COLRED_SMEM
+    const double tot = col_reduce8s(v, lane, scr);   // column sums through the warp's shared-memory scratch
+    if (lane < 8) uni_red_add(g_gam + j0 + lane, tot);
+#else
     int col;
-    double tot = col_reduce8(v, lane, col);
+    const double tot = col_reduce8(v, lane, col);
     if ((lane & 3) == 0) uni_red_add(g_gam + j0 + col, tot);
+#endif
   }
 }
 
@@ -636,7 +638,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
                                              const double* __restrict__ Qm, const double* __restrict__ il2,
                                              const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
                                              int lane, double* __restrict__ g_gam, double* __restrict__ g_rho,
-                                             double* __restrict__ g_xi, unsigned s_tab) {
+                                             double* __restrict__ g_xi, double* __restrict__ scr) {
   constexpr int E = EV;
   const int NP = p.NP;
   const int i0 = 64 * I + 2 * lane, i1 = i0 + 1;   // adjacent rows (16-byte iK loads), as in the forward sweep
@@ -671,7 +673,7 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   const int jd1 = 64 * I + 64;
   jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns contribute exact zeros: skip them (8 columns per round)
   // row factor e_i of the exponential (uni_fwd_cols) folded into the coefficient row vectors and the trace weights
-  const double e0 = uni_row_factor(kr0, s_tab), e1 = uni_row_factor(kr1, s_tab);   // kr0, kr1 become residual shifts
+  const double e0 = uni_row_factor(kr0), e1 = uni_row_factor(kr1);   // kr0, kr1 become residual shifts
   const bool far = __any_sync(0xffffffffu, kr0 != 0.0 || kr1 != 0.0);
   const double wb0 = wbar * e0, wb1 = wbar * e1;
 #pragma unroll
@@ -680,16 +682,16 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
 #pragma unroll
     for (int a = 0; a < E; a++) { p0[a] *= 0.5; p1[a] *= 0.5; }
     if (far) uni_bwd_cols<EV, true>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, p0, p1, 0.5 * wb0, 0.5 * wb1, rho0, rho1,
-                                    xi0, xi1, lane, g_gam, s_tab);
+                                    xi0, xi1, lane, g_gam, scr);
     else uni_bwd_cols<EV, false>(p, s_rec, i0, jbeg, min(jend, jd1), u0, u1, kr0, kr1, p0, p1, 0.5 * wb0, 0.5 * wb1, rho0, rho1,
-                                 xi0, xi1, lane, g_gam, s_tab);
+                                 xi0, xi1, lane, g_gam, scr);
 #pragma unroll
     for (int a = 0; a < E; a++) { p0[a] *= 2.0; p1[a] *= 2.0; }
   }
   if (far) uni_bwd_cols<EV, true>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, p0, p1, wb0, wb1, rho0, rho1, xi0, xi1,
-                                  lane, g_gam, s_tab);
+                                  lane, g_gam, scr);
   else uni_bwd_cols<EV, false>(p, s_rec, i0, max(jbeg, jd1), jend, u0, u1, kr0, kr1, p0, p1, wb0, wb1, rho0, rho1, xi0, xi1,
-                               lane, g_gam, s_tab);
+                               lane, g_gam, scr);
   uni_red_add(g_rho + i0, rho0);
   uni_red_add(g_rho + i1, rho1);
 #pragma unroll
@@ -812,7 +814,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
   const int warp = tid >> 5, nwarps = NT >> 5;
   double* s_wp = sm + L.wp; double* s_wp2 = s_wp + 8 * L.wplen;   // per-warp rows of the B1 / B3 point sums
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q;
-  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints); double* s_tabp = sm + L.tab; const unsigned s_tab = exp2s_table_addr(s_tabp);
+  double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints);
   double* s2p = sm + L.small2;
   // small2 carve: mu_bar[E], s_bar[E2], Om[E2], Rinv[E2], Ub[E2], Vb[E2], hg[E + E2] (h_bar, g_bar), scal[16]
   double* s_mubar = s2p; double* s_sbar = s_mubar + GPMPC_MAX_EV; double* s_Om = s_sbar + EV * EV;
@@ -822,7 +824,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
   const double* il2 = p.il2;
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
-  for (int i = tid; i < EXP2S_N; i += NT) s_tabp[i] = p.exp2tab[i];
+  exp2s_fill(p.exp2tab, tid, NT);
   if (C == 1)
     for (int i = tid; i < NP * (2 + EV); i += NT) g_gam[i] = 0.0;   // B3 re-zeroes after every step (clusters: host memset)
   __syncthreads();
@@ -981,7 +983,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
           an[d] = 0.0;
           if (d < D) { tail = fma(nu[d] * nu[d], il2[d], tail); an[d] = nu[d] * il2[d]; }
         }
-        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail), s_tab) : 0.0;
+        const double ei = (i < N) ? exp2s((-0.5 * GPMPC_EXP2S_SCALE) * (quad + tail)) : 0.0;
         double* rcd = s_rec + i * (2 * EV + 2);
 #pragma unroll
         for (int e = 0; e < EV; e++) rcd[e] = nu[e];
@@ -1035,7 +1037,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
           while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
           const int ce = min(c1, base + cpt * (nrb - I));
           uni_bwd_item<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base),
-                           lane, g_gam, g_rho, g_xi, s_tab);
+                           lane, g_gam, g_rho, g_xi, sm + L.colred + warp * COLRED_WARP);
           c0 = ce;
         }
       }

@@ -6,8 +6,8 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, tail, tlen, rhot, pre, prelen, out, nOut, part, partlen, wp, wplen, S, cst;
-  int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, tab, small2, total;
+  int rec, tail, tlen, rhot, pre, prelen, out, nOut, part, partlen, wp, wplen, S, cst, colred;
+  int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, small2, total;
 };
 
 // bwd=false: forward kernel; bwd=true: reverse-sweep kernel (its row / column sums live in a global per-CTA scratch)
@@ -33,6 +33,12 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   // per-warp partial rows of the O(N) reductions (lane per output): forward E (1 + D) outputs, reverse sweep D + P
   L.wplen = bwd ? (D + P) : (E * L.nOut);
   L.wp = o; o += (bwd ? 16 : 8) * L.wplen;   // reverse sweep: two sets (B1, B3)
+  // reverse sweep, optional (UNI_BWD_COLRED_SMEM): per-warp scratch of col_reduce8s (COLRED_WARP doubles, <= 8 warps)
+  o = (o + 1) & ~1;
+  L.colred = o;
+#if defined(UNI_BWD_COLRED_SMEM) && UNI_BWD_COLRED_SMEM
+  if (bwd) o += 8 * 320;
+#endif
   L.S = o; o += 2 * E * E;          // S and s V^T of the recurrence stage
   L.cst = o;                        // target, W, WT (read from shared memory by the forward kernel only)
 #ifdef GPMPC_BWD_NO_CST              // tuning variant (tools/variants.sh build-all): 2.7 KB less for the reverse sweep
@@ -54,7 +60,6 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.rv = o; o += H + 1;
   L.ints = o; o += 4;
   o = (o + 1) & ~1;
-  L.tab = o; o += EXP2S_N;   // 2^(j/2048) for exp2s (pre-biased entries)
   L.small2 = o; o += bwd ? (8 * EV * EV + 8 * GPMPC_MAX_D + E * E + 64) : 0;
   L.total = (o + 1) & ~1;
   return L;

@@ -4,7 +4,13 @@ its objective evaluated by the B200 CUDA engine.
   compute_mean_lcb_trajectory        gp_mpc_controller.py:229-285 -> one gpmpc_rollout call (value + gradient)
   compute_mean_lcb_trajectory_batch  NEW: B candidate sequences in one call -> costs (B,), grads (B, H*Na)
   get_action / _get_optimal_actions  gp_mpc_controller.py:52-153  same orchestration (scipy L-BFGS-B, restarts)
-The five side-effect tensors (:279-283) are kept; for a batch they describe the best candidate."""
+The five side-effect tensors (:279-283) are kept; for a batch they describe the best candidate.
+
+Multi-GPU (one process per GPU, torch.distributed): GpMpcController(..., process_group=group) shards the candidate
+batch of compute_mean_lcb_trajectory_batch and of the batched optimiser over the ranks of `group` (contiguous slices,
+rl_gp_mpc/parallel.py): every rank scores / optimises its slice, ONE in-place all-gather brings every candidate's cost
+to every rank, all ranks agree on the arg-min, and the winner's trajectory is broadcast from its owner.  Gradients stay
+on the owning rank."""
 import atexit
 import multiprocessing
 import sys
@@ -71,8 +77,17 @@ def _stop_training_threads():
 
 
 class GpMpcController(BaseControllerObject):
-    def __init__(self, observation_low, observation_high, action_low, action_high, config: Config, device=None):
+    def __init__(self, observation_low, observation_high, action_low, action_high, config: Config, device=None,
+                 process_group=None):
+        """process_group (additive): None = single GPU; True / "world" = the default torch.distributed group; or a
+        ProcessGroup.  Every rank must construct the controller with the same config and feed it the same memory."""
         self.config = config
+        self.sharder = None
+        if process_group is not None and process_group is not False:
+            from rl_gp_mpc.parallel import CandidateSharder
+            self.sharder = CandidateSharder(None if process_group is True or process_group == "world" else process_group)
+        self.shard = None          # (lo, hi) of the last sharded batch: rows of the returned gradients
+        self._cand_gen = None
         self.observation_state_mapper = NormalizationObservationStateMapper(
             config=config.observation, observation_low=observation_low, observation_high=observation_high)
         mapper_cls = DerivativeActionMapper if config.actions.limit_action_change else NormalizationActionMapper
@@ -94,6 +109,7 @@ class GpMpcController(BaseControllerObject):
         self.queue_train = self.ctx.Queue()
         self.info_iters = {}
         self._cost_bound = False
+        self._cost_key_values = None
 
     # ------------------------------------------------------------------ control step
     def get_action(self, obs_mu, obs_var=None, random: bool = False):
@@ -132,41 +148,81 @@ class GpMpcController(BaseControllerObject):
         x_mem, y_mem = self.memory.get()
         self.transition_model.prepare_inference(x_mem, y_mem)
 
+    def _candidate_inits(self, nb, n):
+        """(nb, n) uniform random restarts from the controller's own generator (ControllerConfig.batched_seed; drawn once
+        otherwise).  With a process group every rank draws the SAME matrix (rank 0's seed is broadcast once) and then
+        works on its rows, so the sharded optimiser starts from the candidates a single GPU would start from."""
+        if self._cand_gen is None:
+            seed = getattr(self.config.controller, "batched_seed", None)
+            if seed is None:
+                seed = int(torch.seed() % (2 ** 31))
+                if self.sharder is not None:
+                    t = torch.tensor([seed], dtype=torch.int64, device=self.transition_model.engine.device)
+                    self.sharder.broadcast(t, 0)
+                    seed = int(t.item())
+            self._cand_gen = torch.Generator(device="cpu").manual_seed(int(seed))
+        return torch.rand((nb, n), dtype=torch.float64, generator=self._cand_gen)
+
     def _get_optimal_actions_batched(self, state_mu, state_var):
         """B candidate action sequences optimised at once on the device (batched_optim.py: projected L-BFGS, or
         projected Adam with ControllerConfig(batched_method="adam")) on the LCB objective.
 
         Replaces the serial restart loop of the reference (gp_mpc_controller.py:125-148): candidate 0 is the shifted
         previous solution (when init_from_previous_actions), the others are uniform random restarts; each iteration
-        costs one batched rollout (value + gradient for all candidates).  Returns the model actions of the best one."""
+        costs one batched rollout (value + gradient for all candidates).  Returns the model actions of the best one.
+        With a process group the candidates are sharded over the ranks: each rank optimises its slice with no collective
+        inside the iterations; the final costs are all-gathered once, the winner's sequence and trajectory broadcast."""
         ctl = self.config.controller
         h, na = ctl.len_horizon, self.actions_mapper.dim_action
         nb = int(ctl.batched_candidates)
         dev = self.transition_model.engine.device
-        x = torch.rand((nb, h * na), dtype=torch.float64, device=dev)
+        x = self._candidate_inits(nb, h * na).to(dev)
         if ctl.init_from_previous_actions and self.actions_mpc_previous_iter is not None:
             warm = generate_mpc_action_init_frompreviousiter(self.actions_mpc_previous_iter, dim_action=na)
             x[0] = torch.as_tensor(warm, dtype=torch.float64, device=dev)
+        sh = self.sharder
+        lo, hi = sh.bounds(nb) if sh is not None else (0, nb)
+        x = x[lo:hi]
 
         def fun(xb):
             out = self._rollout(xb, state_mu, state_var, need_grad=True, need_traj=False)
             return out["cost"], out["grad"]
 
-        if getattr(ctl, "batched_method", "lbfgs") == "adam":
-            best_x, best_cost, x_last = minimize_box_adam(fun, x, ctl.batched_iters, lr=ctl.batched_lr)
-            cost = self._rollout(x_last, state_mu, state_var, need_grad=False, need_traj=False)["cost"]
-            better = torch.isfinite(cost) & (cost < best_cost)
-            best_cost = torch.where(better, cost, best_cost)
-            best_x = torch.where(better[:, None], x_last, best_x)
+        if hi > lo:
+            if getattr(ctl, "batched_method", "lbfgs") == "adam":
+                best_x, best_cost, x_last = minimize_box_adam(fun, x, ctl.batched_iters, lr=ctl.batched_lr)
+                cost = self._rollout(x_last, state_mu, state_var, need_grad=False, need_traj=False)["cost"]
+                better = torch.isfinite(cost) & (cost < best_cost)
+                best_cost = torch.where(better, cost, best_cost)
+                best_x = torch.where(better[:, None], x_last, best_x)
+            else:
+                best_x, best_cost = minimize_box_lbfgs(fun, x, ctl.batched_iters)
         else:
-            best_x, best_cost = minimize_box_lbfgs(fun, x, ctl.batched_iters)
-        idx = int(torch.argmin(best_cost).item())
-        final = self._rollout(best_x[idx:idx + 1], state_mu, state_var, need_grad=False)   # side effects of the winner
-        self._store_side_effects(final, 0)
-        self.batched_costs = best_cost
-        self.last_optim_cost = float(best_cost[idx].item())
-        self.actions_mpc_previous_iter = best_x[idx].cpu().numpy().copy()
-        return self.actions_mapper.transform_action_mpc_to_action_model(best_x[idx].cpu())
+            best_x, best_cost = x, torch.empty((0,), dtype=torch.float64, device=dev)
+        if sh is None:
+            idx = int(torch.argmin(best_cost).item())
+            final = self._rollout(best_x[idx:idx + 1], state_mu, state_var, need_grad=False)   # side effects of the winner
+            self._store_side_effects(final, 0)
+            self.batched_costs = best_cost
+            self.last_optim_cost = float(best_cost[idx].item())
+            self.actions_mpc_previous_iter = best_x[idx].cpu().numpy().copy()
+            return self.actions_mapper.transform_action_mpc_to_action_model(best_x[idx].cpu())
+        buf = sh.cost_buffer(nb, dev)
+        sh.local_view(buf, nb).copy_(best_cost)
+        costs = sh.gather(buf, nb)
+        idx = sh.argmin(buf, nb)
+        owner = sh.owner(idx, nb)
+        winner = torch.empty((h * na,), dtype=torch.float64, device=dev)
+        final = None
+        if sh.rank == owner:
+            winner.copy_(best_x[idx - lo])
+            final = self._rollout(winner[None], state_mu, state_var, need_grad=False)
+        sh.broadcast(winner, owner)
+        self._share_side_effects(final, 0, owner, 1)
+        self.batched_costs = costs.clone()
+        self.last_optim_cost = float(costs[idx].item())
+        self.actions_mpc_previous_iter = winner.cpu().numpy().copy()
+        return self.actions_mapper.transform_action_mpc_to_action_model(winner.cpu())
 
     def _get_optimal_actions(self, state_mu, state_var):
         self._prepare()
@@ -226,8 +282,16 @@ class GpMpcController(BaseControllerObject):
         # the fit and the control loop both make many short blocking CUDA calls; with CPython's default 5 ms switch
         # interval every hand-over of the interpreter lock can stall that long (measured: 26 ms per objective evaluation
         # of the fit instead of ~1 ms), so the interval is shortened while both are active
+        if getattr(self, "_switch_interval_saved", None) is None:
+            self._switch_interval_saved = sys.getswitchinterval()
         sys.setswitchinterval(min(sys.getswitchinterval(), 2e-4))
         self.p_train.start()
+
+    def _restore_switch_interval(self):
+        """The shortened interpreter switch interval only serves the concurrent fit: put the process's own value back."""
+        if getattr(self, "_switch_interval_saved", None) is not None:
+            sys.setswitchinterval(self._switch_interval_saved)
+            self._switch_interval_saved = None
 
     def check_and_close_processes(self):
         if "p_train" in self.__dict__ and not self.p_train._closed and not self.p_train.is_alive():
@@ -236,20 +300,40 @@ class GpMpcController(BaseControllerObject):
             for model, p in zip(self.transition_model.models, params):
                 model.initialize(**p)
             self.p_train.close()
+            self._restore_switch_interval()
             self._prepare()
 
     def close(self):
         """Stops a hyper-parameter fit that is still running (its result is dropped) -- call at the end of a run."""
         if "p_train" in self.__dict__:
             self.p_train.stop()
+        self._restore_switch_interval()
 
     # ------------------------------------------------------------------ objective
     def _bind_cost(self):
-        if not self._cost_bound or self.transition_model._cost_key != id(self.config.reward):
+        """(Re)uploads the cost description when the reward config changed -- by identity OR in place: the reference
+        re-reads config.reward on every objective evaluation (gp_mpc_controller.py:269), so an in-place edit of targets,
+        weights, exploration factor or constraints must reach the fused kernels too (key = the values themselves)."""
+        key = self._cost_fingerprint(self.config.reward)
+        if not self._cost_bound or self._cost_key_values != key:
             self.transition_model.set_cost(self.config.reward)
-            self._cost_bound = True
+            self._cost_bound, self._cost_key_values = True, key
 
-    def _rollout(self, actions_mpc, obs_mu, obs_var, need_grad=True, need_traj=True):
+    @staticmethod
+    def _cost_fingerprint(r):
+        def flat(v):
+            return tuple(np.asarray(torch.as_tensor(v).detach().cpu(), dtype=np.float64).reshape(-1).tolist())
+        parts = [id(r)]
+        for name in ("target_state_action_norm", "weight_matrix_cost", "weight_matrix_cost_terminal", "state_min",
+                     "state_max", "target_state_norm", "target_action_norm", "weight_state", "weight_action",
+                     "weight_state_terminal"):
+            if hasattr(r, name) and getattr(r, name) is not None:
+                parts.append(flat(getattr(r, name)))
+        for name in ("exploration_factor", "use_constraints", "clip_lower_bound_cost_to_0", "area_multiplier"):
+            parts.append(getattr(r, name, None))
+        return tuple(parts)
+
+    def _rollout(self, actions_mpc, obs_mu, obs_var, need_grad=True, need_traj=True, out=None):
         self._bind_cost()
         am = self.actions_mapper
         limit = bool(self.config.actions.limit_action_change)
@@ -257,7 +341,8 @@ class GpMpcController(BaseControllerObject):
             actions_mpc, obs_mu, obs_var, self.config.controller.len_horizon, iter_ctrl=self.iter_ctrl,
             limit_action_change=limit,
             max_change=self.config.actions.max_change_action_norm if limit else None,
-            action_prev=am.action_model_previous_iter if limit else None, need_grad=need_grad, need_traj=need_traj)
+            action_prev=am.action_model_previous_iter if limit else None, need_grad=need_grad, need_traj=need_traj,
+            out=out)
 
     def _store_side_effects(self, out, idx):
         self.cost_traj_mean_lcb = -out["cost"][idx].cpu()
@@ -265,6 +350,26 @@ class GpMpcController(BaseControllerObject):
         self.rewards_trajectory = out["rewards_trajectory"][idx].cpu()
         self.rewards_traj_var = out["rewards_traj_var"][idx].cpu()
         self.states_var_pred = out["states_var_pred"][idx].cpu()
+
+    def _share_side_effects(self, out, idx, owner, _unused=None):
+        """Sharded runs: the five side-effect tensors of candidate `idx` of `out` (held by rank `owner` only) are packed
+        into one flat buffer, broadcast, and stored on every rank -- get_action then reads the same trajectory everywhere."""
+        h, e = self.config.controller.len_horizon, self.transition_model.dim_state
+        sizes = [1, (h + 1) * e, h + 1, h + 1, (h + 1) * e * e]
+        flat = torch.empty((sum(sizes),), dtype=torch.float64, device=self.transition_model.engine.device)
+        if self.sharder.rank == owner:
+            parts = [out["cost"][idx].reshape(1), out["states_mu_pred"][idx].reshape(-1),
+                     out["rewards_trajectory"][idx].reshape(-1), out["rewards_traj_var"][idx].reshape(-1),
+                     out["states_var_pred"][idx].reshape(-1)]
+            torch.cat(parts, out=flat)
+        self.sharder.broadcast(flat, owner)
+        host = flat.cpu()
+        c, mu, r, rv, var = torch.split(host, sizes)
+        self.cost_traj_mean_lcb = -c[0].clone()
+        self.states_mu_pred = mu.reshape(h + 1, e).clone()
+        self.rewards_trajectory = r.clone()
+        self.rewards_traj_var = rv.clone()
+        self.states_var_pred = var.reshape(h + 1, e, e).clone()
 
     def _packed_outputs(self, batch):
         """One flat device buffer holding every output of a rollout of `batch` sequences, plus views into it in the
@@ -318,14 +423,37 @@ class GpMpcController(BaseControllerObject):
         self.states_var_pred = hviews["states_var_pred"][0].clone()
         return float(hviews["cost"][0]), hviews["grad"][0].numpy().copy()
 
-    def compute_mean_lcb_trajectory_batch(self, actions_mpc, obs_mu, obs_var, need_grad=True):
-        """(B, H*Na) -> costs (B,), grads (B, H*Na) as CUDA tensors; side effects = best candidate."""
+    def compute_mean_lcb_trajectory_batch(self, actions_mpc, obs_mu, obs_var, need_grad=True, need_traj=True):
+        """(B, H*Na) -> costs (B,), grads (B, H*Na) as CUDA tensors; side effects = best candidate.
+
+        With a process group: every rank passes the SAME (B, H*Na) batch (host or device tensor; only the rank's own rows
+        are copied to its GPU), scores rows [lo, hi) = self.shard, and after ONE all-gather returns the costs of ALL B
+        candidates; the gradients returned are those of the rank's own rows, (hi - lo, H*Na).  self.best_candidate is the
+        global arg-min on every rank.  need_traj=False skips the trajectory outputs and the side-effect tensors."""
         a = torch.as_tensor(actions_mpc)
-        out = self._rollout(a.reshape(a.shape[0], -1), obs_mu, obs_var, need_grad=need_grad)
-        best = int(torch.argmin(torch.nan_to_num(out["cost"], nan=float("inf"))).item())
-        self._store_side_effects(out, best)
-        self.best_candidate = best
-        return out["cost"], out.get("grad")
+        a = a.reshape(a.shape[0], -1)
+        sh = self.sharder
+        if sh is None:
+            out = self._rollout(a, obs_mu, obs_var, need_grad=need_grad, need_traj=need_traj)
+            best = int(torch.argmin(torch.nan_to_num(out["cost"], nan=float("inf"))).item())
+            if need_traj:
+                self._store_side_effects(out, best)
+            self.best_candidate = best
+            return out["cost"], out.get("grad")
+        nb = a.shape[0]
+        lo, hi = sh.bounds(nb)
+        dev = self.transition_model.engine.device
+        buf = sh.cost_buffer(nb, dev)
+        out = {"cost": sh.local_view(buf, nb)}        # the kernel writes its slice of the gather buffer directly
+        if hi > lo:
+            out = self._rollout(a[lo:hi], obs_mu, obs_var, need_grad=need_grad, need_traj=need_traj, out=out)
+        costs = sh.gather(buf, nb)
+        best = sh.argmin(buf, nb)
+        self.best_candidate, self.shard = best, (lo, hi)
+        if need_traj:
+            self._share_side_effects(out, best - lo, sh.owner(best, nb))
+        grads = out.get("grad") if hi > lo else torch.empty((0, a.shape[1]), dtype=torch.float64, device=dev)
+        return costs, grads
 
     def compute_cost_unnormalized(self, obs, action, obs_var=None):
         state_mu, state_var = self.observation_state_mapper.get_state(obs=obs, obs_var=obs_var, update_internals=False)

@@ -42,8 +42,18 @@ CASES = {
     "empty_memory": dict(E=2, Na=1, N=1, H=3, B=2, ls=0.5, seed=8),
 }
 
+# The reference's own hyper-parameter regime at the BASELINE.json training-set sizes: noise 1e-5 at N = 200 / 500 gives
+# cond(K + noise I) ~ 1e6 .. 1e7, where the covariance sums cancel by ~1e8.  `python -m
+# oracle.make_golden --large` writes tests/golden/big_<name>.npz WITHOUT the (E, N, N) inverse (4 MB at N = 500):
+# its diagonal and row sums are kept instead, beta and every output of the path in full.
+LARGE_CASES = {
+    "c4a_n500": dict(name="C4a", B=1, H=3, seed=41),                       # E=2, Na=2, N=500 (ProcessControl dims)
+    "c2_n200_h25": dict(name="C2", B=1, H=25, seed=42),                    # E=3, Na=1, N=200, full horizon
+    "c4a_n500_distinct": dict(name="C4a", B=1, H=3, seed=43, distinct_lengthscales=True),   # general kernel path
+}
 
-def run_case(kwargs, ref):
+
+def run_case(kwargs, ref, large=False):
     cfg = make_workload(**kwargs)
     if kwargs.get("name") is None and cfg["N"] == 1:
         cfg["x"][:] = 0.0  # gp_memory.py:109-111: zeros (1,D)/(1,E) when the memory is empty
@@ -55,6 +65,10 @@ def run_case(kwargs, ref):
         tm.prepare_inference(x, y)
     out = dict(iK=tm.iK.numpy(), beta=tm.beta.numpy(),
                lengthscales=tm.lengthscales.detach().numpy(), variances=tm.variances.detach().numpy())
+    if large:
+        iK = out.pop("iK")
+        out.update(iK_diag=np.diagonal(iK, axis1=1, axis2=2).copy(), iK_rowsum=iK.sum(axis=2),
+                   iK_absmax=np.abs(iK).max())
     # one moment-matching step at a full (non-diagonal) input covariance
     E, D = cfg["E"], cfg["D"]
     rng = np.random.default_rng(77 + cfg["seed"])
@@ -86,6 +100,14 @@ def main():
     ref = load_reference()
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    if "--large" in sys.argv:
+        with open(os.path.join(outdir, "cases_big.json"), "w") as f:
+            json.dump(LARGE_CASES, f, indent=1, sort_keys=True)
+        for name, kwargs in LARGE_CASES.items():
+            out = run_case(kwargs, ref, large=True)
+            np.savez_compressed(os.path.join(outdir, "big_" + name + ".npz"), **out)
+            print(name, "cost", out["cost"], "|grad|max", np.abs(out["grad"]).max(), "|iK|max", out["iK_absmax"])
+        return
     with open(os.path.join(outdir, "cases.json"), "w") as f:
         json.dump(CASES, f, indent=1, sort_keys=True)
     for name, kwargs in CASES.items():

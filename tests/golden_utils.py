@@ -26,3 +26,20 @@ def load_case(name):
     for k in ("x", "y", "actions", "mu0"):
         assert np.array_equal(gold[k], cfg[k]), "workload generator drifted for %s/%s" % (name, k)
     return cfg, gold
+
+
+def big_case_names():
+    """Reference-generated vectors at the BASELINE.json training-set sizes (oracle/make_golden.py --large): noise 1e-5 at
+    N = 200 / 500, i.e. cond(K + noise I) ~ 1e6 .. 1e7.  The (E, N, N) inverse is not stored (diagonal + row sums are)."""
+    with open(os.path.join(GOLDEN_DIR, "cases_big.json")) as f:
+        return sorted(json.load(f).keys())
+
+
+def load_big_case(name):
+    with open(os.path.join(GOLDEN_DIR, "cases_big.json")) as f:
+        kwargs = json.load(f)[name]
+    cfg = make_workload(**kwargs)
+    gold = dict(np.load(os.path.join(GOLDEN_DIR, "big_" + name + ".npz")))
+    for k in ("x", "y", "actions", "mu0"):
+        assert np.array_equal(gold[k], cfg[k]), "workload generator drifted for %s/%s" % (name, k)
+    return cfg, gold
