@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--distinct-lengthscales", action="store_true",
                     help="per-GP ARD lengthscales ('trained' hyper-parameters) instead of the reference defaults")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-general-path", action="store_true", help="skip the general_path block (per-GP hyper-parameters)")
     return ap.parse_args()
 
 
@@ -174,33 +175,45 @@ def workload_config(cfg, args):
               "(1.2 GB per step) exceed L2, and a 256 MB buffer is rewritten between timed iterations (L2 flush)"}
 
 
-def fp64_report(uniform, E, N, preds, fwd_ms, bwd_ms, f_alg, peak):
-    """Float64 roofline: (a) SURVEY 8(d)'s algorithmic flops (E^2-pair algorithm) and (b) the float64 instructions the
-    kernels actually execute per prediction in their hot loops (counted in the SASS), each counted
-    as one FMA = 2 flops, against the measured DFMA peak.  NB: a DFMA with three distinct register operands issues at
-    2/3 of that peak on B200 (tools/micro/dfma_operands.cu)."""
+def sass_counts(E):
+    """Float64 instructions per element of the sweeps' hot loops, counted in the SASS of the built library by
+    tools/sass_counts.py (committed: profiles/sass_loop_counts.json).  Falls back to the source-level count."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "sass_loop_counts.json")))["state_dims"][str(E)]
+        out = {"source": "profiles/sass_loop_counts.json (tools/sass_counts.py: cuobjdump -sass of the built library)"}
+        out["uniform_fwd"] = tab["uniform_fwd"]["float64_per_element"]
+        out["uniform_bwd"] = tab["uniform_bwd"]["float64_per_element"]
+        out["general_grad"] = (tab["general_grad"]["float64_per_element_off_diagonal"],
+                               tab["general_grad"]["float64_per_element_diagonal"])
+        out["general_value"] = (tab["general_value"]["float64_per_element_off_diagonal"],
+                                tab["general_value"]["float64_per_element_diagonal"])
+        return out
+    except Exception:
+        return {"source": "source-level count (profiles/sass_loop_counts.json not readable)",
+                "uniform_fwd": E + 7 + E + 1, "uniform_bwd": E + 7 + (E + 1) + 3.06 + E,
+                "general_grad": (E + 7 + 1 + E + 1.56, E + 7 + 4 + E + 1.31), "general_value": (E + 8, E + 10)}
+
+
+def sweep_elements(uniform, E, N):
+    """(i, j) elements one prediction sweeps: the uniform kernels visit the 64 x 64 tiles on or above the diagonal once
+    for all output pairs; the general kernel visits them per diagonal pair and the full N x N per off-diagonal pair.
+    Rows are padded to a multiple of 64, padded columns are skipped."""
     NP = (N + 63) // 64 * 64
+    nrb = NP // 64
+    cols = (N + 7) // 8 * 8
+    tri = sum(64 * max(0, cols - 64 * I) for I in range(nrb))
     if uniform:
-        tri = (NP // 64) * (NP // 64 + 1) // 2 * 64 * 64      # elements of the upper tile triangle (both sweeps)
-        # (the row factor of the exponential is applied after the sweep: E exponent FMAs, no per-element add)
-        fwd_ops = tri * (E + 7 + E + 1)                       # exponent, exp2s, beta-weighted row sums, trace
-        bwd_ops = tri * (E + 7 + (E + 1) + 3.06 + E)          # + coefficient, w, rho/col sums, xi
-    else:
-        elems = E * NP * (NP + 64) // 2 + E * (E - 1) // 2 * NP * NP
-        fwd_ops = elems * ((E + 1) + 7 + 2 + 1 + (E + 3.1))   # gradient mode: + rho/gamma/xi accumulation
-        bwd_ops = 0
-    ex_f = 2.0 * fwd_ops * preds / (fwd_ms * 1e-3)
-    out = {"peak_tflops": peak / 1e12, "peak_source": "measured (gpmpc_fp64_peak: register-resident DFMA loop)",
-           "algorithmic_flops_per_prediction": f_alg,
-           "algorithmic_tflops": preds * f_alg / (fwd_ms * 1e-3) / 1e12,
-           "algorithmic_frac": preds * f_alg / (fwd_ms * 1e-3) / peak,
-           "executed_flops_per_prediction_fwd": 2.0 * fwd_ops, "executed_tflops_fwd": ex_f / 1e12,
-           "executed_frac_fwd": ex_f / peak}
-    if bwd_ops and bwd_ms > 0:
-        ex_b = 2.0 * bwd_ops * preds / (bwd_ms * 1e-3)
-        out.update({"executed_flops_per_prediction_bwd": 2.0 * bwd_ops, "executed_tflops_bwd": ex_b / 1e12,
-                    "executed_frac_bwd": ex_b / peak})
-    return out
+        return {"triangle": tri}
+    return {"diagonal": E * tri, "off_diagonal": E * (E - 1) // 2 * NP * cols}
+
+
+def fp64_model(kernel, E, N, counts):
+    """Executed float64 instructions per prediction of one kernel's hot loops (each = one 2-flop FMA slot of the pipe)."""
+    if kernel in ("uniform_fwd", "uniform_bwd"):
+        return sweep_elements(True, E, N)["triangle"] * counts[kernel]
+    el = sweep_elements(False, E, N)
+    off, dia = counts[kernel]
+    return el["off_diagonal"] * off + el["diagonal"] * dia
 
 
 def ncu_traffic(kernel_prefix, workload):
@@ -244,7 +257,6 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
     from rl_gp_mpc import GpMpcController, _cabi
-    from rl_gp_mpc.parallel import allgather_costs, shard_bounds
     from rl_gp_mpc.config_classes.actions_config import ActionsConfig
     from rl_gp_mpc.config_classes.controller_config import ControllerConfig
     from rl_gp_mpc.config_classes.model_config import ModelConfig
@@ -253,23 +265,27 @@ def main():
     from rl_gp_mpc.config_classes.total_config import Config
 
     E, Na, H, B, N, D = cfg["E"], cfg["Na"], cfg["H"], cfg["B"], cfg["N"], cfg["D"]
-    # ---- shard the candidate batch (contiguous slices; the training block is replicated, every rank factorises)
-    per, lo, hi = shard_bounds(B, world, rank)
-    Bl = hi - lo
-    r = cfg["reward"]
-    config = Config(
-        observation_config=ObservationConfig(obs_var_norm=[cfg["obs_var"]] * E),
-        reward_config=RewardConfig(target_state_norm=list(r["target_state"]), weight_state=list(r["weight_state"]),
-                                   weight_state_terminal=list(r["weight_state_terminal"]),
-                                   target_action_norm=list(r["target_action"]), weight_action=list(r["weight_action"]),
-                                   exploration_factor=r["exploration_factor"]),
-        actions_config=ActionsConfig(), controller_config=ControllerConfig(len_horizon=H),
-        model_config=ModelConfig(gp_init={"noise_covar.noise": list(cfg["noise"]),
-                                          "base_kernel.lengthscale": [list(v) for v in cfg["lengthscale"]],
-                                          "outputscale": list(cfg["outputscale"])},
-                                 min_std_noise=1e-4, max_std_noise=1.0, min_outputscale=1e-6, max_outputscale=10.0,
-                                 min_lengthscale=1e-3, max_lengthscale=1e3))
-    ctrl = GpMpcController(-np.ones(E), np.ones(E), -np.ones(Na), np.ones(Na), config, device=dev)
+
+    def make_controller(c):
+        """The product's public object for this path: GpMpcController; with more than one rank it shards the candidate
+        batch over the process group itself (rl_gp_mpc/parallel.py): contiguous slices, ONE in-place all-gather of costs."""
+        r = c["reward"]
+        config = Config(
+            observation_config=ObservationConfig(obs_var_norm=[c["obs_var"]] * E),
+            reward_config=RewardConfig(target_state_norm=list(r["target_state"]), weight_state=list(r["weight_state"]),
+                                       weight_state_terminal=list(r["weight_state_terminal"]),
+                                       target_action_norm=list(r["target_action"]), weight_action=list(r["weight_action"]),
+                                       exploration_factor=r["exploration_factor"]),
+            actions_config=ActionsConfig(), controller_config=ControllerConfig(len_horizon=H),
+            model_config=ModelConfig(gp_init={"noise_covar.noise": list(c["noise"]),
+                                              "base_kernel.lengthscale": [list(v) for v in c["lengthscale"]],
+                                              "outputscale": list(c["outputscale"])},
+                                     min_std_noise=1e-4, max_std_noise=1.0, min_outputscale=1e-6, max_outputscale=10.0,
+                                     min_lengthscale=1e-3, max_lengthscale=1e3))
+        return GpMpcController(-np.ones(E), np.ones(E), -np.ones(Na), np.ones(Na), config, device=dev,
+                               process_group=True if world > 1 else None)
+
+    ctrl = make_controller(cfg)
     tm = ctrl.transition_model
     t0 = time.perf_counter()
     tm.prepare_inference(torch.as_tensor(cfg["x"]), torch.as_tensor(cfg["y"]))
@@ -289,36 +305,20 @@ def main():
     tm.incremental_updates = False
     tm.prepare_inference(torch.as_tensor(cfg["x"]), torch.as_tensor(cfg["y"]))
     tm.incremental_updates = True
-    eng = tm.engine
-    eng.enable_timing(True)
     obs_mu, obs_var = torch.as_tensor(cfg["mu0"]), torch.as_tensor(cfg["Sigma0"])
-    actions_host = torch.as_tensor(cfg["actions"][lo:hi].reshape(Bl, H * Na)).pin_memory()
+    actions_host = torch.as_tensor(cfg["actions"].reshape(B, H * Na)).pin_memory()   # the whole batch, on every rank
     actions_dev = actions_host.to(dev)
     mu_dev, var_dev = obs_mu.to(dev), obs_var.to(dev)
     flush = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device=dev)   # 256 MB > 126 MB L2
-    costs_all = torch.empty(per * world, dtype=torch.float64, device=dev)
-    out = {"cost": costs_all[rank * per: rank * per + Bl]}                   # all-gather in place (no copy)
+    lo, hi = ctrl.sharder.bounds(B) if ctrl.sharder is not None else (0, B)
+    Bl = hi - lo
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(need_grad):
-        ctrl._bind_cost()
-        eng.rollout(actions_dev, mu_dev, var_dev, H, need_grad=need_grad, need_traj=False, out=out)
-        if dist is not None:
-            allgather_costs(dist, costs_all, per, rank)
-
-    def step_e2e():
-        a = actions_host.to(dev, non_blocking=True)
-        costs, grads = ctrl.compute_mean_lcb_trajectory_batch(a, obs_mu, obs_var, need_grad=True)
-        if dist is not None:
-            costs_all[rank * per: rank * per + Bl].copy_(costs)
-            allgather_costs(dist, costs_all, per, rank)
-        return costs.cpu(), grads.cpu()
-
-    def timed(fn, steps, kernel_times=None):
+    def timed(fn, steps, kernel_times=None, eng=None):
         """K steps between barriers + syncs; device time by CUDA events on the launching stream; max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -336,33 +336,62 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    launches0 = None
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
-        step_device(True)
+    def measure(c, steps, warmup, e2e=True):
+        """value (device-resident inputs), forward_only and e2e (host buffers) of one controller, all through
+        GpMpcController.compute_mean_lcb_trajectory_batch: with several ranks every call shards the batch, scores the
+        rank's slice and all-gathers the costs in place (NCCL) inside the timed region."""
+        eng = c.transition_model.engine
+        eng.enable_timing(True)
+        last = {}
+
+        def step_device(need_grad):
+            costs, _ = c.compute_mean_lcb_trajectory_batch(actions_dev, mu_dev, var_dev, need_grad=need_grad, need_traj=False)
+            last["costs"] = costs
+
+        def step_e2e():
+            costs, grads = c.compute_mean_lcb_trajectory_batch(actions_host, obs_mu, obs_var, need_grad=True, need_traj=False)
+            return costs.cpu(), grads.cpu()
+
+        for _ in range(max(warmup, 3)):
+            step_device(True)
+            flush.zero_()
+        step_device(False)
+        if e2e:
+            step_e2e()
+        barrier()
+        ktimes = []
+        launches0 = eng.launch_count()
         flush.zero_()
-    step_device(False)
-    step_e2e()
-    barrier()
+        ms_total = timed(lambda: step_device(True), steps, ktimes, eng)
+        launches = eng.launch_count() - launches0
+        costs = last["costs"].clone()
+        flush.zero_()
+        ms_fwd = timed(lambda: step_device(False), steps)
+        ms_e2e = None
+        if e2e:
+            flush.zero_()
+            ms_e2e = timed(step_e2e, steps)
+        return {"ms_total": ms_total, "ms_fwd": ms_fwd, "ms_e2e": ms_e2e, "launches": int(launches),
+                "fwd_ms": float(np.mean([k[0] for k in ktimes])), "bwd_ms": float(np.mean([k[1] for k in ktimes])),
+                "uniform": eng.uses_uniform_path(), "costs": costs}
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    # warm-up of everything happens inside measure(); the clock sampler covers the timed regions of the headline arm
     if sampler:
         sampler.start()
-    # ---- timed: fwd+grad on device-resident inputs (the `value`)
-    ktimes = []
-    launches0 = eng.launch_count()
-    flush.zero_()
-    ms_total = timed(lambda: step_device(True), args.steps, ktimes)
-    launches = eng.launch_count() - launches0
-    flush.zero_()
-    ms_fwd = timed(lambda: step_device(False), args.steps)
-    flush.zero_()
-    ms_e2e = timed(step_e2e, args.steps)
+    m = measure(ctrl, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
+    # ---- the same workload with per-GP ("trained") hyper-parameters: the general kernel path every control step takes
+    #      after the first hyper-parameter fit (reference gp_mpc_controller.py:197-199, 216-227)
+    mg = None
+    if not args.distinct_lengthscales and not args.no_general_path:
+        cfg_g = make_workload(args.workload, B=args.batch, H=args.horizon, distinct_lengthscales=True)
+        ctrl_g = make_controller(cfg_g)
+        ctrl_g.transition_model.prepare_inference(torch.as_tensor(cfg_g["x"]), torch.as_tensor(cfg_g["y"]))
+        mg = measure(ctrl_g, min(args.steps, 3), 3, e2e=False)
     preds = B * H
-    value = preds * args.steps / (ms_total * 1e-3)
+    value = preds * args.steps / (m["ms_total"] * 1e-3)
     if rank == 0:
-        fwd_ms = float(np.mean([k[0] for k in ktimes]))
-        bwd_ms = float(np.mean([k[1] for k in ktimes]))
         hbm_peak, peak_src = 6650.0, "fallback"
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -372,40 +401,87 @@ def main():
         b_alg = algorithmic_bytes_per_prediction(E, D, N, 8)
         f_alg = algorithmic_flops_per_prediction(E, D, N)
         preds_rank0 = Bl * H
-        achieved = preds_rank0 * b_alg / (fwd_ms * 1e-3) / 1e9
-        fp64_peak = _cabi.measure_fp64_peak(local_rank)
-        uniform = eng.uses_uniform_path()
-        kname = ("gpmpc::uniform_fwd_kernel<%d> (one exp per (i,j) for all output pairs)" % E) if uniform else \
-            ("gpmpc::rollout_kernel<%d,true> (per-pair sweep + forward-mode Jacobian records)" % E)
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": ncu_traffic("uniform_fwd" if uniform else "rollout_kernel", "%s B=%d H=%d" % (cfg["name"], Bl, H)),
-                    "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                    "kernel": "%s, %.2f ms/launch for %d predictions" % (kname, fwd_ms, preds_rank0),
-                    "reverse_sweep_kernel": ("gpmpc::uniform_bwd_kernel<%d> (adjoint-weighted upper-triangle N^2 sweep), "
-                                             "%.2f ms/launch" % (E, bwd_ms)) if uniform else
-                    ("gpmpc::backward_kernel<%d> (small-matrix algebra on records), %.2f ms/launch" % (E, bwd_ms)),
-                    "algorithmic_bytes_per_prediction": b_alg,
-                    "note": "algorithmic bytes (SURVEY 8(d): 8*(E N^2 + E N + N D) per prediction) are served from L2/L1/"
-                            "shared memory -- the training block is shared by all candidates (`traffic` = DRAM bytes per launch "
-                            "from ncu, mostly the per-step records and outputs) -- so frac>1 is expected; the binding roofline is float64 FMA "
-                            "throughput (fp64 block)",
-                    "fp64": fp64_report(uniform, E, N, preds_rank0, fwd_ms, bwd_ms, f_alg, fp64_peak)}
+        fp64_peak = _cabi.measure_fp64_peak(local_rank)          # flop/s of a register-resident DFMA loop
+        counts = sass_counts(E)
+
+        def kernel_block(name, kernel, ms):
+            """Float64-pipe roofline of one kernel: executed float64 instructions (SASS count x swept elements) per second
+            against the measured DFMA issue rate (one DFMA per lane = 2 flop)."""
+            instr = fp64_model(kernel, E, N, counts)             # per prediction (thread-level instructions)
+            ach = 2.0 * instr * preds_rank0 / (ms * 1e-3)
+            return {"kernel": name, "ms_per_launch": ms, "float64_instructions_per_prediction": instr,
+                    "achieved_tflops": ach / 1e12, "frac": ach / fp64_peak}
+
+        if m["uniform"]:
+            kf = kernel_block("gpmpc::uniform_fwd_kernel<%d> (forward sweep, one exp per (i,j) for all output pairs)" % E,
+                              "uniform_fwd", m["fwd_ms"])
+            kb = kernel_block("gpmpc::uniform_bwd_kernel<%d> (reverse sweep: adjoint-weighted upper-triangle N^2 sweep)" % E,
+                              "uniform_bwd", m["bwd_ms"])
+            dom = kb if m["bwd_ms"] >= m["fwd_ms"] else kf
+            kernels = [kf, kb]
+        else:
+            dom = kernel_block("gpmpc::rollout_kernel<%d,true> (per-pair sweep + forward-mode Jacobian sums)" % E,
+                               "general_grad", m["fwd_ms"])
+            kernels = [dom]
+        # bytes the kernels read per prediction from L2 (iK triangle once per uniform sweep / per diagonal pair)
+        el = sweep_elements(m["uniform"], E, N)
+        l2_bytes = 8.0 * (el["triangle"] if m["uniform"] else el["diagonal"])
+        roofline = {
+            "bound": "fp64", "unit": "TFLOP/s", "achieved": dom["achieved_tflops"], "peak": fp64_peak / 1e12,
+            "frac": dom["frac"], "kernel": dom["kernel"], "ms_per_launch": dom["ms_per_launch"],
+            "float64_instructions_per_prediction": dom["float64_instructions_per_prediction"],
+            "predictions_per_launch": preds_rank0,
+            "how": "achieved = 2 flop x float64_instructions_per_prediction x predictions_per_launch / ms_per_launch; the "
+                   "instruction count = (float64 instructions per (i,j) element of the kernel's hot loop, counted in the SASS of "
+                   "the built library) x (elements one prediction sweeps); peak = DFMA issue rate measured on this GPU by "
+                   "gpmpc_fp64_peak (register-resident FMA loop; MEASURED_PEAKS.json carries no float64 figure).  NB: B200 "
+                   "issues a DFMA with three distinct register operands at 2/3 of that rate and the sweeps are issue-bound "
+                   "(float64 = 2 issue slots, every other instruction = 1): profiles/r02_micro_*.txt",
+            "sass_counts": counts, "kernels": kernels,
+            "traffic": ncu_traffic("uniform_bwd" if m["uniform"] else "rollout_kernel", "%s B=%d H=%d" % (cfg["name"], Bl, H)),
+            "l2_read_gbs": l2_bytes * preds_rank0 / (kernels[0]["ms_per_launch"] * 1e-3) / 1e9,
+            "hbm_model": {"algorithmic_bytes_per_prediction": b_alg,
+                          "algorithmic_gbs": preds_rank0 * b_alg / (kernels[0]["ms_per_launch"] * 1e-3) / 1e9,
+                          "peak_gbs": hbm_peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                          "note": "SURVEY 8(d)'s per-prediction streaming model (8 (E N^2 + E N + N D) bytes): NOT the bound here -- "
+                                  "the training block is identical for all candidates and stays in L2 / shared memory, DRAM sees "
+                                  "only the per-step records and outputs (`traffic`, ncu dram bytes per launch), so this figure "
+                                  "exceeds the HBM peak by design; `l2_read_gbs` is what the forward kernel pulls from L2 (iK)"},
+            "algorithmic_flops_per_prediction": f_alg}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "warmup": max(args.warmup, 3), "ms_per_step": m["ms_total"] / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(cfg, args),
-                "forward_only": {"value": preds * args.steps / (ms_fwd * 1e-3), "unit": UNIT,
-                                 "ms_per_step": ms_fwd / args.steps},
-                "kernel_path": "uniform (all GPs share their hyper-parameters)" if uniform else "general (per-pair)",
-                "kernel_ms": {"rollout_fwd": fwd_ms, "reverse_sweep": bwd_ms},
+                "forward_only": {"value": preds * args.steps / (m["ms_fwd"] * 1e-3), "unit": UNIT,
+                                 "ms_per_step": m["ms_fwd"] / args.steps},
+                "kernel_path": "uniform (all GPs share their hyper-parameters)" if m["uniform"] else "general (per-pair)",
+                "kernel_ms": {"rollout_fwd": m["fwd_ms"], "reverse_sweep": m["bwd_ms"]},
                 "prepare_ms": {"first_call": prepare_ms_first, "steady": prepare_ms, "append_one_point": append_ms,
                                "what": "Gram + Cholesky + iK + beta for %d GPs, N=%d (once per control step); "
                                        "append_one_point = gpmpc_append through prepare_inference when the memory grew by one" % (E, N)},
-                "e2e": {"value": preds * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": int(actions_host.numel() * 8 * world),
-                        "d2h_bytes_per_step": int((Bl + Bl * H * Na) * 8 * world),
+                "e2e": {"value": preds * args.steps / (m["ms_e2e"] * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(B * H * Na * 8),
+                        "d2h_bytes_per_step": int((B * world + B * H * Na) * 8),
                         "api": "GpMpcController.compute_mean_lcb_trajectory_batch (pinned host actions in, costs+grads out)"},
-                "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+                "gpu_launches": m["launches"], "roofline": roofline, "clocks": clocks,
+                # the same answer whatever the number of GPUs: sum and arg-min of the B gathered costs
+                "cost_checksum": float("%.9g" % float(m["costs"].sum().item())),
+                "cost_argmin": int(torch.argmin(torch.nan_to_num(m["costs"], nan=float("inf"))).item())}
+        if mg is not None:
+            kg = None
+            instr_g = fp64_model("general_grad", E, N, counts)
+            ach_g = 2.0 * instr_g * preds_rank0 / (mg["fwd_ms"] * 1e-3)
+            st = min(args.steps, 3)
+            line["general_path"] = {
+                "what": "same workload, distinct per-GP hyper-parameters (what every control step runs after the first "
+                        "hyper-parameter fit): gpmpc::rollout_kernel<%d,true> + backward_kernel" % E,
+                "value": preds * st / (mg["ms_total"] * 1e-3), "unit": UNIT, "steps": st,
+                "forward_only": preds * st / (mg["ms_fwd"] * 1e-3),
+                "kernel_ms": {"rollout_fwd": mg["fwd_ms"], "reverse_sweep": mg["bwd_ms"]},
+                "float64_instructions_per_prediction": instr_g, "executed_frac": ach_g / fp64_peak,
+                "ceiling_predictions_per_s": world * (fp64_peak / 2.0) / instr_g,
+                "ceiling_note": "float64 instructions of the hot loops alone at the measured DFMA issue rate",
+                "cost_checksum": float("%.9g" % float(mg["costs"].sum().item()))}
         if not args.no_cpu_baseline:
             rate, dt = cpu_port_rate(cfg, min(16, B), H)      # ~10-15 s of host work at the headline shape
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

@@ -40,6 +40,9 @@ constexpr int EXP2S_N = 1 << EXP2S_LOG;
 // -- two integer instructions per exp instead of three with a run-time table base (the sweeps are issue-bound, every
 // instruction counts: profiles/r02_micro_gen_loop.txt).  exp2s_fill checks the assumed offset at kernel start (trap).
 #define GPMPC_SS_OFFSET 1024
+#ifndef GPMPC_EXP2S_IMM_OFFSET
+#define GPMPC_EXP2S_IMM_OFFSET 1
+#endif
 struct __align__(16) GpmpcStaticSmem {
   double tab[EXP2S_N];      // 2^(j/2048), pre-biased (gpmpc_api.cu)
   double one;               // the constant 1.0 (rollout_kernel: stride-0 factor of the moment sums)
@@ -59,10 +62,16 @@ __device__ __forceinline__ double exp2s_clamp(double t2) {
 // The table is stored PRE-BIASED: entry j holds the bit pattern of 2^(j/2048) with (j << 9) subtracted from its high
 // word (gpmpc_api.cu).  Adding (n << 9) = ((n >> 11) << 20) + ((n & 2047) << 9) to the high word of entry n & 2047 then
 // restores the mantissa AND applies 2^(n >> 11) through the exponent field in ONE integer instruction (no masks).
+template <bool IMM = true>
 __device__ __forceinline__ double exp2s_entry(int n) {   // 2^(n / 2048)
-  const unsigned rank_bits = (unsigned)__cvta_generic_to_shared(&gpmpc_ss) - GPMPC_SS_OFFSET;   // loop invariant (r << 24)
   double raw;
-  asm("ld.shared.f64 %0, [%1 + 1024];" : "=d"(raw) : "r"(((n << 3) & (8 * EXP2S_N - 8)) | rank_bits));
+  if (IMM && GPMPC_EXP2S_IMM_OFFSET) {
+    const unsigned rank_bits = (unsigned)__cvta_generic_to_shared(&gpmpc_ss) - GPMPC_SS_OFFSET;   // loop invariant (r << 24)
+    asm("ld.shared.f64 %0, [%1 + 1024];" : "=d"(raw) : "r"(((n << 3) & (8 * EXP2S_N - 8)) | rank_bits));
+  } else {   // run-time base, three integer instructions (measured 2 % faster in the uniform reverse sweep, 3 % slower elsewhere:
+             // profiles/r02e_table_addressing.txt)
+    asm("ld.shared.f64 %0, [%1];" : "=d"(raw) : "r"((unsigned)__cvta_generic_to_shared(&gpmpc_ss) + ((n << 3) & (8 * EXP2S_N - 8))));
+  }
   return __hiloint2double(__double2hiint(raw) + (n << (20 - EXP2S_LOG)), __double2loint(raw));
 }
 
@@ -81,6 +90,7 @@ __device__ __forceinline__ double exp2s(double t2) {
 }
 
 // Four at once, stage by stage (4 independent float64 operations per stage).
+template <bool IMM = true>
 __device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4]) {
   const double SHIFT = 6755399441055744.0;
   double x[4], kd[4], f[4], p[4], t[4];
@@ -92,7 +102,7 @@ __device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4
 #pragma unroll
   for (int c = 0; c < 4; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }   // (an I2F.F64 instead of this add is slower)
 #pragma unroll
-  for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_entry(n[c]); }
+  for (int c = 0; c < 4; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_entry<IMM>(n[c]); }
 #pragma unroll
   for (int c = 0; c < 4; c++) p[c] = __fma_rn(GPMPC_EXP2S_C3, f[c], GPMPC_EXP2S_C2);
 #pragma unroll

@@ -10,14 +10,15 @@ class ControllerConfig:
     def __init__(self, len_horizon: int = 15, actions_optimizer_params: dict = None,
                  init_from_previous_actions: bool = True, restarts_optim: int = 1, optimize: bool = True,
                  num_repeat_actions: int = 1, batched_candidates: int = 0, batched_iters: int = 30,
-                 batched_lr: float = 0.05, batched_method: str = "lbfgs"):
+                 batched_lr: float = 0.05, batched_method: str = "lbfgs", batched_seed: int = None):
         """len_horizon: MPC steps; actions_optimizer_params: scipy L-BFGS-B options; init_from_previous_actions:
         warm start from the shifted previous solution; restarts_optim: optimiser restarts; optimize: False =
         random actions (debug); num_repeat_actions: each action is held this many env steps.
         NEW (additive, default off): batched_candidates > 0 replaces the serial scipy restarts by that many candidate
         sequences optimised simultaneously on the device, every objective/gradient evaluation being ONE batched rollout
         (SURVEY.md section 8(f) N1): batched_method "lbfgs" = projected L-BFGS (batched_iters + 1 evaluations),
-        "adam" = projected Adam (batched_iters steps of size batched_lr, + 1 value-only evaluation)."""
+        "adam" = projected Adam (batched_iters steps of size batched_lr, + 1 value-only evaluation); batched_seed: seed of
+        the controller's own generator of the random restarts (None: drawn once; with a process group rank 0's is used)."""
         self.len_horizon = len_horizon
         self.actions_optimizer_params = dict(_DEFAULT_OPTIMIZER_PARAMS) if actions_optimizer_params is None \
             else actions_optimizer_params
@@ -28,6 +29,7 @@ class ControllerConfig:
         self.batched_candidates = batched_candidates
         self.batched_iters = batched_iters
         self.batched_lr = batched_lr
+        self.batched_seed = batched_seed
         if batched_method not in ("lbfgs", "adam"):
             raise ValueError("batched_method must be 'lbfgs' or 'adam'")
         self.batched_method = batched_method

@@ -91,7 +91,9 @@ def minimize_box_lbfgs(fun, x0, iters, history=8, c1=1e-4, shrink=0.25, max_firs
         xt = (x + a_eff[:, None] * d).clamp_(0.0, 1.0)
         ft, gt = _clean(*fun(xt))
         step = xt - x
-        ok = torch.isfinite(ft) & (ft <= f + c1 * (gf * step).sum(1)) & (step.abs().amax(1) > 0)
+        # Armijo test on the projected step; the directional term is capped at 0: when the clamp removes components of d,
+        # gf . step can be positive, and a trial with ft > f must never be accepted (the returned point is the best seen)
+        ok = torch.isfinite(ft) & (ft <= f + c1 * (gf * step).sum(1).clamp_max(0.0)) & (step.abs().amax(1) > 0)
         s_new = torch.where(ok[:, None], step, torch.zeros_like(step))
         y_new = torch.where(ok[:, None], gt - g, torch.zeros_like(step))
         sy = (s_new * y_new).sum(1)

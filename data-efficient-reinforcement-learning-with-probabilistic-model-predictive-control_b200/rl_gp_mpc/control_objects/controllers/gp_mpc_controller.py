@@ -321,14 +321,16 @@ class GpMpcController(BaseControllerObject):
 
     @staticmethod
     def _cost_fingerprint(r):
-        def flat(v):
-            return tuple(np.asarray(torch.as_tensor(v).detach().cpu(), dtype=np.float64).reshape(-1).tolist())
+        """Cheap key of everything set_cost uploads: tensors by (identity, in-place version counter), the rest by value."""
         parts = [id(r)]
         for name in ("target_state_action_norm", "weight_matrix_cost", "weight_matrix_cost_terminal", "state_min",
                      "state_max", "target_state_norm", "target_action_norm", "weight_state", "weight_action",
                      "weight_state_terminal"):
-            if hasattr(r, name) and getattr(r, name) is not None:
-                parts.append(flat(getattr(r, name)))
+            v = getattr(r, name, None)
+            if torch.is_tensor(v):
+                parts.append((id(v), v._version))
+            elif v is not None:
+                parts.append(tuple(np.asarray(v, dtype=np.float64).reshape(-1).tolist()))
         for name in ("exploration_factor", "use_constraints", "clip_lower_bound_cost_to_0", "area_multiplier"):
             parts.append(getattr(r, name, None))
         return tuple(parts)

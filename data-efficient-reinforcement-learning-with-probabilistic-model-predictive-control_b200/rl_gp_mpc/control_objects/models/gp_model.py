@@ -151,10 +151,18 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
         self.y_mem = state_changes
         self.lengthscales, self.variances = ls, s2
         if can_append:
-            for i in range(n_old, n_old + n_new):
-                self.engine.append(inputs[i], state_changes[i])
-            self.last_prepare_mode = "append"
-        else:
+            try:
+                for i in range(n_old, n_old + n_new):
+                    self.engine.append(inputs[i], state_changes[i])
+                if self.engine.N != len(inputs):
+                    raise RuntimeError("engine holds %d points after the appends, expected %d" % (self.engine.N, len(inputs)))
+                self.last_prepare_mode = "append"
+            except Exception:
+                # a failed append (Schur complement not positive, CUDA error) leaves the engine with SOME of the new rows:
+                # forget the cached training set (so that a retry cannot append the same rows twice) and refactorise
+                self._prep_x = self._prep_y = self._prep_hyp = None
+                can_append = False
+        if not can_append:
             self.engine.prepare(inputs, state_changes, ls, s2, noise)
             self.last_prepare_mode = "full"
         self._prep_x = torch.as_tensor(inputs, dtype=torch.float64).cpu().clone()
@@ -214,21 +222,27 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
 
     @staticmethod
     def train(queue, saved_state, lr_train, num_iter_train, clip_grad_value, print_train=False, step_print_train=25,
-              device=None, stop_event=None):
+              device=None, stop_event=None, lockstep=True):
         """Hyper-parameter fitting with the reference's procedure (gp_model.py:193-306): for every GP, uniform random
         re-initialisation inside the Interval bounds, torch LBFGS (strong Wolfe) on the unconstrained parameters,
         keep the best negative marginal log-likelihood (per data point, as gpytorch's ExactMarginalLogLikelihood
         reports it) and fall back to the previous hyper-parameters when nothing better is found.  The objective and
         its gradient come from the device (gpmpc_prepare + gpmpc_mll: Gram, Cholesky, K^-1, 1/2 tr((aa^T-K^-1) dK));
         only the O(D) optimiser state lives on the host.  The result goes to `queue` as a list of
-        {'covar_module.base_kernel.lengthscale', 'covar_module.outputscale', 'likelihood.noise'} dicts."""
+        {'covar_module.base_kernel.lengthscale', 'covar_module.outputscale', 'likelihood.noise'} dicts.
+
+        lockstep (default): the E fits run as E host threads whose objective evaluations are BATCHED -- every round, the
+        trial hyper-parameters of all GPs still fitting go to the device in ONE gpmpc_prepare + gpmpc_mll (the engine
+        factorises E GPs at once; a GP that is waiting or done rides along with its last values).  Each GP sees exactly the
+        evaluations its own LBFGS asks for, so the result equals the serial procedure's (lockstep=False: one GP after
+        the other, E times as many device calls)."""
+        import threading
         import time
         t0 = time.time()
         saved_state.to_tensors()
         x = torch.as_tensor(saved_state.inputs, dtype=torch.float64)
         y_all = torch.as_tensor(saved_state.states_change, dtype=torch.float64)
         cons = saved_state.constraints_hyperparams
-        params_out = []
         try:
             engine = _cabi.Engine(device)
         except Exception as exc:                       # no device / no library: keep the current hyper-parameters
@@ -236,6 +250,7 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
             queue.put([{k: np.asarray(v) for k, v in p.items()} for p in saved_state.parameters])
             return
         n, d = x.shape
+        n_gp = len(saved_state.parameters)
 
         def bounds(idx):
             lo = torch.cat([torch.as_tensor(cons["min_lengthscale"], dtype=torch.float64)[idx].reshape(-1),
@@ -246,66 +261,157 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
                             torch.as_tensor(cons["max_std_noise"], dtype=torch.float64)[idx].reshape(1) ** 2])
             return lo, hi
 
-        class _NegMll(torch.autograd.Function):
-            @staticmethod
-            def forward(ctx, theta, y_col):            # theta = [lengthscale (D), outputscale, noise] constrained
-                if stop_event is not None and stop_event.is_set():
-                    raise InterruptedError("training stopped")
-                engine.prepare(x, y_col, theta[:d].reshape(1, d), theta[d:d + 1], theta[d + 1:d + 2])
-                out = engine.mll(y_col)[0].cpu()
-                grad = torch.cat([out[3:3 + d], out[1:3]])
-                ctx.save_for_backward(-grad / n)
-                return -out[0] / n
-
-            @staticmethod
-            def backward(ctx, g):
-                return g * ctx.saved_tensors[0], None
-
-        for idx, prev in enumerate(saved_state.parameters):
+        def eval_one(idx, theta):
+            """-LML / n and its gradient w.r.t. theta = [lengthscale (D), outputscale, noise] of GP idx alone."""
             y_col = y_all[:, idx:idx + 1].contiguous()
-            lo, hi = bounds(idx)
-            prev_theta = torch.cat([torch.as_tensor(prev["covar_module.base_kernel.lengthscale"], dtype=torch.float64).reshape(-1),
-                                    torch.as_tensor(prev["covar_module.outputscale"], dtype=torch.float64).reshape(1),
-                                    torch.as_tensor(prev["likelihood.noise"], dtype=torch.float64).reshape(1)])
-            best_theta = prev_theta.clone()
+            engine.prepare(x, y_col, theta[:d].reshape(1, d), theta[d:d + 1], theta[d + 1:d + 2])
+            out = engine.mll(y_col)[0].cpu()
+            return -out[0] / n, -torch.cat([out[3:3 + d], out[1:3]]) / n
+
+        def eval_all(thetas, want):
+            """One device round for all GPs (rows of `thetas`); falls back to GP-by-GP calls when the joint factorisation
+            fails (a trial point of ONE GP with a non positive definite kernel matrix must not hurt the others)."""
             try:
-                best_loss = float(_NegMll.apply(prev_theta, y_col))
-            except InterruptedError:
-                break
+                th = torch.stack(thetas)
+                engine.prepare(x, y_all, th[:, :d], th[:, d], th[:, d + 1])
+                out = engine.mll(y_all).cpu()
+                return {i: (-out[i, 0] / n, -torch.cat([out[i, 3:3 + d], out[i, 1:3]]) / n) for i in want}
             except Exception:
-                best_loss = float("inf")
-            prev_loss = best_loss
-            start = lo + torch.rand(d + 2, dtype=torch.float64) * (hi - lo)          # random restart (:229-247)
-            p0 = ((start - lo) / (hi - lo)).clamp(1e-6, 1 - 1e-6)
-            raw = (torch.log(p0) - torch.log1p(-p0)).requires_grad_(True)
-            opt = torch.optim.LBFGS([raw], lr=lr_train, line_search_fn="strong_wolfe")
+                res = {}
+                for i in want:
+                    try:
+                        res[i] = eval_one(i, thetas[i])
+                    except Exception as exc:      # noqa: BLE001 -- handed to the GP's own thread
+                        res[i] = exc
+                return res
+
+        class _Lockstep:
+            """Rendez-vous of the fitting threads: the last one to arrive runs the batched evaluation for everybody."""
+            def __init__(self, thetas0):
+                self.cv = threading.Condition()
+                self.active = set(range(n_gp))
+                self.pending, self.results, self.round = {}, {}, 0
+                self.last = [t.clone() for t in thetas0]
+
+            def _run(self):                       # lock held; every other active thread is waiting
+                thetas = [self.pending.get(i, self.last[i]).detach() for i in range(n_gp)]
+                out = eval_all(thetas, list(self.pending))
+                for i in list(self.pending):
+                    self.results[i] = out[i]
+                    if not isinstance(out[i], Exception):
+                        self.last[i] = thetas[i].clone()
+                self.pending.clear()
+                self.round += 1
+                self.cv.notify_all()
+
+            def evaluate(self, idx, theta):
+                with self.cv:
+                    self.pending[idx] = theta
+                    rnd = self.round
+                    if set(self.pending) >= self.active:
+                        self._run()
+                    else:
+                        while self.round == rnd:
+                            self.cv.wait()
+                    res = self.results.pop(idx)
+                if isinstance(res, Exception):
+                    raise res
+                return res
+
+            def finish(self, idx):
+                with self.cv:
+                    self.active.discard(idx)
+                    if self.pending and set(self.pending) >= self.active:
+                        self._run()
+
+        prev_thetas = [torch.cat([torch.as_tensor(p["covar_module.base_kernel.lengthscale"], dtype=torch.float64).reshape(-1),
+                                  torch.as_tensor(p["covar_module.outputscale"], dtype=torch.float64).reshape(1),
+                                  torch.as_tensor(p["likelihood.noise"], dtype=torch.float64).reshape(1)])
+                       for p in saved_state.parameters]
+        starts = [torch.rand(d + 2, dtype=torch.float64) for _ in range(n_gp)]       # random restarts (:229-247)
+        sync = _Lockstep(prev_thetas) if (lockstep and n_gp > 1) else None
+        results = [None] * n_gp
+
+        def fit(idx):
+            evaluate = (lambda th: sync.evaluate(idx, th)) if sync is not None else (lambda th: eval_one(idx, th))
+
+            class _NegMll(torch.autograd.Function):
+                @staticmethod
+                def forward(ctx, theta):
+                    if stop_event is not None and stop_event.is_set():
+                        raise InterruptedError("training stopped")
+                    loss, grad = evaluate(theta.detach())
+                    ctx.save_for_backward(grad)
+                    return loss
+
+                @staticmethod
+                def backward(ctx, g):
+                    return g * ctx.saved_tensors[0]
+
+            lo, hi = bounds(idx)
+            prev_theta = prev_thetas[idx]
+            best_theta = prev_theta.clone()
+            stopped = False
             try:
-                for it in range(num_iter_train):
-                    def closure():
-                        opt.zero_grad()
-                        theta = lo + (hi - lo) * torch.sigmoid(raw)
-                        loss = _NegMll.apply(theta, y_col)
-                        loss.backward()
-                        if print_train and it % step_print_train == 0:
-                            print("Iter %d/%d - Loss: %.5f" % (it + 1, num_iter_train, loss.item()))
-                        return loss
-                    loss = float(opt.step(closure))
-                    if loss < best_loss:
-                        best_loss = loss
-                        best_theta = (lo + (hi - lo) * torch.sigmoid(raw)).detach().clone()
-            except InterruptedError:                   # controller shut down: hand back what is there
-                break
-            except Exception as exc:                   # e.g. a trial point with a non positive definite kernel matrix
-                print(exc)
-            print("training - model %d - time %.2f s - loss %.5f -> %.5f - outputscale %s - lengthscales %s - noise %s" % (
-                idx, time.time() - t0, prev_loss, best_loss, best_theta[d].numpy(), best_theta[:d].numpy(),
-                best_theta[d + 1].numpy()))
-            params_out.append({"covar_module.base_kernel.lengthscale": best_theta[:d].reshape(1, d).numpy(),
-                               "covar_module.outputscale": best_theta[d].reshape(()).numpy(),
-                               "likelihood.noise": best_theta[d + 1].reshape(1).numpy()})
-        for prev in saved_state.parameters[len(params_out):]:      # stopped early: the remaining GPs keep their values
-            params_out.append({k: np.asarray(v) for k, v in prev.items()})
-        queue.put(params_out)
+                try:
+                    best_loss = float(_NegMll.apply(prev_theta))
+                except InterruptedError:
+                    raise
+                except Exception:
+                    best_loss = float("inf")
+                prev_loss = best_loss
+                start = lo + starts[idx] * (hi - lo)
+                p0 = ((start - lo) / (hi - lo)).clamp(1e-6, 1 - 1e-6)
+                raw = (torch.log(p0) - torch.log1p(-p0)).requires_grad_(True)
+                opt = torch.optim.LBFGS([raw], lr=lr_train, line_search_fn="strong_wolfe")
+                try:
+                    for it in range(num_iter_train):
+                        def closure():
+                            opt.zero_grad()
+                            theta = lo + (hi - lo) * torch.sigmoid(raw)
+                            loss = _NegMll.apply(theta)
+                            loss.backward()
+                            if print_train and it % step_print_train == 0:
+                                print("Iter %d/%d - Loss: %.5f" % (it + 1, num_iter_train, loss.item()))
+                            return loss
+                        loss = float(opt.step(closure))
+                        if loss < best_loss:
+                            best_loss = loss
+                            best_theta = (lo + (hi - lo) * torch.sigmoid(raw)).detach().clone()
+                except InterruptedError:
+                    raise
+                except Exception as exc:               # e.g. a trial point with a non positive definite kernel matrix
+                    print(exc)
+                print("training - model %d - time %.2f s - loss %.5f -> %.5f - outputscale %s - lengthscales %s - noise %s" % (
+                    idx, time.time() - t0, prev_loss, best_loss, best_theta[d].numpy(), best_theta[:d].numpy(),
+                    best_theta[d + 1].numpy()))
+            except InterruptedError:                   # controller shut down: this GP keeps what it has
+                stopped = True
+            finally:
+                if sync is not None:
+                    sync.finish(idx)
+            if stopped and torch.equal(best_theta, prev_theta):
+                results[idx] = {k: np.asarray(v) for k, v in saved_state.parameters[idx].items()}
+            else:
+                results[idx] = {"covar_module.base_kernel.lengthscale": best_theta[:d].reshape(1, d).numpy(),
+                                "covar_module.outputscale": best_theta[d].reshape(()).numpy(),
+                                "likelihood.noise": best_theta[d + 1].reshape(1).numpy()}
+
+        if sync is not None:
+            threads = [threading.Thread(target=fit, args=(i,), daemon=True) for i in range(n_gp)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        else:
+            for i in range(n_gp):
+                fit(i)
+                if stop_event is not None and stop_event.is_set():
+                    break
+        for i in range(n_gp):
+            if results[i] is None:
+                results[i] = {k: np.asarray(v) for k, v in saved_state.parameters[i].items()}
+        queue.put(results)
 
     def save_state(self):
         return SavedState(inputs=self.x_mem, states_change=self.y_mem,

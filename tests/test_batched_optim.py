@@ -134,7 +134,7 @@ def test_controller_batched_path_with_a_stand_in_engine():
                                                         batched_method=method))
         c = GpMpcController(-np.ones(E), np.ones(E), -np.ones(Na), np.ones(Na), cfg)
         c.transition_model._engine = FakeEngine()
-        c._cost_bound, c.transition_model._cost_key = True, id(cfg.reward)
+        c._cost_bound, c._cost_key_values = True, c._cost_fingerprint(cfg.reward)
         FakeEngine.calls = 0
         torch.manual_seed(0)
         act = c._get_optimal_actions_batched(torch.zeros(E, dtype=torch.float64), torch.eye(E, dtype=torch.float64))

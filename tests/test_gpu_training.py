@@ -104,3 +104,32 @@ def test_training_procedure_improves_the_marginal_likelihood_and_feeds_the_contr
     assert ctrl.p_train._closed
     act = ctrl.get_action(np.zeros(2))                       # per-GP hyper-parameters now -> general kernel path
     assert act.shape == (1,) and np.isfinite(ctrl.last_optim_cost)
+
+
+def test_lockstep_fit_of_all_gps_equals_the_serial_fit():
+    """GpStateTransitionModel.train(lockstep=True) batches the objective evaluations of the E concurrent LBFGS fits into
+    one gpmpc_prepare + gpmpc_mll per round; every GP must end where the one-GP-after-the-other procedure ends
+    (same random restarts: same torch seed)."""
+    from rl_gp_mpc.config_classes.model_config import ModelConfig
+    from rl_gp_mpc.control_objects.models.gp_model import GpStateTransitionModel
+    cfg = make_workload(E=3, Na=1, N=120, H=3, B=1, ls=0.5, seed=57)
+    mc = ModelConfig(gp_init={"noise_covar.noise": [1e-3] * 3, "base_kernel.lengthscale": [1.5] * 3, "outputscale": [0.3] * 3},
+                     min_std_noise=1e-3, max_std_noise=1e-1, min_outputscale=1e-4, max_outputscale=1.0,
+                     min_lengthscale=5e-2, max_lengthscale=10.0)
+    tm = GpStateTransitionModel(mc, dim_state=3, dim_action=1)
+    tm.prepare_inference(torch.as_tensor(cfg["x"]), torch.as_tensor(cfg["y"]))
+    out = {}
+    for lockstep in (False, True):
+        torch.manual_seed(5)
+        q = queue_mod.Queue()
+        st = tm.save_state(); st.to_arrays()
+        GpStateTransitionModel.train(q, st, 0.5, 6, 1e-3, lockstep=lockstep)
+        out[lockstep] = q.get(timeout=5)
+    eng = tm.engine
+    def neg_mll(params):
+        eng.prepare(cfg["x"], cfg["y"], np.stack([p["covar_module.base_kernel.lengthscale"][0] for p in params]),
+                    [float(p["covar_module.outputscale"]) for p in params], [float(p["likelihood.noise"][0]) for p in params])
+        return -eng.mll(cfg["y"])[:, 0].cpu().numpy() / cfg["N"]
+    np.testing.assert_allclose(neg_mll(out[True]), neg_mll(out[False]), rtol=0, atol=1e-6)
+    for a, b in zip(out[True], out[False]):
+        np.testing.assert_allclose(a["covar_module.base_kernel.lengthscale"], b["covar_module.base_kernel.lengthscale"], rtol=1e-5)
