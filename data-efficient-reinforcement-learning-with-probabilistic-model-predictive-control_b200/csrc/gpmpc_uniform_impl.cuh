@@ -820,6 +820,10 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
   double* s_mubar = s2p; double* s_sbar = s_mubar + GPMPC_MAX_EV; double* s_Om = s_sbar + EV * EV;
   double* s_Rinv = s_Om + EV * EV; double* s_U = s_Rinv + EV * EV; double* s_Vb = s_U + EV * EV;
   double* s_hbar = s_Vb + EV * EV; double* s_gbar = s_hbar + GPMPC_MAX_EV; double* s_scal = s_gbar + EV * EV;
+  // scratch of the staged small algebra (B0 / B4, warp 0): the forward record of the step, then E x E temporaries
+  double* s_rc = s_scal + 8 + EV * EV; double* s_Mb = s_rc + uni_rec_layout(EV).size; double* s_mb = s_Mb + GPMPC_MAX_EV;
+  double* s_sp = s_mb + GPMPC_MAX_D; double* s_Ag = s_sp + EV * EV; double* s_t1 = s_Ag + EV * EV; double* s_X = s_t1 + EV * EV;
+  double* s_RQ = s_sp; double* s_spb = s_Ag;    // B4 reuses the B0 temporaries
   const UniRecLayout RL = uni_rec_layout(E);
   const double* il2 = p.il2;
   const double s2 = p.s2[0];
@@ -889,68 +893,81 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
       // ---- B0: model input, shared matrices, adjoint coefficients (thread 0: O(E^3))
       if (tid < D) s_m[tid] = (tid < E) ? mup[tid] : (tid < E + Na ? am[tid - E] : (double)(p.iter_ctrl + t - 1));
       for (int o = tid; o < L.accN + 1; o += NT) s_acc[o] = 0.0;
-      if (tid == 0) {
-        s_int[0] = 0;
-        double Ai[EV * EV], Rinv[EV * EV], Qm[EV * EV], c, detR;
+      // warp 0, one small stage per __syncwarp: every lane owns entries of the E x E matrices (a product is E FMAs deep per
+      // lane instead of E^3 on one thread: these serial phases are latency, and they hold the CTA's other warps up)
+      if (warp == 0) {
+        if (lane == 0) s_int[0] = 0;
         if (premat) {
           const double* pr = s_pre + (size_t)(t - 1) * L.prelen;
-          for (int e = 0; e < EV * EV; e++) { Ai[e] = pr[oA + e]; Qm[e] = pr[oQ + e]; Rinv[e] = pr[oRi + e]; }
-          c = pr[oc]; detR = pr[odet];
-        } else {
-          uni_step_matrices<EV>(sp, il2, s2, Ai, Qm, Rinv, c, detR);
+          for (int o = lane; o < EV * EV; o += 32) { s_A[o] = pr[oA + o]; s_Q[o] = pr[oQ + o]; s_Rinv[o] = pr[oRi + o]; }
+          if (lane == 0) { s_scal[0] = pr[oc]; s_scal[1] = pr[odet]; }
+        } else if (lane == 0) {
+          double Ai[EV * EV], Rinv[EV * EV], Qm[EV * EV], c0, detR0;
+          uni_step_matrices<EV>(sp, il2, s2, Ai, Qm, Rinv, c0, detR0);
+          for (int e = 0; e < EV * EV; e++) { s_A[e] = Ai[e]; s_Q[e] = Qm[e]; s_Rinv[e] = Rinv[e]; }
+          s_scal[0] = c0; s_scal[1] = detR0;
         }
-        for (int e = 0; e < EV * EV; e++) { s_A[e] = Ai[e]; s_Q[e] = Qm[e]; s_Rinv[e] = Rinv[e]; }
-        const double rs = 1.0 / sqrt(detR);
-        const double* Mrec = rec + RL.offM;
-        // U = s_bar + s_bar^T ; V_bar[a][e] = sum_k sp[k][e] U[k][a]
-        for (int i = 0; i < E; i++)
-          for (int k = 0; k < E; k++) s_U[i * E + k] = s_sbar[i * E + k] + s_sbar[k * E + i];
-        for (int a = 0; a < E; a++)
-          for (int e = 0; e < E; e++) {
-            double v = 0.0;
-            for (int k = 0; k < E; k++) v += sp[k * E + e] * s_U[k * E + a];
-            s_Vb[a * E + e] = v;
-          }
-        double M_bar[E], detR_bar = 0.0, wbar = 0.0;
-        for (int a = 0; a < E; a++) M_bar[a] = s_mubar[a];
-        int pr = 0;
-        for (int a = 0; a < E; a++)
-          for (int b = a; b < E; b++) {
+        for (int o = lane; o < E * E; o += 32) {
+          s_sp[o] = sp[o];
+          s_U[o] = s_sbar[o] + s_sbar[(o % E) * E + o / E];              // U = s_bar + s_bar^T
+        }
+        for (int o = lane; o < RL.size; o += 32) s_rc[o] = rec[o];       // the step's forward record (M, V, h, g, S_raw)
+        __syncwarp();
+        const double c = s_scal[0], detR = s_scal[1], rs = 1.0 / sqrt(detR);
+        // V_bar[a][e] = sum_k sp[k][e] U[k][a] ;  M_bar = mu_bar - U M ;  pairs: Omega, wbar, detR_bar
+        for (int o = lane; o < E * E; o += 32) {
+          const int a = o / E, e = o - a * E;
+          double v = 0.0;
+#pragma unroll
+          for (int k = 0; k < E; k++) v = fma(s_sp[k * E + e], s_U[k * E + a], v);
+          s_Vb[o] = v;
+        }
+        if (lane < E) {
+          double v = s_mubar[lane];
+#pragma unroll
+          for (int b = 0; b < E; b++) v -= s_U[lane * E + b] * s_rc[RL.offM + b];
+          s_Mb[lane] = v;
+        }
+        {
+          double dpart = 0.0, wpart = 0.0;
+          for (int pr = lane; pr < P; pr += 32) {
+            int a = 0, w = pr;
+            while (w >= E - a) { w -= E - a; a++; }
+            const int b = a + w;
             const double sb = s_sbar[a * E + b] + (a != b ? s_sbar[b * E + a] : 0.0);
-            M_bar[a] -= sb * Mrec[b];
-            M_bar[b] -= sb * Mrec[a];
-            const double Sraw = rec[RL.offS + pr];
-            detR_bar += -0.5 * sb * Sraw * rs / detR;
+            dpart += -0.5 * sb * s_rc[RL.offS + pr] * rs / detR;
             const double om = sb * rs * s2 * s2;          // d L / d Shat_ab
-            if (a == b) { s_Om[a * E + a] = om; wbar += om; }
+            if (a == b) { s_Om[a * E + a] = om; wpart += om; }
             else { s_Om[a * E + b] = 0.5 * om; s_Om[b * E + a] = 0.5 * om; }
-            pr++;
           }
-        // mean part adjoints: c_bar (summed), h_bar_a, g_bar_a, A_bar (direct part)
-        double cbar_c = 0.0;     // sum_a c_bar_a * c
-        double A_bar[EV * EV];
-        for (int e = 0; e < EV * EV; e++) A_bar[e] = 0.0;
-        for (int a = 0; a < E; a++) {
-          const double h = rec[RL.offH + a];
-          const double* gE = rec + RL.offG + a * E;
-          double cb = M_bar[a] * h;
-          for (int e = 0; e < E; e++) {
-            double v = 0.0;
-            for (int f = 0; f < E; f++) v += Ai[e * E + f] * gE[f];
-            cb += s_Vb[a * E + e] * v;
-          }
-          cbar_c += cb * c;
-          s_hbar[a] = M_bar[a] * c;
-          for (int e = 0; e < E; e++) {
-            double v = 0.0;
-            for (int f = 0; f < E; f++) v += Ai[f * E + e] * s_Vb[a * E + f];
-            s_gbar[a * E + e] = c * v;
-          }
-          for (int k = 0; k < E; k++)
-            for (int l = 0; l < E; l++) A_bar[k * E + l] += c * s_Vb[a * E + k] * gE[l];
+          dpart = warp_sum(dpart);
+          wpart = warp_sum(wpart);
+          if (lane == 0) { s_scal[2] = dpart; s_scal[3] = wpart; }
         }
-        s_scal[0] = c; s_scal[1] = detR; s_scal[2] = detR_bar; s_scal[3] = wbar; s_scal[4] = cbar_c;
-        for (int e = 0; e < EV * EV; e++) s_scal[8 + e] = A_bar[e];   // needs 8 + E2 <= 72 doubles
+        __syncwarp();
+        // mean part adjoints: (A g_a), g_bar_a = c A^T V_bar_a, A_bar (direct part) = c sum_a V_bar_a g_a^T, h_bar_a = c M_bar_a
+        for (int o = lane; o < E * E; o += 32) {
+          const int a = o / E, e = o - a * E;
+          double ag = 0.0, gb = 0.0, ab = 0.0;
+#pragma unroll
+          for (int f = 0; f < E; f++) {
+            ag = fma(s_A[e * E + f], s_rc[RL.offG + a * E + f], ag);
+            gb = fma(s_A[f * E + e], s_Vb[a * E + f], gb);
+            ab = fma(s_Vb[f * E + a], s_rc[RL.offG + f * E + e], ab);     // (k, l) = (a, e): sum over the GPs f
+          }
+          s_Ag[o] = ag;
+          s_gbar[o] = c * gb;
+          s_scal[8 + o] = c * ab;                                          // needs 8 + E2 <= 72 doubles
+        }
+        if (lane < E) s_hbar[lane] = s_Mb[lane] * c;
+        __syncwarp();
+        {   // c_bar (summed) * c = c sum_a (M_bar_a h_a + V_bar_a . (A g_a))
+          double part = 0.0;
+          for (int o = lane; o < E * E; o += 32) part = fma(s_Vb[o], s_Ag[o], part);
+          if (lane < E) part = fma(s_Mb[lane], s_rc[RL.offH + lane], part);
+          part = warp_sum(part);
+          if (lane == 0) s_scal[4] = part * c;
+        }
       }
       __syncthreads();
       UNI_CLK(9);
@@ -1118,98 +1135,105 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
       }
       __syncthreads();
       UNI_CLK(12);
-      // ---- B4: small algebra (thread 0): assemble m_bar, s_prev_bar, stage-cost adjoints
-      if (tid == 0) {
-        const double c = s_scal[0], detR = s_scal[1], detR_bar = s_scal[2], cbar_c = s_scal[4];
-        double m_bar[GPMPC_MAX_D], sp_bar[EV * EV], Wd[EV], A_bar[EV * EV];
-        for (int e = 0; e < EV; e++) Wd[e] = 2.0 * il2[e];
-        for (int e = 0; e < EV * EV; e++) { sp_bar[e] = 0.0; A_bar[e] = s_scal[8 + e]; }
-        // pair part: x2 for the upper-triangle sweep, ybar correction, then Q/detR adjoints
-        double Gm[GPMPC_MAX_D], GQ[EV * EV], yb[EV];
-        for (int d = 0; d < D; d++) Gm[d] = 2.0 * s_acc[accGm + d];
-        for (int e = 0; e < EV * EV; e++) GQ[e] = 2.0 * s_acc[accGQ + e];
-        for (int e = 0; e < EV; e++) yb[e] = Gm[e];
-        for (int e = 0; e < EV; e++) {
-          double v = 0.0;
-          for (int f = 0; f < EV; f++) v += s_Q[e * EV + f] * yb[f];
-          Gm[e] -= 2.0 * Wd[e] * v;
-        }
-        for (int d = 0; d < D; d++) m_bar[d] = Gm[d];
-        double RQ[EV * EV];
-        for (int i = 0; i < E; i++)
-          for (int k = 0; k < E; k++) {
+      // ---- B4: small algebra (warp 0, staged like B0): assemble m_bar, s_prev_bar, stage-cost adjoints
+      if (warp == 0) {
+        const double detR = s_scal[1], detR_bar = s_scal[2], cbar_c = s_scal[4];
+        // pair part: x2 for the upper-triangle sweep, ybar correction (dS/dm[:EV] -= 2 W (Q ybar)), R^-T G_Q
+        for (int d = lane; d < D; d += 32) {
+          double g = 2.0 * s_acc[accGm + d];
+          if (d < EV) {
             double v = 0.0;
-            for (int l = 0; l < E; l++) v += s_Rinv[l * E + i] * GQ[l * E + k];
-            RQ[i * E + k] = v;
+#pragma unroll
+            for (int f = 0; f < EV; f++) v = fma(s_Q[d * EV + f], 2.0 * s_acc[accGm + f], v);
+            g -= 2.0 * (2.0 * il2[d]) * v;
           }
-        for (int i = 0; i < E; i++)
-          for (int k = 0; k < E; k++) {
-            double v = 0.0;
-            for (int l = 0; l < E; l++) v += RQ[i * E + l] * s_Q[k * E + l];
-            sp_bar[i * E + k] += 0.5 * RQ[i * E + k] - v * Wd[k] + detR_bar * detR * s_Rinv[k * E + i] * Wd[k];
-          }
-        // mean part: m_bar += Phi_m - sum_a h_a g_bar_a (state dims) ; A_bar += -1/2 Phi_A
-        for (int d = 0; d < D; d++) {   // Phi_m = A (sum_i phi_i nu_i) on the state block, il2 * (...) elsewhere
+          // mean part: m_bar += Phi_m - sum_a h_a g_bar_a (state dims); Phi_m = A (sum_i phi_i nu_i) on the state block
           double v;
-          if (d < EV) { v = 0.0; for (int f = 0; f < EV; f++) v += s_A[d * EV + f] * s_acc[accPm + f]; }
-          else v = il2[d] * s_acc[accPm + d];
-          m_bar[d] += v;
-        }
-        for (int a = 0; a < E; a++) {
-          const double h = rec[RL.offH + a];
-          for (int e = 0; e < E; e++) m_bar[e] -= h * s_gbar[a * E + e];
-        }
-        {
-          int w = 0;
-          for (int k = 0; k < E; k++)
-            for (int l = k; l < E; l++) {
-              const double v = -0.5 * s_acc[accPA + w];
-              A_bar[k * E + l] += v;
-              if (l != k) A_bar[l * E + k] += v;
-              w++;
-            }
-        }
-        double t1[EV * EV];
-        for (int i = 0; i < E; i++)
-          for (int k = 0; k < E; k++) {
-            double v = 0.0;
-            for (int l = 0; l < E; l++) v += s_A[l * E + i] * A_bar[l * E + k];
-            t1[i * E + k] = v;
+          if (d < EV) {
+            v = 0.0;
+#pragma unroll
+            for (int f = 0; f < EV; f++) v = fma(s_A[d * EV + f], s_acc[accPm + f], v);
+#pragma unroll
+            for (int a = 0; a < E; a++) v -= s_rc[RL.offH + a] * s_gbar[a * E + d];
+          } else {
+            v = il2[d] * s_acc[accPm + d];
           }
-        for (int i = 0; i < E; i++)
-          for (int k = 0; k < E; k++) {
-            double v = 0.0;
-            for (int l = 0; l < E; l++) v += t1[i * E + l] * s_A[k * E + l];
-            sp_bar[i * E + k] += -0.5 * cbar_c * s_A[k * E + i] - v;
+          s_mb[d] = g + v;
+        }
+        for (int o = lane; o < E * E; o += 32) {
+          const int i = o / E, k = o - i * E;
+          double v = 0.0;
+#pragma unroll
+          for (int l = 0; l < E; l++) v = fma(s_Rinv[l * E + i], 2.0 * s_acc[accGQ + l * E + k], v);
+          s_RQ[o] = v;
+          // A_bar += -1/2 Phi_A (symmetric, stored as its upper triangle)
+          const int kk = i < k ? i : k, ll = i < k ? k : i;
+          s_scal[8 + o] += -0.5 * s_acc[accPA + kk * E - (kk * (kk - 1)) / 2 + (ll - kk)];
+        }
+        __syncwarp();
+        for (int o = lane; o < E * E; o += 32) {
+          const int i = o / E, k = o - i * E;
+          const double Wk = 2.0 * il2[k];
+          double v = 0.0, t1 = 0.0, x = 0.0;
+#pragma unroll
+          for (int l = 0; l < E; l++) {
+            v = fma(s_RQ[i * E + l], s_Q[k * E + l], v);
+            t1 = fma(s_A[l * E + i], s_scal[8 + l * E + k], t1);          // (A^T A_bar)[i][k]
+            x = fma(s_U[i * E + l], s_rc[RL.offV + l * E + k], x);       // recurrence term U V
           }
-        (void)c;
-        // recurrence terms
-        const double* Vrec = rec + RL.offV;
-        double X[EV * EV], nsb[EV * EV], nmu[EV], a_bar[GPMPC_MAX_D];
-        for (int i = 0; i < E; i++)
-          for (int k = 0; k < E; k++) {
-            double v = 0.0;
-            for (int a = 0; a < E; a++) v += s_U[i * E + a] * Vrec[a * E + k];
-            X[i * E + k] = v;
+          s_spb[o] = 0.5 * s_RQ[o] - v * Wk + detR_bar * detR * s_Rinv[k * E + i] * Wk;
+          s_t1[o] = t1;
+          s_X[o] = x;
+        }
+        __syncwarp();
+        for (int o = lane; o < E * E; o += 32) {
+          const int i = o / E, k = o - i * E;
+          double v = 0.0;
+#pragma unroll
+          for (int l = 0; l < E; l++) v = fma(s_t1[i * E + l], s_A[k * E + l], v);
+          s_spb[o] += -0.5 * cbar_c * s_A[k * E + i] - v;
+        }
+        __syncwarp();
+        // symmetrised step adjoint + recurrence + stage-cost adjoint at t-1 -> the adjoints the next (earlier) step starts from
+        constexpr int NR = (E * E + 31) / 32;
+        double nsb[NR], nmu = 0.0, abar = 0.0;
+        const double* pr = premat ? s_pre + (size_t)(t - 1) * L.prelen : nullptr;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          const int o = lane + 32 * r;
+          nsb[r] = 0.0;
+          if (o < E * E) {
+            const int i = o / E, k = o - i * E, ot = k * E + i;
+            nsb[r] = 0.5 * (s_spb[o] + s_spb[ot]) + 0.5 * (s_sbar[o] + s_sbar[ot]) + 0.5 * (s_X[o] + s_X[ot]);
+            if (premat) nsb[r] += pr[odS + o];
           }
-        for (int i = 0; i < E; i++)
-          for (int k = 0; k < E; k++)
-            nsb[i * E + k] = 0.5 * (sp_bar[i * E + k] + sp_bar[k * E + i]) + 0.5 * (s_sbar[i * E + k] + s_sbar[k * E + i]) +
-                             0.5 * (X[i * E + k] + X[k * E + i]);
-        for (int e = 0; e < E; e++) nmu[e] = s_mubar[e] + m_bar[e];
-        for (int k = 0; k < Na; k++) a_bar[k] = m_bar[E + k];
-        if (premat) {   // stage-cost adjoint at t-1, precomputed
-          const double* pr = s_pre + (size_t)(t - 1) * L.prelen;
-          for (int e = 0; e < E; e++) nmu[e] += pr[odmu + e];
-          for (int k = 0; k < Na; k++) a_bar[k] += pr[oda + k];
-          for (int e = 0; e < E * E; e++) nsb[e] += pr[odS + e];
+        }
+        if (lane < E) nmu = s_mubar[lane] + s_mb[lane] + (premat ? pr[odmu + lane] : 0.0);
+        if (lane < Na) abar = s_mb[E + lane] + (premat ? pr[oda + lane] : 0.0);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          const int o = lane + 32 * r;
+          if (o < E * E) s_sbar[o] = nsb[r];
+        }
+        if (lane < E) s_mubar[lane] = nmu;
+        if (premat) {
+          if (lane < Na && lead) gout[(size_t)(t - 1) * Na + lane] = abar;
         } else {
-          uni_stage_adjoint<EV>(p, Na, wmu, -p.kappa * wmu * 0.5 / sqrt(rvs[t - 1]), mup, sp, am, nmu, a_bar, nsb);
+          if (lane < Na) s_mb[lane] = abar;      // a_bar staged for the serial stage-cost adjoint
+          __syncwarp();
+          if (lane == 0) {
+            double nmu1[EV], a_bar[GPMPC_MAX_D], nsb1[EV * EV];
+            for (int e = 0; e < E; e++) nmu1[e] = s_mubar[e];
+            for (int k = 0; k < Na; k++) a_bar[k] = s_mb[k];
+            for (int e = 0; e < E * E; e++) nsb1[e] = s_sbar[e];
+            uni_stage_adjoint<EV>(p, Na, wmu, -p.kappa * wmu * 0.5 / sqrt(rvs[t - 1]), mup, sp, am, nmu1, a_bar, nsb1);
+            if (lead)
+              for (int k = 0; k < Na; k++) gout[(size_t)(t - 1) * Na + k] = a_bar[k];
+            for (int e = 0; e < E; e++) s_mubar[e] = nmu1[e];
+            for (int e = 0; e < E * E; e++) s_sbar[e] = nsb1[e];
+          }
         }
-        if (lead)
-          for (int k = 0; k < Na; k++) gout[(size_t)(t - 1) * Na + k] = a_bar[k];
-        for (int e = 0; e < E; e++) s_mubar[e] = nmu[e];
-        for (int e = 0; e < E * E; e++) s_sbar[e] = nsb[e];
       }
       gstep++;
       __syncthreads();

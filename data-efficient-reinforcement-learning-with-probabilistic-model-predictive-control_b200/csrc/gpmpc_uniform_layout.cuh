@@ -60,7 +60,7 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.rv = o; o += H + 1;
   L.ints = o; o += 4;
   o = (o + 1) & ~1;
-  L.small2 = o; o += bwd ? (8 * EV * EV + 8 * GPMPC_MAX_D + E * E + 64) : 0;
+  L.small2 = o; o += bwd ? (15 * EV * EV + 64) : 0;   // carve: uniform_bwd_kernel (small matrices + B0/B4 scratch)
   L.total = (o + 1) & ~1;
   return L;
 }
