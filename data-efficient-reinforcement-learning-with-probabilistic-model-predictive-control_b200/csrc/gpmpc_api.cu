@@ -47,11 +47,13 @@ struct gpmpc_handle {
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
   DevBuf dbg_clk, ws_uni, queue, ws_cl;
-  DevBuf ws_kk, ws_gam, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
+  DevBuf ws_kk, ws_gam, colcoef, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
   long long launches = 0;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_fwd = false, ev_bwd = false;
+  size_t cl_cap_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cache of uniform_max_clusters (key: shared-memory plan, cluster size)
+  int cl_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cl_cap_next = 0;
 };
 
 static int fail(gpmpc_handle* h, int code, const char* msg, cudaError_t ce = cudaSuccess) {
@@ -161,7 +163,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
-                   &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->ws_gam, &h->t_mu, &h->t_var,
+                   &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->ws_gam, &h->colcoef, &h->t_mu, &h->t_var,
                    &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue, &h->ws_cl};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
@@ -355,6 +357,9 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
   cudaError_t ce = h->ws_kk.ensure(sizeof(double) * (size_t)(*grid) * h->E * h->NP);
   if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
   p.ws_kk = h->ws_kk.as<double>();
+  ce = h->colcoef.ensure(sizeof(double) * 2 * (size_t)h->E * h->NP);
+  if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
+  p.colcoef = h->colcoef.as<double>();
   if (grad) {
     ce = h->ws_gam.ensure(sizeof(double) * (size_t)(*grid) * G * h->NP);
     if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
@@ -379,8 +384,9 @@ int gpmpc_predict_step(gpmpc_handle* h, const double* input_mu, const double* in
   p.mode = 1;
   p.obs_mu = input_mu; p.obs_var = input_var;
   p.stepM = M; p.stepS = S; p.stepV = V;
+  CU(launch_colcoef(h->beta.as<double>(), h->colcoef.as<double>(), h->E * h->NP, st));
   CU(launch_rollout(EV, false, p, grid, threads, smem, st));
-  h->launches += 1;
+  h->launches += 2;
   return GPMPC_OK;
 }
 
@@ -479,10 +485,26 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     p.cluster = 1;
     {
       const int nrb = h->NP / 64, chunks8 = 8 * nrb * (nrb + 1) / 2;
+      // capacity: clusters of c CTAs (256 threads) the device holds at once -- two CTAs per SM are co-resident when the
+      // shared memory allows it, so a mid-size batch (the batched optimiser's 64 .. 128 candidates) still gets a cluster
+      // per candidate; asked from the driver (GPC boundaries), cached per (c, shared-memory plan)
+      auto capacity = [&](int c) -> int {
+        const size_t key = (want_grad ? smb : smf) * 16 + c;
+        for (int k = 0; k < 8; k++)
+          if (h->cl_cap_key[k] == key) return h->cl_cap[k];
+        int nf = 0, nb = 1 << 30;
+        if (uniform_max_clusters(E, false, c, 256, smf, &nf) != cudaSuccess) { cudaGetLastError(); nf = h->num_sms / c; }
+        if (want_grad && uniform_max_clusters(E, true, c, 256, smb, &nb) != cudaSuccess) { cudaGetLastError(); nb = h->num_sms / c; }
+        const int n = nf < nb ? nf : nb;
+        h->cl_cap_key[h->cl_cap_next] = key; h->cl_cap[h->cl_cap_next] = n; h->cl_cap_next = (h->cl_cap_next + 1) % 8;
+        return n;
+      };
+      int cap_mode = 2;
+      if (const char* e = getenv("GPMPC_UNI_CLUSTER_CAP")) { int v = atoi(e); if (v == 1 || v == 2) cap_mode = v; }   // tuning aid: 1 = one CTA per SM
       int c = 8;
-      while (c > 1 && (B * c > h->num_sms || chunks8 < 2 * c * 8)) c /= 2;   // cluster launches use 256 threads
+      while (c > 1 && (chunks8 < 2 * c * 8 || (cap_mode == 1 ? B * c > h->num_sms : B > capacity(c)))) c /= 2;   // cluster launches use 256 threads
       if (E <= 5) p.cluster = c;       // the 255-register kernels (E > 5) stay on the plain path
-      if (const char* e = getenv("GPMPC_UNI_CLUSTER")) { int v = atoi(e); if (v == 1 || ((v == 2 || v == 4 || v == 8) && B * v <= h->num_sms)) p.cluster = v; }
+      if (const char* e = getenv("GPMPC_UNI_CLUSTER")) { int v = atoi(e); if (v == 1 || ((v == 2 || v == 4 || v == 8) && B <= capacity(v))) p.cluster = v; }
     }
     if (p.cluster > 1) {
       grid_f = grid_b = B * p.cluster;
@@ -566,9 +588,10 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     CU(cudaMemsetAsync(h->dbg_clk.ptr, 0, sizeof(long long) * 64, st));
     p.dbg_clk = h->dbg_clk.as<long long>();
   }
+  CU(launch_colcoef(h->beta.as<double>(), h->colcoef.as<double>(), h->E * h->NP, st));
   if (h->timing) CU(cudaEventRecord(h->ev[0], st));
   CU(launch_rollout(E, want_grad, p, grid, threads, smem, st));
-  h->launches += 1;
+  h->launches += 2;
   if (dbg_gen) {
     long long c[64];
     CU(cudaMemcpyAsync(c, h->dbg_clk.ptr, sizeof(c), cudaMemcpyDeviceToHost, st));

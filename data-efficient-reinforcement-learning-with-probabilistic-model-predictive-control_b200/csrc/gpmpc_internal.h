@@ -13,6 +13,7 @@ struct RolloutParams {
   const double* il2;    // (E, D)  1 / lengthscale^2
   const double* s2;     // (E)     outputscale
   const double* exp2tab; // (2048)  2^(j/2048), correctly rounded, pre-biased (general path, exp2s)
+  const double* colcoef; // (E, NP, 2) general path: { 2048/ln 2 * log|beta_b,j| , exp2s magic constant carrying sign(beta_b,j) }
   int N, NP, D, DP, E, Na;
   // ---- candidates
   int B, H, mode;            // mode 0: rollout, 1: single moment-matching step on given inputs
@@ -72,6 +73,7 @@ inline int rollout_max_threads(int EV) { return GEN_MAXT(EV); }
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
 size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat);
 cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t uniform_max_clusters(int EV, bool bwd, int cluster, int threads, size_t smem, int* nclusters);
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,
                            const double* noise, int N, int NP, int D, int E, double* Kbuf, double* Zbuf,
                            double* iK, double* beta, double* betaT, int* info, cudaStream_t st, long long* launches);
@@ -82,6 +84,7 @@ cudaError_t launch_mll(const double* x, const double* y, const double* ls, const
                        const double* iK, const double* beta, double* out, int N, int NP, int D, int E, int stride,
                        cudaStream_t st, long long* launches);
 cudaError_t launch_il2(const double* ls, double* il2, int n, cudaStream_t st);
+cudaError_t launch_colcoef(const double* beta, double* colcoef, int n, cudaStream_t st);
 
 // static shared memory of the rollout kernels: the 16 KB table of exp2s (gpmpc_common.cuh) + a few scalars
 constexpr size_t GPMPC_STATIC_SMEM = 16 * 1024 + 128;   // sizeof(GpmpcStaticSmem) rounded up

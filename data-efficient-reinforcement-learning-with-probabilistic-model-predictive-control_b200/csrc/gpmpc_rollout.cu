@@ -23,10 +23,12 @@ int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, i
 template <int EV> cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
 template <int EV> cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, int threads, size_t smem, cudaStream_t st);
 template <int E> cudaError_t launch_backward_inst(const BackwardParams& p, cudaStream_t st);
+template <int EV> cudaError_t max_clusters_uniform_inst(bool bwd, int cluster, int threads, size_t smem, int* nclusters);
 #define GPMPC_DECL(n)                                                                                             \
   extern template cudaError_t launch_rollout_inst<n>(bool, const RolloutParams&, int, int, size_t, cudaStream_t);      \
   extern template cudaError_t launch_backward_inst<n>(const BackwardParams&, cudaStream_t);                       \
-  extern template cudaError_t launch_uniform_inst<n>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t);
+  extern template cudaError_t launch_uniform_inst<n>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t); \
+  extern template cudaError_t max_clusters_uniform_inst<n>(bool, int, int, size_t, int*);
 GPMPC_DECL(1) GPMPC_DECL(2) GPMPC_DECL(3) GPMPC_DECL(4) GPMPC_DECL(5) GPMPC_DECL(6) GPMPC_DECL(7) GPMPC_DECL(8)
 #undef GPMPC_DECL
 
@@ -58,6 +60,20 @@ cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* gra
   }
 }
 
+cudaError_t uniform_max_clusters(int EV, bool bwd, int cluster, int threads, size_t smem, int* nclusters) {
+  switch (EV) {
+    case 1: return max_clusters_uniform_inst<1>(bwd, cluster, threads, smem, nclusters);
+    case 2: return max_clusters_uniform_inst<2>(bwd, cluster, threads, smem, nclusters);
+    case 3: return max_clusters_uniform_inst<3>(bwd, cluster, threads, smem, nclusters);
+    case 4: return max_clusters_uniform_inst<4>(bwd, cluster, threads, smem, nclusters);
+    case 5: return max_clusters_uniform_inst<5>(bwd, cluster, threads, smem, nclusters);
+    case 6: return max_clusters_uniform_inst<6>(bwd, cluster, threads, smem, nclusters);
+    case 7: return max_clusters_uniform_inst<7>(bwd, cluster, threads, smem, nclusters);
+    case 8: return max_clusters_uniform_inst<8>(bwd, cluster, threads, smem, nclusters);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat) {
   return (size_t)make_uni_layout(EV, bwd, NP, DP, D, H, Na, premat).total * sizeof(double);
 }
@@ -79,6 +95,20 @@ cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st) {
 __global__ void il2_kernel(const double* __restrict__ ls, double* __restrict__ il2, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) il2[i] = 1.0 / (ls[i] * ls[i]);
+}
+// Column coefficients of the general kernel's off-diagonal pairs (gen_cols): the coefficient beta_b,j rides in the exponent
+// as log|beta| (table units) and its sign in the magic constant of the exp's range reduction (exp2s_x4_signed).
+__global__ void colcoef_kernel(const double* __restrict__ beta, double* __restrict__ cc, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double b = beta[i];
+    cc[2 * i] = GPMPC_EXP2S_SCALE * log(fabs(b));
+    cc[2 * i + 1] = __hiloint2double(0x43380000, b < 0.0 ? GPMPC_EXP2S_NEG_LO : 0);
+  }
+}
+cudaError_t launch_colcoef(const double* beta, double* colcoef, int n, cudaStream_t st) {
+  colcoef_kernel<<<(n + 127) / 128, 128, 0, st>>>(beta, colcoef, n);
+  return cudaGetLastError();
 }
 cudaError_t launch_il2(const double* ls, double* il2, int n, cudaStream_t st) {
   il2_kernel<<<(n + 127) / 128, 128, 0, st>>>(ls, il2, n);

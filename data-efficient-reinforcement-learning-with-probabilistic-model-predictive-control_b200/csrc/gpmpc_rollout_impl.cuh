@@ -726,16 +726,24 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
               b2 = s_nu + k1; st2 = DP;
               b3 = s_nu + (k1 + kl); st3 = DP;
             }
-            double acc0 = 0.0, acc1 = 0.0;
+            // four independent accumulation chains (the loop is LDS -> DMUL -> DFMA latency, not throughput), running
+            // pointers instead of index * stride
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double* q0 = lb + ibeg;
+            const double* q1 = b1 + (size_t)ibeg * st1;
+            const double* q2 = b2 + (size_t)ibeg * st2;
+            const double* q3 = b3 + (size_t)ibeg * st3;
             int i = ibeg;
-            for (; i + 1 < iend; i += 2) {
-              const double f0 = lb[i] * b1[i * st1], f1 = lb[i + 1] * b1[(i + 1) * st1];
-              const double g0 = b2[i * st2] * b3[i * st3], g1 = b2[(i + 1) * st2] * b3[(i + 1) * st3];
-              acc0 = fma(f0, g0, acc0);
-              acc1 = fma(f1, g1, acc1);
+            for (; i + 3 < iend; i += 4) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) acc[k] = fma(q0[k] * q1[k * st1], q2[k * st2] * q3[k * st3], acc[k]);
+              q0 += 4; q1 += 4 * st1; q2 += 4 * st2; q3 += 4 * st3;
             }
-            if (i < iend) acc0 = fma(lb[i] * b1[i * st1], b2[i * st2] * b3[i * st3], acc0);
-            atomicAdd(s_out + o, acc0 + acc1);
+            for (; i < iend; i++) {
+              acc[0] = fma(q0[0] * q1[0], q2[0] * q3[0], acc[0]);
+              q0 += 1; q1 += st1; q2 += st2; q3 += st3;
+            }
+            atomicAdd(s_out + o, (acc[0] + acc[1]) + (acc[2] + acc[3]));
           }
         }
       }
@@ -819,9 +827,10 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
           if (a != b) {
             // off-diagonal pairs: the coefficient beta_b,j moves into the exponent (log|beta|) and its sign into the magic
             // constant of the exp's range reduction (gen_cols, exp2s_x4_signed); padded columns get exp(-huge) = 0
-            const double bj = (j < N) ? __ldg(p.beta + (size_t)b * NP + j) : 0.0;
-            kap = (j < N) ? GPMPC_EXP2S_SCALE * (kap + log(fabs(bj))) : -1.0e300;
-            s_kap[2 * o + 1] = exp2s_shift(bj < 0.0 ? GPMPC_EXP2S_NEG_LO : 0);
+            // (colcoef = {SCALE log|beta_b,j|, magic constant with the sign}: candidate independent, formed once per launch)
+            const double2 cc = __ldg(reinterpret_cast<const double2*>(p.colcoef) + (size_t)b * NP + j);
+            kap = (j < N) ? fma(GPMPC_EXP2S_SCALE, kap, cc.x) : -1.0e300;
+            s_kap[2 * o + 1] = cc.y;
           } else {
             kap *= GPMPC_EXP2S_SCALE;
           }

@@ -1289,4 +1289,30 @@ cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, 
   return cudaGetLastError();
 }
 
+// Thread-block clusters of `cluster` CTAs (threads, smem each) of the uniform kernels that the device can hold at once
+// (cudaOccupancyMaxActiveClusters: GPC boundaries make this less than SMs x CTAs-per-SM / cluster).
+template <int EV>
+cudaError_t max_clusters_uniform_inst(bool bwd, int cluster, int threads, size_t smem, int* nclusters) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster * 64);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (bwd) {
+    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveClusters(nclusters, uniform_bwd_kernel<EV>, &cfg);
+  }
+  e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveClusters(nclusters, uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, &cfg);
+}
+
 }  // namespace gpmpc

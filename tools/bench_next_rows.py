@@ -88,13 +88,15 @@ def main():
         q = queue.Queue()
         eng = tm.engine
         l0 = eng.launch_count()
-        for rep in range(2):
-            t0 = time.perf_counter()
-            GpStateTransitionModel.train(q, st, 7e-3, 15, 1e-3, False, 5)
-            dt = time.perf_counter() - t0
-            q.get()
-        print("N2 %-4s N=%d E=%d  train(): 15 LBFGS iterations per GP, all GPs: %.2f s (second call)" % (
-            name, cfg["N"], cfg["E"], dt), flush=True)
+        for lockstep in (False, True):     # same random restarts for both procedures
+            for rep in range(2):
+                torch.manual_seed(1234)
+                t0 = time.perf_counter()
+                GpStateTransitionModel.train(q, st, 7e-3, 15, 1e-3, False, 5, lockstep=lockstep)
+                dt = time.perf_counter() - t0
+                q.get()
+            print("N2 %-4s N=%d E=%d  train(): 15 LBFGS iterations per GP, all GPs, %-38s %.2f s (second call)" % (
+                name, cfg["N"], cfg["E"], "lockstep-batched evaluations:" if lockstep else "one GP after the other:", dt), flush=True)
     # N3: append vs prepare
     for name in ("C2", "C4b", "C5"):
         cfg = make_workload(name, B=1, H=2)
