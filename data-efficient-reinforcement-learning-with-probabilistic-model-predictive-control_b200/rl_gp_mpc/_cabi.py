@@ -37,6 +37,7 @@ _SIGNATURES = {
     "gpmpc_last_rollout_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "gpmpc_last_backward_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "gpmpc_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "gpmpc_lbfgs_update": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.c_double] * 3 + [ctypes.c_void_p] * 13),
 }
 
 
@@ -78,6 +79,20 @@ def _f64(t, device, shape=None):
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(t.shape)))
     return t
+
+
+def lbfgs_update(x, g, f, S, Y, rho, alpha, fails, first, xt, ft, gt, head, c1=1e-4, shrink=0.25, max_first_move=0.1):
+    """One batched projected L-BFGS update on the device (gpmpc_lbfgs_update, include/gpmpc.h); all tensors CUDA,
+    contiguous; ft / gt = None on the first call (no trial point evaluated yet)."""
+    lib = load_library()
+    nb, n = x.shape
+    with torch.cuda.device(x.device):
+        rc = lib.gpmpc_lbfgs_update(int(nb), int(n), int(S.shape[0]), int(head), 0 if ft is None else 1, float(c1),
+                                    float(shrink), float(max_first_move), _ptr(x), _ptr(g), _ptr(f), _ptr(S), _ptr(Y),
+                                    _ptr(rho), _ptr(alpha), _ptr(fails), _ptr(first), _ptr(xt), _ptr(ft), _ptr(gt),
+                                    ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != GPMPC_OK:
+        raise GpmpcError("gpmpc_lbfgs_update failed: %s" % _STATUS.get(rc, rc))
 
 
 def measure_fp64_peak(device_index=0):

@@ -184,8 +184,22 @@ class GpMpcController(BaseControllerObject):
         lo, hi = sh.bounds(nb) if sh is not None else (0, nb)
         x = x[lo:hi]
 
+        # everything the objective needs is staged on the device ONCE, and its results land in the same buffers at every
+        # call: an iteration then enqueues kernels only -- the batched rollout and ONE update kernel (gpmpc_lbfgs_update) --
+        # with no host-to-device copies, allocations or synchronisations in between
+        self._bind_cost()
+        eng = self.transition_model.engine
+        limit = bool(self.config.actions.limit_action_change)
+        mu_d = torch.as_tensor(state_mu, dtype=torch.float64).to(dev)
+        var_d = torch.as_tensor(state_var, dtype=torch.float64).to(dev)
+        mc_d = torch.as_tensor(self.config.actions.max_change_action_norm, dtype=torch.float64).reshape(-1).to(dev) if limit else None
+        ap_d = torch.as_tensor(self.actions_mapper.action_model_previous_iter, dtype=torch.float64).reshape(-1).to(dev) if limit else None
+        bufs = {"cost": torch.empty((hi - lo,), dtype=torch.float64, device=dev),
+                "grad": torch.empty((hi - lo, h * na), dtype=torch.float64, device=dev)}
+
         def fun(xb):
-            out = self._rollout(xb, state_mu, state_var, need_grad=True, need_traj=False)
+            out = eng.rollout(xb, mu_d, var_d, h, iter_ctrl=self.iter_ctrl, limit_action_change=limit, max_change=mc_d,
+                              action_prev=ap_d, need_grad=True, need_traj=False, out=dict(bufs))
             return out["cost"], out["grad"]
 
         if hi > lo:
@@ -196,7 +210,9 @@ class GpMpcController(BaseControllerObject):
                 best_cost = torch.where(better, cost, best_cost)
                 best_x = torch.where(better[:, None], x_last, best_x)
             else:
-                best_x, best_cost = minimize_box_lbfgs(fun, x, ctl.batched_iters)
+                best_x, best_cost = minimize_box_lbfgs(fun, x, ctl.batched_iters,
+                                                       cuda_graph=bool(getattr(ctl, "batched_cuda_graph", False)),
+                                                       fused=bool(getattr(ctl, "batched_fused", True)))
         else:
             best_x, best_cost = x, torch.empty((0,), dtype=torch.float64, device=dev)
         if sh is None:

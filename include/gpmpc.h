@@ -128,6 +128,24 @@ int gpmpc_mll(gpmpc_handle* h, const double* y, double* out, void* stream);
 int gpmpc_set_path(gpmpc_handle* h, int mode);
 int gpmpc_uses_uniform_path(const gpmpc_handle* h);
 
+/*
+ * Batched projected L-BFGS on the box [0, 1]^n, one update per call and B candidates per launch -- the device-side
+ * counterpart of the serial scipy L-BFGS-B restart loop of GpMpcController._get_optimal_actions
+ * (control_objects/controllers/gp_mpc_controller.py:125-148; bounds: actions_mappers/normalization_action_mapper.py:13).
+ * Stateless: all optimiser state lives in caller-owned device arrays (row-major, float64 unless noted):
+ *   x, g (B, n), f (B): current point, its gradient and cost;  S, Y (history, B, n), rho (history, B): curvature pairs,
+ *   ring buffer, `head` = slot the next pair goes to;  alpha (B), fails, first (B, int32): step scale, consecutive
+ *   rejected trials, "no accepted step yet";  xt (B, n): trial point.
+ * have_trial = 0 (first call): writes the first trial point xt from (x, g).  have_trial = 1: (ft (B), gt (B, n)) are the
+ * cost and gradient evaluated at xt (e.g. by gpmpc_rollout); the trial is accepted per candidate by the Armijo test on the
+ * projected step, the pair (s, y) enters slot `head` (the caller then advances head = (head + 1) % history), and the next
+ * trial point is written to xt.  Non-finite ft rejects the trial, non-finite entries of gt count as 0.
+ * rl_gp_mpc/control_objects/controllers/batched_optim.py::minimize_box_lbfgs is the executable specification.
+ */
+int gpmpc_lbfgs_update(int B, int n, int history, int head, int have_trial, double c1, double shrink,
+                       double max_first_move, double* x, double* g, double* f, double* S, double* Y, double* rho,
+                       double* alpha, int* fails, int* first, double* xt, const double* ft, const double* gt, void* stream);
+
 /* Introspection for benchmarks/tests: number of kernels launched by this handle so far, and the
  * device time [ms] of the last rollout's forward kernel measured with CUDA events on `stream`
  * (valid after the stream has been synchronised; <0 if timing was not enabled). */

@@ -444,3 +444,36 @@ def test_general_path_cluster_mode_matches_single_cta_mode(kw, monkeypatch):
     np.testing.assert_allclose(got["grad"][:1], want["grad"].reshape(1, -1), rtol=0, atol=ATOL_GRAD)
     fwd_only = rollout(eng, cfg, need_grad=False)
     np.testing.assert_allclose(fwd_only["cost"], got["cost"], rtol=0, atol=ATOL)
+
+
+@pytest.mark.parametrize("n,history,iters", [(60, 8, 25), (7, 3, 12), (200, 5, 10)])
+def test_fused_lbfgs_update_kernel_follows_its_torch_specification(n, history, iters):
+    """gpmpc_lbfgs_update (csrc/gpmpc_optim.cu: one kernel per optimiser iteration) against
+    batched_optim.minimize_box_lbfgs (plain torch) on a batch of box-constrained problems with active bounds, a
+    non-quadratic term, a candidate whose objective turns non-finite off the start point and NaN gradient entries:
+    same iterates."""
+    from rl_gp_mpc.control_objects.controllers.batched_optim import minimize_box_lbfgs
+    g = torch.Generator().manual_seed(5)
+    nb = 37
+    dev = torch.device("cuda")
+    tgt = (torch.rand((nb, n), generator=g, dtype=torch.float64) * 1.6 - 0.3).to(dev)     # some optima outside the box
+    w = (0.5 + 4.0 * torch.rand((nb, n), generator=g, dtype=torch.float64)).to(dev)
+    x0 = torch.rand((nb, n), generator=g, dtype=torch.float64).to(dev)
+    x0[3, :] = 0.0                                                                          # starts on a bound
+
+    def fun(x):
+        d = x - tgt
+        cost = (w * d * d).sum(1) + 0.1 * torch.sin(3.0 * x).sum(1)
+        grad = 2.0 * w * d + 0.3 * torch.cos(3.0 * x)
+        bad = (x[:, 0] > 0.9)                                                               # non-finite region for some candidates
+        cost = torch.where(bad & (torch.arange(nb, device=dev) % 5 == 1), torch.full_like(cost, float("nan")), cost)
+        grad = grad.clone()
+        grad[7, 1] = float("nan")
+        return cost, grad
+
+    xa, fa = minimize_box_lbfgs(fun, x0, iters, history=history)
+    xb, fb = minimize_box_lbfgs(fun, x0, iters, history=history, fused=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(xb.cpu().numpy(), xa.cpu().numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(fb.cpu().numpy(), fa.cpu().numpy(), rtol=0, atol=1e-6)
+    assert float((fa - fun(x0)[0]).nan_to_num(0.0).max()) <= 0.0                            # never worse than the start
