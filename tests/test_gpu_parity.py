@@ -477,3 +477,4 @@ def test_fused_lbfgs_update_kernel_follows_its_torch_specification(n, history, i
     np.testing.assert_allclose(xb.cpu().numpy(), xa.cpu().numpy(), rtol=0, atol=1e-6)
     np.testing.assert_allclose(fb.cpu().numpy(), fa.cpu().numpy(), rtol=0, atol=1e-6)
     assert float((fa - fun(x0)[0]).nan_to_num(0.0).max()) <= 0.0                            # never worse than the start
+
