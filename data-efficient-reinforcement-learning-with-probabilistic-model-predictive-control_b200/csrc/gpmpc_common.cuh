@@ -141,6 +141,21 @@ __device__ __forceinline__ void exp2s_x4_signed(const double (&xin)[4], double (
   for (int c = 0; c < 4; c++) res[c] = __fma_rn(t[c], p[c], t[c]);
 }
 
+// iK is streamed: every value is used once per prediction, so its lines should not displace the small arrays the per-step
+// phases re-read (x, betaT) from L1.  GPMPC_IK_NO_L1 = 1: 16-byte read-only load that does not allocate in L1.
+#ifndef GPMPC_IK_NO_L1
+#define GPMPC_IK_NO_L1 1
+#endif
+__device__ __forceinline__ double2 ldg_stream2(const double* p) {
+#if GPMPC_IK_NO_L1
+  double2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const double2*>(p));
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Thread-block cluster helpers (small batches: several CTAs on neighbouring SMs share one candidate).
 // ---------------------------------------------------------------------------------------------

@@ -314,8 +314,8 @@ __device__ __forceinline__ void gen_cols(const double* __restrict__ s_nu, int DP
       }
       if (DIAG) {
         const double2 bb2 = __ldg(reinterpret_cast<const double2*>(beta_b + j));
-        const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
-        const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
+        const double2 ika = ldg_stream2(ik0);
+        const double2 ikb = ldg_stream2(ik0 + NP);
         ik0 += 2 * (size_t)NP;
         double c[4] = {-ce0 * ika.x, -ce1 * ika.y, -ce0 * ikb.x, -ce1 * ikb.y};
         c[0] = fma(cb0, bb2.x, c[0]);

@@ -110,8 +110,8 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
     double na[EV], nb[EV], ba[E], bb[E], ka, kb;
     uni_load_rec<EV>(s_rec, j, na, ka, ba);
     uni_load_rec<EV>(s_rec, j + 1, nb, kb, bb);
-    const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
-    const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
+    const double2 ika = ldg_stream2(ik0);
+    const double2 ikb = ldg_stream2(ik0 + NP);
     ik0 += 2 * (size_t)NP;
     double t[4], ex[4];
     if (SH) { t[0] = kr0 + ka; t[1] = kr1 + ka; t[2] = kr0 + kb; t[3] = kr1 + kb; }
@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
         s_int[1] = isfinite(chk) ? 0 : 1;
       }
       // ---- P1: nu, shared exponent terms, hot-loop record (thread per training point)
+#pragma unroll 2
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
@@ -580,8 +581,8 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
       double na[EV], nb[EV], ba[E], bb[E], ka, kb;
       uni_load_rec<EV>(s_rec, j, na, ka, ba);
       uni_load_rec<EV>(s_rec, j + 1, nb, kb, bb);
-      const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
-      const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
+      const double2 ika = ldg_stream2(ik0);
+      const double2 ikb = ldg_stream2(ik0 + NP);
       double c[4] = {-wb0 * ika.x, -wb1 * ika.y, -wb0 * ikb.x, -wb1 * ikb.y};
       ik0 += 2 * (size_t)NP;
 #pragma unroll
@@ -977,6 +978,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
       for (int k = 0; k < P; k++) vp[k] = 0.0;
 #pragma unroll
       for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = 0.0;
+#pragma unroll 2
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll

@@ -179,3 +179,23 @@ def test_prepare_inference_chooses_append_or_full_refactorisation():
     model.incremental_updates = True
     model.prepare_inference(x2[:30], y[:30])                          # shrank
     assert model.last_prepare_mode == "full" and eng.N == 30
+
+
+def test_cost_binding_follows_in_place_changes_of_the_reward_config():
+    """The reference re-reads config.reward at every objective evaluation (gp_mpc_controller.py:269); the fused kernels
+    get the cost description uploaded once, so the controller must notice in-place edits (tensor contents, scalar
+    fields) as well as a replaced object -- its cache key covers identities, tensor version counters and scalars."""
+    from rl_gp_mpc import GpMpcController
+    from rl_gp_mpc.config_classes.total_config import Config
+    cfg = Config()
+    r = cfg.reward
+    key0 = GpMpcController._cost_fingerprint(r)
+    assert GpMpcController._cost_fingerprint(r) == key0                 # stable while nothing changes
+    r.weight_matrix_cost[0, 0] += 1.0                                    # in-place edit of a tensor
+    key1 = GpMpcController._cost_fingerprint(r)
+    assert key1 != key0
+    r.exploration_factor = r.exploration_factor + 0.5                    # scalar field
+    key2 = GpMpcController._cost_fingerprint(r)
+    assert key2 != key1
+    r.target_state_action_norm = r.target_state_action_norm.clone()     # replaced tensor object
+    assert GpMpcController._cost_fingerprint(r) != key2
