@@ -42,14 +42,14 @@ case "$cmd" in
         objs="$objs $CSRC/gpmpc_inst_ev$n.o"
       fi
     done
-    nvcc $ARCH -shared -o "$OUT/libgpmpc_$name.so" "$CSRC/gpmpc_api.o" "$CSRC/gpmpc_prepare.o" "$CSRC/gpmpc_rollout.o" $objs -lcudart
+    nvcc $ARCH -shared -o "$OUT/libgpmpc_$name.so" "$CSRC/gpmpc_api.o" "$CSRC/gpmpc_prepare.o" "$CSRC/gpmpc_rollout.o" "$CSRC/gpmpc_optim.o" $objs -lcudart
     ls -la "$OUT/libgpmpc_$name.so"
     ;;
   build-all)
     flags=$3
     mkdir -p "$OUT"
     objs=""
-    for src in gpmpc_api gpmpc_prepare gpmpc_rollout gpmpc_inst_ev1 gpmpc_inst_ev2 gpmpc_inst_ev3 gpmpc_inst_ev4 gpmpc_inst_ev5 \
+    for src in gpmpc_api gpmpc_prepare gpmpc_rollout gpmpc_optim gpmpc_inst_ev1 gpmpc_inst_ev2 gpmpc_inst_ev3 gpmpc_inst_ev4 gpmpc_inst_ev5 \
                gpmpc_inst_ev6 gpmpc_inst_ev7 gpmpc_inst_ev8; do
       ( nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC -Xptxas -v $flags -c "$CSRC/$src.cu" -o "$OUT/${name}_${src#gpmpc_inst_}.o" \
              2> "$OUT/${name}_${src#gpmpc_inst_}.ptxas.log" || { cat "$OUT/${name}_${src#gpmpc_inst_}.ptxas.log" | grep -i error; exit 1; } ) &
