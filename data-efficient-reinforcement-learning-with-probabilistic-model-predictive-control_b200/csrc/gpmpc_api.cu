@@ -324,8 +324,13 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
   const size_t half_sm = (size_t)(227 * 1024) / 2 - 1024 - GPMPC_STATIC_SMEM;
   const int P = h->E * (h->E + 1) / 2;
   const int maxt = rollout_max_threads(EV);
-  const int G1 = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, maxt / 32, h->smem_optin);
-  const int G2 = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, maxt / 64, half_sm < h->smem_optin ? half_sm : h->smem_optin);
+  int G1 = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, maxt / 32, h->smem_optin, false);
+  p.lb_global = 0;
+  if (G1 < 2 && P > 1) {   // tight plan (e.g. E = 8, N = 1000 with the gradient): move lb[E][NP] to the global scratch
+    const int Gg = rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, maxt / 32, h->smem_optin, true);
+    if (Gg > G1) { G1 = Gg; p.lb_global = 1; }
+  }
+  const int G2 = p.lb_global ? 0 : rollout_pick_group(EV, grad, h->NP, h->DP, h->D, h->E, H, Na, maxt / 64, half_sm < h->smem_optin ? half_sm : h->smem_optin, false);
   if (G1 < 1) return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
   // measured at the headline shape (profiles/r02a_general_launch_plans.txt): 1 x 384 threads 237.6 k predictions/s,
   // 2 x 192 219.2 k, 2 x 128 223.3 k; the 128-register build: 1 x 512 236.5 k, 2 x 256 233.1 k -> one CTA per SM
@@ -352,9 +357,9 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
     while (p.seg > 8 && (64 / p.seg) * nrb * (nrb + 1) / 2 * ((P + p.cluster - 1) / p.cluster) < 2 * nw) p.seg /= 2;
   }
   if (const char* e = getenv("GPMPC_GEN_SEG")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) p.seg = v; }
-  *smem = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G, H, Na, *threads / 32);
+  *smem = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G, H, Na, *threads / 32, p.lb_global != 0);
   *grid = p.cluster > 1 ? B * p.cluster : (B < h->num_sms * ctas ? B : h->num_sms * ctas);
-  cudaError_t ce = h->ws_kk.ensure(sizeof(double) * (size_t)(*grid) * h->E * h->NP);
+  cudaError_t ce = h->ws_kk.ensure(sizeof(double) * 2 * (size_t)(*grid) * h->E * h->NP);
   if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "workspace allocation", ce);
   p.ws_kk = h->ws_kk.as<double>();
   ce = h->colcoef.ensure(sizeof(double) * 2 * (size_t)h->E * h->NP);

@@ -35,7 +35,8 @@ struct RolloutParams {
   double* actions_model; // (B, H, Na)
   double* stepM; double* stepS; double* stepV;   // mode 1 outputs (may be NULL)
   double* records;     // (B, H, rec.size) gradient-mode records (NULL in value mode)
-  double* ws_kk;       // (gridDim.x, E, NP) per-CTA scratch
+  double* ws_kk;       // (gridDim.x, 2, E, NP) per-CTA scratch: kk, and lb when lb_global
+  int lb_global;       // general kernel: lb[E][NP] of phases P1/P2 in the global scratch (shapes whose shared-memory plan is too tight)
   double* ws_gam;      // general kernel, gradient mode: (gridDim.x, group, NP) column sums of the sweeps (RED at L2)
   // ---- launch geometry
   int group;           // pairs per N^2 phase
@@ -61,8 +62,8 @@ struct BackwardParams {
   double* grad;        // (B, H*Na)
 };
 
-size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na, int nwarps);
-int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, int nwarps, size_t smem_limit);
+size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na, int nwarps, bool lb_global);
+int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, int nwarps, size_t smem_limit, bool lb_global);
 cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, int threads, size_t smem, cudaStream_t st);
 // Launch bounds of rollout_kernel<EV, .> = threads per SM of its launch plans: state dimensions <= 5 are built for 384
 // threads (<= 168 registers: two CTAs of 192 threads, or one of 384), larger ones for 256 threads (full register file).

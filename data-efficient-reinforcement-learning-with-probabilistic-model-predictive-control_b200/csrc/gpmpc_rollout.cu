@@ -5,16 +5,16 @@
 
 namespace gpmpc {
 
-size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na, int nwarps) {
-  SmemLayout L = make_layout(EV, grad, NP, DP, D, E, group, H, Na, nwarps);
+size_t rollout_smem_bytes(int EV, bool grad, int NP, int DP, int D, int E, int group, int H, int Na, int nwarps, bool lb_global) {
+  SmemLayout L = make_layout(EV, grad, NP, DP, D, E, group, H, Na, nwarps, lb_global);
   return (size_t)L.total * sizeof(double);
 }
 
-int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, int nwarps, size_t smem_limit) {
+int rollout_pick_group(int EV, bool grad, int NP, int DP, int D, int E, int H, int Na, int nwarps, size_t smem_limit, bool lb_global) {
   const int P = E * (E + 1) / 2;
   int best = 0;
   for (int g = 1; g <= P; g++) {
-    if (rollout_smem_bytes(EV, grad, NP, DP, D, E, g, H, Na, nwarps) <= smem_limit) best = g;
+    if (rollout_smem_bytes(EV, grad, NP, DP, D, E, g, H, Na, nwarps, lb_global) <= smem_limit) best = g;
   }
   return best;
 }

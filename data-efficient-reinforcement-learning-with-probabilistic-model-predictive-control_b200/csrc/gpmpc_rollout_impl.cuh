@@ -264,7 +264,10 @@ __device__ __forceinline__ void gen_load_nu(const double* __restrict__ row, doub
 //    gen_item); column sums gam_j by an 8-column transpose-reduce and a float64 RED at L2 (per-CTA scratch).
 // ---------------------------------------------------------------------------------------------
 #ifndef GEN_IK_PREFETCH
-#define GEN_IK_PREFETCH 1
+#define GEN_IK_PREFETCH 1     // diagonal pairs: L1 prefetch of the next round's iK rows (+ L1-allocating loads)
+#endif
+#ifndef GEN_ROWS4
+#define GEN_ROWS4 1        // off-diagonal pairs: four rows per lane (gen_cols4) when NP is a multiple of 128
 #endif
 template <int EV, bool GRAD, bool DIAG, bool SH>
 __device__ __forceinline__ void gen_cols(const double* __restrict__ s_nu, int DP, const double* __restrict__ s_kp,
@@ -314,8 +317,13 @@ __device__ __forceinline__ void gen_cols(const double* __restrict__ s_nu, int DP
       }
       if (DIAG) {
         const double2 bb2 = __ldg(reinterpret_cast<const double2*>(beta_b + j));
+#if GEN_IK_PREFETCH      // the prefetched rows are taken from L1
+        const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
+        const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
+#else
         const double2 ika = ldg_stream2(ik0);
         const double2 ikb = ldg_stream2(ik0 + NP);
+#endif
         ik0 += 2 * (size_t)NP;
         double c[4] = {-ce0 * ika.x, -ce1 * ika.y, -ce0 * ikb.x, -ce1 * ikb.y};
         c[0] = fma(cb0, bb2.x, c[0]);
@@ -470,6 +478,147 @@ __device__ __forceinline__ void gen_item(const RolloutParams& p, const double* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// Off-diagonal pairs, 128-row warp tiles: a lane owns FOUR adjacent rows (128 I + 4 lane + r) and takes the columns one at
+// a time (4 independent chains per warp = the 4 rows).  Per element this halves the column-record loads and the column-sum
+// reduction of the 2 x 2 variant (gen_cols) -- the shared-memory pipe is the co-limiter of this kernel (70 %) -- at the
+// price of twice the row state in registers (fits the 168 budget).  Used when NP is a multiple of 128.
+// ---------------------------------------------------------------------------------------------
+template <int EV, bool GRAD, bool SH>
+__device__ __forceinline__ void gen_cols4(const double* __restrict__ s_nu, int DP, const double* __restrict__ s_kp,
+                                          int jbeg, int jend, const double (&u)[4][EV], const double (&kr)[4],
+                                          const double (&be)[4], double (&rho)[4], double (&xi)[4][EV], int lane,
+                                          double* __restrict__ g_gam, double* __restrict__ scr) {
+  const double* __restrict__ pn = s_nu + (size_t)jbeg * DP;
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      double nj[EV];
+      gen_load_nu<EV>(pn, nj);
+      pn += DP;
+      const double2 cj = *reinterpret_cast<const double2*>(s_kp + 2 * (j0 + jj));   // {kap'_j, magic constant with the sign}
+      double t[4], w[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) t[r] = SH ? kr[r] + cj.x : cj.x;
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) t[r] = fma(u[r][e], nj[e], t[r]);     // nj[e] shared by four consecutive FMAs (operand reuse)
+      }
+      exp2s_x4_signed(t, w, cj.y, cj.y);
+#pragma unroll
+      for (int r = 0; r < 4; r++) rho[r] += w[r];
+      if (GRAD) {
+#pragma unroll
+        for (int e = 0; e < EV; e++) {
+#pragma unroll
+          for (int r = 0; r < 4; r++) xi[r][e] = fma(w[r], nj[e], xi[r][e]);
+        }
+        double vv = be[0] * w[0];
+        vv = fma(be[1], w[1], vv);
+        vv = fma(be[2], w[2], vv);
+        v[jj] = fma(be[3], w[3], vv);
+      }
+    }
+    if (GRAD) {
+      const double tot = col_reduce8s(v, lane, scr);
+      if (lane < 8) uni_red_add(g_gam + j0 + lane, tot);
+    }
+  }
+}
+
+template <int EV, bool GRAD>
+__device__ __forceinline__ void gen_item4(const RolloutParams& p, const double* __restrict__ s_nu,
+                                          const double* __restrict__ s_kp, const double* __restrict__ Qm,
+                                          const double* __restrict__ il2a, const double* __restrict__ il2b,
+                                          const double* __restrict__ kka, const double* __restrict__ beta_a, int I4,
+                                          int jbeg, int jend, int lane, double* __restrict__ g_gam,
+                                          double* __restrict__ acc, double* __restrict__ scr) {
+  constexpr int PV = EV * (EV + 1) / 2;
+  const int DP = p.DP, D = p.D;
+  const int i0 = 128 * I4 + 4 * lane;
+  const double* __restrict__ np0 = s_nu + (size_t)i0 * DP;
+  double u[4][EV], kr[4], be[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const double* nr = np0 + r * DP;
+    double z[EV];
+#pragma unroll
+    for (int e = 0; e < EV; e++) z[e] = nr[e] * il2a[e];
+    double k = kka[i0 + r];
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      double q = 0.0;
+#pragma unroll
+      for (int f = 0; f < EV; f++) q = fma(Qm[e * EV + f], z[f], q);
+      k = fma(z[e], q, k);
+      u[r][e] = (2.0 * GPMPC_EXP2S_SCALE) * q * il2b[e];
+    }
+    kr[r] = k * GPMPC_EXP2S_SCALE;
+  }
+  bool anyfar = false;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const double e = uni_row_factor(kr[r]);          // kr becomes the residual shift
+    be[r] = __ldg(beta_a + i0 + r) * e;
+    anyfar = anyfar || kr[r] != 0.0;
+  }
+  const bool far = __any_sync(0xffffffffu, anyfar);
+  double rho[4], xi[4][EV];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    rho[r] = 0.0;
+#pragma unroll
+    for (int e = 0; e < EV; e++) xi[r][e] = 0.0;
+  }
+  jend = min(jend, (p.N + 7) & ~7);
+  if (far) gen_cols4<EV, GRAD, true>(s_nu, DP, s_kp, jbeg, jend, u, kr, be, rho, xi, lane, g_gam, scr);
+  else gen_cols4<EV, GRAD, false>(s_nu, DP, s_kp, jbeg, jend, u, kr, be, rho, xi, lane, g_gam, scr);
+  double accS = 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    rho[r] *= be[r];
+    accS += rho[r];
+    if (GRAD) {
+#pragma unroll
+      for (int e = 0; e < EV; e++) xi[r][e] *= be[r];
+    }
+  }
+  accS = warp_sum(accS);
+  if (lane == 0) atomicAdd(acc, accS);
+  if (GRAD) {
+    double vs[GPMPC_MAX_D], vp[PV];
+#pragma unroll
+    for (int d = 0; d < GPMPC_MAX_D; d++) vs[d] = 0.0;
+#pragma unroll
+    for (int q = 0; q < PV; q++) vp[q] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double* nr = np0 + r * DP;
+#pragma unroll
+      for (int d = 0; d < GPMPC_MAX_D; d++)
+        if (d < D) vs[d] = fma(rho[r] * il2a[d], nr[d], vs[d]);
+      double za[EV], xs[EV];
+#pragma unroll
+      for (int e = 0; e < EV; e++) { za[e] = nr[e] * il2a[e]; xs[e] = xi[r][e] * il2b[e]; }
+      int q = 0;
+#pragma unroll
+      for (int k = 0; k < EV; k++) {
+        const double rk = rho[r] * za[k];
+#pragma unroll
+        for (int l = k; l < EV; l++) {
+          double a0 = fma(rk, za[l], vp[q]);
+          a0 = fma(za[k], xs[l], a0);
+          vp[q] = fma(za[l], xs[k], a0);
+          q++;
+        }
+      }
+    }
+    gen_warp_sums_add<PV>(vp, vs, D, lane, acc + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
 // Launch plans (host: gpmpc_api.cu; GEN_MAXT in gpmpc_internal.h): state dimensions <= 5: 384 threads per SM with <= 168 registers
@@ -481,9 +630,10 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x, warp = tid >> 5, nwarps = NT >> 5;
   const int E = p.E, D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
   const int P = E * (E + 1) / 2, G = p.group;
-  const SmemLayout L = make_layout(EV, GRAD, NP, DP, D, E, G, (p.mode == 0) ? H : 0, Na, nwarps);
+  const SmemLayout L = make_layout(EV, GRAD, NP, DP, D, E, G, (p.mode == 0) ? H : 0, Na, nwarps, p.lb_global != 0);
   double* s_nu = sm + L.nu;
-  double* s_lb = sm + L.grp;  // aliases the group arrays (only live in P1/P2)
+  // lb[E][NP]: aliases the column records in shared memory (only live in P1/P2), or the CTA's global scratch (lb_global)
+  double* s_lb = p.lb_global ? p.ws_kk + ((size_t)blockIdx.x * 2 + 1) * E * NP : sm + L.grp;
   double* s_kap = sm + L.kap;
   double* s_colred = sm + L.colred + warp * COLRED_WARP;   // this warp's scratch of the column-sum reduction (gradient mode)
   double* s_out = sm + L.out;
@@ -533,7 +683,7 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
     int ab = s_int[2 + pr];
     s_Wd[o] = s_il2[(ab >> 4) * D + e] + s_il2[(ab & 15) * D + e];
   }
-  double* kk = p.ws_kk + (size_t)blockIdx.x * E * NP;
+  double* kk = p.ws_kk + (size_t)blockIdx.x * 2 * E * NP;
   // column sums gam_j of the sweeps (float64 RED at L2), one row per pair of the group; zero on entry and re-zeroed
   // by their consumer after every step
   double* g_gam = GRAD ? p.ws_gam + (size_t)blockIdx.x * G * NP : nullptr;
@@ -848,7 +998,8 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
           // contiguous run of the diagonal pairs' chunks and one of the off-diagonal pairs' chunks -- balanced whatever the
           // cost ratio; even warps start with their diagonal run, odd warps with the off-diagonal one (mixed L2 traffic).
           const int CH = p.seg, nrb = NP / 64, cpr = NP / CH, cpt = 64 / CH;
-          const int nOff = nrb * cpr, nDia = cpt * nrb * (nrb + 1) / 2;
+          const bool rows4 = GEN_ROWS4 && (NP % 128 == 0);          // off-diagonal pairs: 128-row warp tiles (gen_item4)
+          const int nOff = (rows4 ? nrb / 2 : nrb) * cpr, nDia = cpt * nrb * (nrb + 1) / 2;
 #pragma unroll 1
           for (int ph = 0; ph < 2; ph++) {
             const bool dia = ((ph ^ warp) & 1) == 0;
@@ -879,6 +1030,14 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
                                            p.beta + (size_t)a * NP, p.beta + (size_t)b * NP, p.iK + (size_t)a * NP * NP, I,
                                            64 * I + CH * (c0 - base), 64 * I + CH * (ce - base), lane, g_gam + pl * NP,
                                            s_pacc + pl * L.paccN, s_colred);
+                  c0 = ce;
+                }
+              } else if (rows4) {
+                while (c0 < c1) {
+                  const int I = c0 / cpr, ce = min(c1, (I + 1) * cpr);
+                  gen_item4<EV, GRAD>(p, s_nu, s_kap + 2 * pl * NP, Qm, s_il2 + a * D, s_il2 + b * D, kk + a * NP,
+                                      p.beta + (size_t)a * NP, I, CH * (c0 - I * cpr), CH * (ce - I * cpr), lane,
+                                      g_gam + pl * NP, s_pacc + pl * L.paccN, s_colred);
                   c0 = ce;
                 }
               } else {

@@ -16,7 +16,9 @@ struct SmemLayout {
 // G = pairs per N^2 phase: the only per-pair shared-memory arrays are the column records {kap'_j, sign constant} (2 NP
 // doubles per pair, one 16-byte load per column in the hot loop);
 // the row sums of the sweeps stay in registers and the column sums live in a per-CTA global scratch (L2)
-HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G, int H, int Na, int nwarps) {
+// lb_global: the per-GP weights lb[E][NP] of phases P1/P2 live in the CTA's global scratch instead of shared memory
+// (large shapes: E = 8, N = 1000 with the gradient would not fit otherwise)
+HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G, int H, int Na, int nwarps, bool lb_global = false) {
   SmemLayout L;
   const int P = E * (E + 1) / 2;
   L.PV = EV * (EV + 1) / 2;
@@ -26,9 +28,10 @@ HD SmemLayout make_layout(int EV, bool grad, int NP, int DP, int D, int E, int G
   int grp = 2 * G * NP;
   L.nOut = 1 + D + (grad ? (EV * D + EV * L.PV) : 0);
   // the lb[E][NP] array of phases P1/P2 and the moment outputs of P2/P2b alias the column terms of P3
-  if (grp < E * NP + E * L.nOut) grp = E * NP + E * L.nOut;
+  const int lbn = lb_global ? 0 : E * NP;
+  if (grp < lbn + E * L.nOut) grp = lbn + E * L.nOut;
   L.kap = L.grp;
-  L.out = L.grp + E * NP;
+  L.out = L.grp + lbn;
   o += grp;
   o = (o + 1) & ~1;   // 16-byte aligned (col_reduce8s stores double2)
   L.colred = o; if (grad) o += nwarps * 320;   // per-warp scratch of col_reduce8s (COLRED_WARP doubles)

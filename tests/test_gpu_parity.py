@@ -478,3 +478,16 @@ def test_fused_lbfgs_update_kernel_follows_its_torch_specification(n, history, i
     np.testing.assert_allclose(fb.cpu().numpy(), fa.cpu().numpy(), rtol=0, atol=1e-6)
     assert float((fa - fun(x0)[0]).nan_to_num(0.0).max()) <= 0.0                            # never worse than the start
 
+
+def test_c5_full_size_gradient_general_path_agrees_with_uniform_path():
+    """BASELINE.json config 5 dims at the full training-set size (E=8, D=11, N=1000) WITH the gradient on the general
+    (per-GP hyper-parameter) kernel: its shared-memory plan only fits with the per-GP weights of the mean part in the
+    global scratch (gpmpc_api.cu, lb_global).  With identical hyper-parameters the general and the uniform kernels
+    compute the same function by different algorithms (forward-mode Jacobians vs reverse sweep): they must agree."""
+    cfg = make_workload("C5", B=2, H=2, seed=55)
+    uni = rollout(make_engine(cfg, 0), cfg)
+    gen = rollout(make_engine(cfg, 1), cfg)
+    np.testing.assert_allclose(gen["cost"], uni["cost"], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(gen["grad"], uni["grad"], rtol=0, atol=ATOL_GRAD)
+    np.testing.assert_allclose(gen["states_var_pred"], uni["states_var_pred"], rtol=0, atol=ATOL)
+    assert np.abs(uni["grad"]).max() > 1e-6
