@@ -183,15 +183,16 @@ def sass_counts(E):
         out = {"source": "profiles/sass_loop_counts.json (tools/sass_counts.py: cuobjdump -sass of the built library)"}
         out["uniform_fwd"] = tab["uniform_fwd"]["float64_per_element"]
         out["uniform_bwd"] = tab["uniform_bwd"]["float64_per_element"]
-        out["general_grad"] = (tab["general_grad"]["float64_per_element_off_diagonal"],
-                               tab["general_grad"]["float64_per_element_diagonal"])
-        out["general_value"] = (tab["general_value"]["float64_per_element_off_diagonal"],
-                                tab["general_value"]["float64_per_element_diagonal"])
+        for key in ("general_grad", "general_value"):      # (off-diagonal 2 rows per lane, diagonal, off-diagonal 4 rows per lane)
+            t = tab[key]
+            out[key] = (t["float64_per_element_off_diagonal"], t["float64_per_element_diagonal"],
+                        t.get("float64_per_element_off_diagonal_rows4", t["float64_per_element_off_diagonal"]))
         return out
     except Exception:
         return {"source": "source-level count (profiles/sass_loop_counts.json not readable)",
                 "uniform_fwd": E + 7 + E + 1, "uniform_bwd": E + 7 + (E + 1) + 3.06 + E,
-                "general_grad": (E + 7 + 1 + E + 1.56, E + 7 + 4 + E + 1.31), "general_value": (E + 8, E + 10)}
+                "general_grad": (E + 7 + 1 + E + 1.56, E + 7 + 4 + E + 1.31, E + 7 + 1 + E + 1.28),
+                "general_value": (E + 8, E + 10, E + 8)}
 
 
 def sweep_elements(uniform, E, N):
@@ -212,8 +213,9 @@ def fp64_model(kernel, E, N, counts):
     if kernel in ("uniform_fwd", "uniform_bwd"):
         return sweep_elements(True, E, N)["triangle"] * counts[kernel]
     el = sweep_elements(False, E, N)
-    off, dia = counts[kernel]
-    return el["off_diagonal"] * off + el["diagonal"] * dia
+    off, dia, off4 = counts[kernel]
+    rows4 = ((N + 63) // 64 * 64) % 128 == 0        # 128-row warp tiles for the off-diagonal pairs (gen_cols4)
+    return el["off_diagonal"] * (off4 if rows4 else off) + el["diagonal"] * dia
 
 
 def ncu_traffic(kernel_prefix, workload):

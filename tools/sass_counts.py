@@ -63,7 +63,9 @@ def main():
             fn = sorted(fns)[0]   # (uniform forward: the 128-thread build when it exists)
             sass = subprocess.run(["cuobjdump", "-sass", "-fun", fn, lib], capture_output=True, text=True).stdout
             # a sweep iteration evaluates one exp per element: exactly `elems` clamps (VIMNMX) per iteration
-            loops = [l for l in loops_of(sass) if l["vimnmx"] == elems]
+            all_loops = loops_of(sass)
+            loops = [l for l in all_loops if l["vimnmx"] == elems]
+            loops4 = [l for l in all_loops if l["vimnmx"] == 2 * elems and l["ldg128"] == 0]   # general kernel: 4 rows per lane
             if key.startswith("uniform"):
                 sweep = loops
                 best = min(sweep, key=lambda l: l["float64"]) if sweep else None
@@ -81,6 +83,11 @@ def main():
                                   "float64_per_element_diagonal": d["float64"] / elems,
                                   "other_per_element_off_diagonal": o["other"] / elems,
                                   "other_per_element_diagonal": d["other"] / elems}
+                    if loops4:      # off-diagonal pairs when NP is a multiple of 128 (gen_cols4: 2 * elems per iteration)
+                        o4 = min(loops4, key=lambda l: l["float64"])
+                        entry[key].update({"loop_off_diagonal_rows4": o4,
+                                           "float64_per_element_off_diagonal_rows4": o4["float64"] / (2 * elems),
+                                           "other_per_element_off_diagonal_rows4": o4["other"] / (2 * elems)})
         if entry:
             table[str(E)] = entry
     out = os.path.join(ROOT, "profiles", "sass_loop_counts.json")
