@@ -141,19 +141,18 @@ __device__ __forceinline__ void exp2s_x4_signed(const double (&xin)[4], double (
   for (int c = 0; c < 4; c++) res[c] = __fma_rn(t[c], p[c], t[c]);
 }
 
-// iK is streamed: every value is used once per prediction, so its lines should not displace the small arrays the per-step
-// phases re-read (x, betaT) from L1.  GPMPC_IK_NO_L1 = 1: 16-byte read-only load that does not allocate in L1.
-#ifndef GPMPC_IK_NO_L1
-#define GPMPC_IK_NO_L1 1
-#endif
+// iK loads of the sweeps (16 bytes: the lane's two adjacent rows of one column).  NO_L1: read-only load that does not
+// allocate in L1 -- every value is used once per prediction by THIS CTA.  Measured (profiles/r02q_ik_l1_policy_and_unroll.txt):
+// the reverse sweep at E <= 5 gains 2 % from it, the forward sweep and the E = 8 kernels LOSE 4-8 % (co-resident CTAs walk
+// the same tile order, one candidate behind the other: L1 serves the second one), so only that kernel streams.
+template <bool NO_L1>
 __device__ __forceinline__ double2 ldg_stream2(const double* p) {
-#if GPMPC_IK_NO_L1
-  double2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-#else
+  if (NO_L1) {
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+  }
   return __ldg(reinterpret_cast<const double2*>(p));
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------

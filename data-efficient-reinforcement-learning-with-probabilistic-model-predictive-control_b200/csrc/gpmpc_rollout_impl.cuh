@@ -321,8 +321,8 @@ __device__ __forceinline__ void gen_cols(const double* __restrict__ s_nu, int DP
         const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
         const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
 #else
-        const double2 ika = ldg_stream2(ik0);
-        const double2 ikb = ldg_stream2(ik0 + NP);
+        const double2 ika = ldg_stream2<true>(ik0);
+        const double2 ikb = ldg_stream2<true>(ik0 + NP);
 #endif
         ik0 += 2 * (size_t)NP;
         double c[4] = {-ce0 * ika.x, -ce1 * ika.y, -ce0 * ikb.x, -ce1 * ikb.y};

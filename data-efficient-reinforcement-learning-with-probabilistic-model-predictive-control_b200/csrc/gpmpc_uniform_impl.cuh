@@ -55,6 +55,9 @@ constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forwar
 #ifndef UNI_BWD_COLRED_SMEM
 #define UNI_BWD_COLRED_SMEM 0
 #endif
+#ifndef UNI_P1_UNROLL
+#define UNI_P1_UNROLL 2     // forward record phase: training points in flight per thread
+#endif
 #ifndef UNI_MINB
 #define UNI_MINB(EV) ((EV) <= 5 ? 2 : 1)
 #endif
@@ -110,8 +113,8 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
     double na[EV], nb[EV], ba[E], bb[E], ka, kb;
     uni_load_rec<EV>(s_rec, j, na, ka, ba);
     uni_load_rec<EV>(s_rec, j + 1, nb, kb, bb);
-    const double2 ika = ldg_stream2(ik0);
-    const double2 ikb = ldg_stream2(ik0 + NP);
+    const double2 ika = ldg_stream2<false>(ik0);
+    const double2 ikb = ldg_stream2<false>(ik0 + NP);
     ik0 += 2 * (size_t)NP;
     double t[4], ex[4];
     if (SH) { t[0] = kr0 + ka; t[1] = kr1 + ka; t[2] = kr0 + kb; t[3] = kr1 + kb; }
@@ -368,7 +371,11 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
       }
       // ---- P1: nu, shared exponent terms, hot-loop record (thread per training point)
       // two training points per thread in flight: this phase is load / dependent-FMA latency (P1a 16.6 k -> 13.8 k clocks)
+#if UNI_P1_UNROLL == 2
 #pragma unroll 2
+#else
+#pragma unroll 1
+#endif
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
@@ -582,8 +589,8 @@ __device__ __forceinline__ void uni_bwd_cols(const RolloutParams& p, const doubl
       double na[EV], nb[EV], ba[E], bb[E], ka, kb;
       uni_load_rec<EV>(s_rec, j, na, ka, ba);
       uni_load_rec<EV>(s_rec, j + 1, nb, kb, bb);
-      const double2 ika = ldg_stream2(ik0);
-      const double2 ikb = ldg_stream2(ik0 + NP);
+      const double2 ika = ldg_stream2<(EV <= 5)>(ik0);
+      const double2 ikb = ldg_stream2<(EV <= 5)>(ik0 + NP);
       double c[4] = {-wb0 * ika.x, -wb1 * ika.y, -wb0 * ikb.x, -wb1 * ikb.y};
       ik0 += 2 * (size_t)NP;
 #pragma unroll
