@@ -477,7 +477,7 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       if (fwd && E <= 5 && fit >= 3) { ctas = 3; *thr = 128; }
       if (const char* e = getenv(env_thr)) { int v = atoi(e); if (v == 128 || v == 256 || (!fwd && v == 192)) *thr = v; }   // tuning aid
       if (const char* e = getenv(env_ctas)) { int v = atoi(e); if (v >= 1 && v <= fit) ctas = v; }
-      if (E > 5) { *thr = 256; ctas = 1; }   // large state dims: 255-register kernels, one CTA per SM
+      if (E > 5) { *thr = UNI_MAXT(E); ctas = 1; }   // large state dims: one CTA per SM (tensor-core sweeps: 384 threads)
       if (ctas * (*thr) > 512) ctas = 512 / (*thr);
       int g = h->num_sms * ctas;
       *grd = B < g ? B : g;

@@ -113,6 +113,38 @@ __device__ __forceinline__ void exp2s_x4(const double (&xin)[4], double (&res)[4
   for (int c = 0; c < 4; c++) res[c] = __fma_rn(t[c], p[c], t[c]);
 }
 
+// N at once (N independent chains), same stages as exp2s_x4.
+template <int N, bool IMM = true>
+__device__ __forceinline__ void exp2s_xn(const double (&xin)[N], double (&res)[N]) {
+  const double SHIFT = 6755399441055744.0;
+  double x[N], kd[N], f[N], p[N], t[N];
+  int n[N];
+#pragma unroll
+  for (int c = 0; c < N; c++) x[c] = exp2s_clamp(xin[c]);
+#pragma unroll
+  for (int c = 0; c < N; c++) kd[c] = x[c] + SHIFT;
+#pragma unroll
+  for (int c = 0; c < N; c++) { n[c] = __double2loint(kd[c]); kd[c] -= SHIFT; }
+#pragma unroll
+  for (int c = 0; c < N; c++) { f[c] = x[c] - kd[c]; t[c] = exp2s_entry<IMM>(n[c]); }
+#pragma unroll
+  for (int c = 0; c < N; c++) p[c] = __fma_rn(GPMPC_EXP2S_C3, f[c], GPMPC_EXP2S_C2);
+#pragma unroll
+  for (int c = 0; c < N; c++) p[c] = __fma_rn(p[c], f[c], GPMPC_EXP2S_C1);
+#pragma unroll
+  for (int c = 0; c < N; c++) p[c] *= f[c];
+#pragma unroll
+  for (int c = 0; c < N; c++) res[c] = __fma_rn(t[c], p[c], t[c]);
+}
+
+// float64 tensor-core tile product D (8 x 8) = A (8 x 4) B (4 x 8) + D, one warp.  Fragments (g = lane >> 2, q = lane & 3):
+//   a = A[g][q] ,  b = B[q][g] ,  d0, d1 = D[g][2 q], D[g][2 q + 1].
+// DMMA runs on the float64 pipe (no extra flops: profiles/r01_micro_dmma_mix.txt) but takes ONE issue slot for 8 warp-DFMAs
+// worth of work and does not pay the three-register-operand penalty of a DFMA (profiles/r02_micro_dfma_operands.txt).
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // exp2s_x4 with a SIGN per pair of results: res[0], res[1] = +-exp(xin[0]), +-exp(xin[1]) (sign a), res[2], res[3] (sign b).
 // The sign costs nothing per element: the caller passes the magic constant of the range reduction as
 //   sh = SHIFT + (negative ? 2^22 : 0)      (exp2s_shift: high word 0x43380000, low word 0 or 0x400000)

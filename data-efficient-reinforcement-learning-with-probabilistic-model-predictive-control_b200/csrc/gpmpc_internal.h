@@ -89,6 +89,16 @@ cudaError_t launch_colcoef(const double* beta, double* colcoef, int n, cudaStrea
 
 // static shared memory of the rollout kernels: the 16 KB table of exp2s (gpmpc_common.cuh) + a few scalars
 constexpr size_t GPMPC_STATIC_SMEM = 16 * 1024 + 128;   // sizeof(GpmpcStaticSmem) rounded up
+// Large state dimensions (E >= 6): tensor-core sweeps (uni_*_mma8 in gpmpc_uniform_impl.cuh), one CTA of 384 threads
+// (<= 168 registers) per SM instead of 256 threads at 255 registers + spills.
+#ifndef UNI_MMA8
+#define UNI_MMA8 1
+#endif
+#define UNI_USE_MMA8(EV) (UNI_MMA8 && (EV) >= 6)
+#ifndef UNI_MMA8_THREADS
+#define UNI_MMA8_THREADS 256   // (384 threads at <= 168 registers: same sweep time, slower small-matrix phases)
+#endif
+#define UNI_MAXT(EV) (UNI_USE_MMA8(EV) ? UNI_MMA8_THREADS : 256)
 constexpr int UNIFORM_MAX_THREADS = 256;   // uniform kernels: __launch_bounds__(256, 2) -> <= 128 registers
 
 }  // namespace gpmpc

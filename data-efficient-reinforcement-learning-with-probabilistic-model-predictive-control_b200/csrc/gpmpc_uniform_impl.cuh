@@ -66,9 +66,11 @@ constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forwar
 // budget ptxas hoists the record / iK loads of a loop body to its top and interleaves the stages of both column pairs
 // (forward 60.6 -> 57.9 ms at the headline shape).  The host picks it when three CTAs fit the shared memory.
 #define UNI_FWD_MINCTAS(EV, MAXT) ((MAXT) == 128 && (EV) <= 5 ? 3 : UNI_MINB(EV))
-// tuning hook (tools/variants.sh): launch bounds of the reverse-sweep kernel, e.g. -DUNI_BWD_MAXT=128 -DUNI_BWD_MINCTAS_ALL=3
-#ifndef UNI_BWD_MAXT
-#define UNI_BWD_MAXT UNIFORM_MAX_THREADS
+// tuning hook (tools/variants.sh): launch bounds of the reverse-sweep kernel, e.g. -DUNI_BWD_MAXT_ALL=128 -DUNI_BWD_MINCTAS_ALL=3
+#ifdef UNI_BWD_MAXT_ALL
+#define UNI_BWD_MAXT(EV) UNI_BWD_MAXT_ALL
+#else
+#define UNI_BWD_MAXT(EV) UNI_MAXT(EV)
 #endif
 #ifdef UNI_BWD_MINCTAS_ALL
 #define UNI_BWD_MINCTAS(EV) UNI_BWD_MINCTAS_ALL
@@ -80,6 +82,33 @@ constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forwar
 // forward hot loop: full sweep, rows {64 I + lane, +32}, columns [jbeg, jend)
 //   r_b,i += Eh_ij beta_b,j  (E FMAs),  tr += Eh_ij iK_ij  (1 FMA)   [gp_model.py:169-175 for all (a,b) at once]
 // ---------------------------------------------------------------------------------------------
+// training inputs x (read by every CTA at every step, N D doubles): with UNI_X_EVICT_LAST the loads ask L1 to keep them
+// while the iK stream of the sweeps passes through
+#ifndef UNI_X_EVICT_LAST
+#define UNI_X_EVICT_LAST 0
+#endif
+#ifndef UNI_FWD_IK_EVICT_FIRST
+#define UNI_FWD_IK_EVICT_FIRST 0
+#endif
+__device__ __forceinline__ double uni_ldg_x(const double* p) {
+#if UNI_X_EVICT_LAST
+  double v;
+  asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double2 uni_ldg_ik_fwd(const double* p) {
+#if UNI_FWD_IK_EVICT_FIRST
+  double2 v;
+  asm("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const double2*>(p));
+#endif
+}
+
 template <int EV>
 __device__ __forceinline__ void uni_load_rec(const double* __restrict__ s_rec, int j, double (&nu)[EV],
                                              double& kap, double (&beta)[EV]) {
@@ -113,8 +142,8 @@ __device__ __forceinline__ void uni_fwd_cols(const RolloutParams& p, const doubl
     double na[EV], nb[EV], ba[E], bb[E], ka, kb;
     uni_load_rec<EV>(s_rec, j, na, ka, ba);
     uni_load_rec<EV>(s_rec, j + 1, nb, kb, bb);
-    const double2 ika = ldg_stream2<false>(ik0);
-    const double2 ikb = ldg_stream2<false>(ik0 + NP);
+    const double2 ika = uni_ldg_ik_fwd(ik0);
+    const double2 ikb = uni_ldg_ik_fwd(ik0 + NP);
     ik0 += 2 * (size_t)NP;
     double t[4], ex[4];
     if (SH) { t[0] = kr0 + ka; t[1] = kr1 + ka; t[2] = kr0 + kb; t[3] = kr1 + kb; }
@@ -225,6 +254,337 @@ __device__ __forceinline__ void uni_fwd_item(const RolloutParams& p, const doubl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant of the forward sweep (UNI_USE_MMA): the exponent tile  t_ij = kap_j + u_i . nu_j  of 8 rows x 8
+// columns is ONE float64 DMMA (m8n8k4: k = state dimension, zero-padded / two steps for E != 4) instead of E DFMAs per
+// element.  A warp tile is 32 rows x 8 columns per round: lane (g, q) = (lane >> 2, lane & 3) owns rows ib + 8 m + g
+// (m = 0..3) and columns j0 + 2 q, j0 + 2 q + 1 -- the DMMA accumulator layout, 8 independent elements per lane.
+//   A fragment  u_{ib + 8 m + g, 4 ks + q}   (loop invariant, registers)
+//   B fragment  nu_{j0 + g, 4 ks + q}         (one LDS.64 per round)
+//   C           kap_{j0 + 2 q}, kap_{j0 + 2 q + 1}  (+ the residual row shift of far-away rows, SH)
+// Everything after the exponent is per element as before (exp2s, r_b,i += Eh beta_b,j, tr += Eh iK_ij); a row's sums are
+// spread over the 4 lanes of its quad, which the linear warp reduction at the end of the item does not care about.
+// 32-row tiles also halve the redundant part of the diagonal tiles (32 x 32 swept in full with half weights).
+// ---------------------------------------------------------------------------------------------
+#ifndef UNI_MMA
+#define UNI_MMA 0          // 1: DMMA exponent / coefficient tiles in both sweeps; 2: forward sweep on the quad layout with DFMAs
+#endif
+#define UNI_USE_MMA(EV) (UNI_MMA == 1 && (EV) == 4)
+#define UNI_USE_QUAD_FWD(EV) ((UNI_MMA == 1 || UNI_MMA == 2) && (EV) == 4)
+
+template <int EV, bool SH>
+__device__ __forceinline__ void uni_fwd_cols_mma(const RolloutParams& p, const double* __restrict__ s_rec, int ib,
+                                                 int jbeg, int jend, int lane, const double (&ua)[4][(EV + 3) / 4],
+                                                 const double (&uf)[4][EV], const double (&kr)[4], double (&r)[4][EV],
+                                                 double (&tr)[4]) {
+  constexpr int E = EV, RLEN = 2 * EV + 2, KS = (EV + 3) / 4;
+  constexpr bool MMA = UNI_MMA == 1;   // else: the exponent with DFMAs on the same layout (uf = the rows' full u vectors)
+  const int g = lane >> 2, q = lane & 3;
+  const size_t rs = 8 * (size_t)p.NP;
+  const double* __restrict__ ik = p.iK + (size_t)(ib + g) * p.NP + jbeg + 2 * q;   // rows of the symmetric iK, two adjacent columns
+  const double* __restrict__ rb = s_rec + (jbeg + g) * RLEN + q;                    // B fragment source
+  const double* __restrict__ rc = s_rec + (jbeg + 2 * q) * RLEN;                    // the lane's two columns
+#pragma unroll 1
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    double bf[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) bf[ks] = MMA ? rb[4 * ks] : 0.0;   // slots >= EV hold finite record data; their A entries are zero
+    const double ka0 = rc[EV], ka1 = rc[RLEN + EV];
+    double be0[E], be1[E];
+#pragma unroll
+    for (int b = 0; b < E; b++) { be0[b] = rc[EV + 1 + b]; be1[b] = rc[RLEN + EV + 1 + b]; }
+    double2 ikv[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) ikv[m] = ldg_stream2<false>(ik + m * rs);
+    double t[8], ex[8];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      double d0 = SH ? ka0 + kr[m] : ka0, d1 = SH ? ka1 + kr[m] : ka1;
+      if (MMA) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) dmma_m8n8k4(d0, d1, ua[m][ks], bf[ks]);
+      }
+      t[2 * m] = d0;
+      t[2 * m + 1] = d1;
+    }
+    if (!MMA) {
+      double n0[EV], n1[EV];
+#pragma unroll
+      for (int e = 0; e < EV; e++) { n0[e] = rc[e]; n1[e] = rc[RLEN + e]; }
+#pragma unroll
+      for (int e = 0; e < EV; e++) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {   // serpentine: every FMA shares a register operand with its predecessor
+          if (m & 1) { t[2 * m + 1] = fma(uf[m][e], n1[e], t[2 * m + 1]); t[2 * m] = fma(uf[m][e], n0[e], t[2 * m]); }
+          else       { t[2 * m] = fma(uf[m][e], n0[e], t[2 * m]); t[2 * m + 1] = fma(uf[m][e], n1[e], t[2 * m + 1]); }
+        }
+      }
+    }
+    exp2s_xn<8>(t, ex);
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int b = 0; b < E; b++) r[m][b] = fma(ex[2 * m], be0[b], r[m][b]);
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int b = 0; b < E; b++) r[m][b] = fma(ex[2 * m + 1], be1[b], r[m][b]);
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      tr[m] = fma(ex[2 * m], ikv[m].x, tr[m]);
+      tr[m] = fma(ex[2 * m + 1], ikv[m].y, tr[m]);
+    }
+    ik += 8;
+    rb += 8 * RLEN;
+    rc += 8 * RLEN;
+  }
+}
+
+// One run of columns [jbeg, jend) (multiples of 8, jbeg >= 32 I) of the 32-row block I: see uni_fwd_item for the algebra.
+template <int EV>
+__device__ __forceinline__ void uni_fwd_item_mma(const RolloutParams& p, const double* __restrict__ s_rec,
+                                                 const double* __restrict__ Qm, const double* __restrict__ il2, int I,
+                                                 int jbeg, int jend, int lane, double* s_part) {
+  constexpr int E = EV, RLEN = 2 * EV + 2, KS = (EV + 3) / 4;
+  const int g = lane >> 2, q = lane & 3, ib = 32 * I;
+  double ua[4][KS], uf[4][EV], kr[4], ei[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double* rec = s_rec + (ib + 8 * m + g) * RLEN;
+    kr[m] = rec[EV];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      const int ee = 4 * ks + q;
+      double acc = 0.0;
+      if (UNI_MMA == 1 && ee < EV) {
+#pragma unroll
+        for (int f = 0; f < EV; f++) acc = fma(Qm[ee * EV + f], rec[f] * il2[f], acc);
+        acc *= (2.0 * GPMPC_EXP2S_SCALE) * il2[ee];   // exponent in table units (exp2s)
+      }
+      ua[m][ks] = acc;
+    }
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      double acc = 0.0;
+      if (UNI_MMA != 1) {
+#pragma unroll
+        for (int f = 0; f < EV; f++) acc = fma(Qm[e * EV + f], rec[f] * il2[f], acc);
+        acc *= (2.0 * GPMPC_EXP2S_SCALE) * il2[e];
+      }
+      uf[m][e] = acc;
+    }
+  }
+  double r[4][E], trD[4], trU[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    trD[m] = 0.0;
+    trU[m] = 0.0;
+#pragma unroll
+    for (int b = 0; b < E; b++) r[m][b] = 0.0;
+  }
+  const int jd1 = ib + 32;
+  jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns (beta = 0, iK = 0) contribute exact zeros: skip them
+#pragma unroll
+  for (int m = 0; m < 4; m++) ei[m] = uni_row_factor(kr[m]);   // kr becomes the residual shift
+  const bool far = __any_sync(0xffffffffu, kr[0] != 0.0 || kr[1] != 0.0 || kr[2] != 0.0 || kr[3] != 0.0);
+  if (jbeg < jd1) {
+    if (far) uni_fwd_cols_mma<EV, true>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, uf, kr, r, trD);
+    else uni_fwd_cols_mma<EV, false>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, uf, kr, r, trD);
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int b = 0; b < E; b++) r[m][b] *= 0.5;
+  }
+  if (far) uni_fwd_cols_mma<EV, true>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, uf, kr, r, trU);
+  else uni_fwd_cols_mma<EV, false>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, uf, kr, r, trU);
+  double tr = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; m++) tr = fma(ei[m], fma(2.0, trU[m], trD[m]), tr);
+  constexpr int P1 = E * (E + 1) / 2 + 1, NCH = (P1 + 15) / 16;
+  double vals[16 * NCH];
+#pragma unroll
+  for (int k = 0; k < 16 * NCH; k++) vals[k] = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double* rec = s_rec + (ib + 8 * m + g) * RLEN + EV + 1;
+    double bi[E];
+#pragma unroll
+    for (int a = 0; a < E; a++) bi[a] = rec[a] * ei[m];   // the row factor, applied once to the finished row sums
+    int pr = 0;
+#pragma unroll
+    for (int a = 0; a < E; a++)
+#pragma unroll
+      for (int b = a; b < E; b++) {
+        vals[pr] += (a == b) ? 2.0 * (bi[a] * r[m][a]) : fma(bi[a], r[m][b], bi[b] * r[m][a]);
+        pr++;
+      }
+  }
+  vals[P1 - 1] = tr;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) {
+    double v16[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v16[k] = vals[16 * ch + k];
+    int idx;
+    const double tot = warp_reduce_multi<16>(v16, lane, idx);
+    if ((lane & 1) == 0 && 16 * ch + idx < P1) s_part[16 * ch + idx] += tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core sweeps for the large state dimensions (UNI_USE_MMA8: E = 6..8).  Same tile layout as uni_fwd_cols_mma
+// (32 rows x 8 columns per round, lane (g, q) = rows ib + 8 m + g, columns j0 + 2 q, j0 + 2 q + 1), and here the products
+// AFTER the exponential are DMMAs too: with E = 8 output dimensions a row-sum update
+//   r_b,i += sum_j Eh_ij beta_b,j      (forward)        xi_i,e += sum_j w_ij nu_j,e     (reverse sweep)
+// is an (8 rows x 8 columns) x (8 columns x 8 outputs) tile product.  The lane's own values Eh / w ARE the A fragments --
+// the k slot q of the first DMMA stands for column j0 + 2 q, of the second for j0 + 2 q + 1, and the B fragments
+// (beta_{g, column} / nu_{column, g}: one LDS.64 each) are picked accordingly -- so nothing moves between lanes, and a
+// row's E sums shrink from E registers per row to the 2 accumulator entries (outputs 2 q, 2 q + 1) of its lane.  An
+// element costs 8 float64 instructions + 2 DMMA / 8 (forward) or 11 + 3 DMMA / 8 (reverse) instead of 24 / 39, the
+// per-column record loads all but vanish, and the kernels need ~150 registers instead of 255 + spills.
+// Slots beyond E (zero-padded k steps, unused outputs) read finite record data against zero A entries / into ignored
+// accumulator columns.
+// ---------------------------------------------------------------------------------------------
+// sums of v[16] (index 2 a + k) over the 8 row groups g of the warp; on return lane (g, q) holds index 2 g, 2 g + 1
+__device__ __forceinline__ void uni_reduce_over_g16(const double (&v)[16], int lane, double& o0, double& o1) {
+  const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+  double a[8], b[4];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const double send = u16 ? v[k] : v[k + 8], keep = u16 ? v[k + 8] : v[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double send = u8 ? a[k] : a[k + 4], keep = u8 ? a[k + 4] : a[k];
+    b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const double s0 = u4 ? b[0] : b[2], k0 = u4 ? b[2] : b[0], s1 = u4 ? b[1] : b[3], k1 = u4 ? b[3] : b[1];
+    o0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+    o1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
+  }
+}
+
+template <int EV, bool SH>
+__device__ __forceinline__ void uni_fwd_cols_mma8(const RolloutParams& p, const double* __restrict__ s_rec, int ib,
+                                                  int jbeg, int jend, int lane, const double (&ua)[4][2],
+                                                  const double (&kr)[4], double (&r)[4][2], double (&tr)[4]) {
+  constexpr int RLEN = 2 * EV + 2;
+  const int g = lane >> 2, q = lane & 3;
+  const size_t rs = 8 * (size_t)p.NP;
+  const double* __restrict__ ik = p.iK + (size_t)(ib + g) * p.NP + jbeg + 2 * q;   // rows of the symmetric iK, two adjacent columns
+  const double* __restrict__ rb = s_rec + (jbeg + g) * RLEN + q;                    // exponent B fragments: nu_{j0 + g, q}, nu_{j0 + g, 4 + q}
+  const double* __restrict__ rc = s_rec + (jbeg + 2 * q) * RLEN;                    // the lane's two columns
+#pragma unroll 1
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    const double bf0 = rb[0], bf1 = rb[4];
+    const double ka0 = rc[EV], ka1 = rc[RLEN + EV];
+    const double bb0 = rc[EV + 1 + g], bb1 = rc[RLEN + EV + 1 + g];   // row-sum B fragments: beta_{g, column}
+    double2 ikv[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) ikv[m] = ldg_stream2<false>(ik + m * rs);
+    double t[8], ex[8];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      double d0 = SH ? ka0 + kr[m] : ka0, d1 = SH ? ka1 + kr[m] : ka1;
+      dmma_m8n8k4(d0, d1, ua[m][0], bf0);
+      dmma_m8n8k4(d0, d1, ua[m][1], bf1);
+      t[2 * m] = d0;
+      t[2 * m + 1] = d1;
+    }
+    exp2s_xn<8>(t, ex);
+#pragma unroll
+    for (int m = 0; m < 4; m++) dmma_m8n8k4(r[m][0], r[m][1], ex[2 * m], bb0);
+#pragma unroll
+    for (int m = 0; m < 4; m++) dmma_m8n8k4(r[m][0], r[m][1], ex[2 * m + 1], bb1);
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      tr[m] = fma(ex[2 * m], ikv[m].x, tr[m]);
+      tr[m] = fma(ex[2 * m + 1], ikv[m].y, tr[m]);
+    }
+    ik += 8;
+    rb += 8 * RLEN;
+    rc += 8 * RLEN;
+  }
+}
+
+// One run of columns [jbeg, jend) (multiples of 8, jbeg >= 32 I) of the 32-row block I (algebra: uni_fwd_item).
+// s_part: the warp's accumulator row (P + 1 sums, padded) followed by its 64-double scratch.
+template <int EV>
+__device__ __forceinline__ void uni_fwd_item_mma8(const RolloutParams& p, const double* __restrict__ s_rec,
+                                                  const double* __restrict__ Qm, const double* __restrict__ il2, int I,
+                                                  int jbeg, int jend, int lane, double* s_part) {
+  constexpr int E = EV, RLEN = 2 * EV + 2, P = E * (E + 1) / 2, PL = ((P + 1) + 15) & ~15;
+  const int g = lane >> 2, q = lane & 3, ib = 32 * I;
+  double ua[4][2], kr[4], ei[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double* rec = s_rec + (ib + 8 * m + g) * RLEN;
+    kr[m] = rec[EV];
+#pragma unroll
+    for (int ks = 0; ks < 2; ks++) {
+      const int ee = 4 * ks + q;
+      double acc = 0.0;
+      if (ee < EV) {
+#pragma unroll
+        for (int f = 0; f < EV; f++) acc = fma(Qm[ee * EV + f], rec[f] * il2[f], acc);
+        acc *= (2.0 * GPMPC_EXP2S_SCALE) * il2[ee];   // exponent in table units (exp2s)
+      }
+      ua[m][ks] = acc;
+    }
+  }
+  double r[4][2], trD[4], trU[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) { trD[m] = 0.0; trU[m] = 0.0; r[m][0] = 0.0; r[m][1] = 0.0; }
+  const int jd1 = ib + 32;
+  jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns (beta = 0, iK = 0) contribute exact zeros: skip them
+#pragma unroll
+  for (int m = 0; m < 4; m++) ei[m] = uni_row_factor(kr[m]);   // kr becomes the residual shift
+  const bool far = __any_sync(0xffffffffu, kr[0] != 0.0 || kr[1] != 0.0 || kr[2] != 0.0 || kr[3] != 0.0);
+  if (jbeg < jd1) {
+    if (far) uni_fwd_cols_mma8<EV, true>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, kr, r, trD);
+    else uni_fwd_cols_mma8<EV, false>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, kr, r, trD);
+#pragma unroll
+    for (int m = 0; m < 4; m++) { r[m][0] *= 0.5; r[m][1] *= 0.5; }
+  }
+  if (far) uni_fwd_cols_mma8<EV, true>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, kr, r, trU);
+  else uni_fwd_cols_mma8<EV, false>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, kr, r, trU);
+  double tr = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; m++) tr = fma(ei[m], fma(2.0, trU[m], trD[m]), tr);
+  tr = warp_sum(tr);
+  // X_ab = sum_i beta_a,i e_i r_b,i : the lane holds r for b = 2 q, 2 q + 1 of its rows -> 2 E partial sums, added up over
+  // the row groups; lane (g, q) ends up with X[g][2 q], X[g][2 q + 1]; S_ab += X_ab + X_ba through the warp's scratch
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) v[k] = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double* rec = s_rec + (ib + 8 * m + g) * RLEN + EV + 1;
+#pragma unroll
+    for (int a = 0; a < E; a++) {
+      const double bi = rec[a] * ei[m];   // the row factor, applied once to the finished row sums
+      v[2 * a] = fma(bi, r[m][0], v[2 * a]);
+      v[2 * a + 1] = fma(bi, r[m][1], v[2 * a + 1]);
+    }
+  }
+  double x0, x1;
+  uni_reduce_over_g16(v, lane, x0, x1);
+  double* xs = s_part + PL;
+  xs[8 * g + 2 * q] = x0;
+  xs[8 * g + 2 * q + 1] = x1;
+  __syncwarp();
+  for (int pr = lane; pr < P; pr += 32) {
+    int a = 0, rem = pr;
+    while (rem >= E - a) { rem -= E - a; a++; }
+    const int b = a + rem;
+    s_part[pr] += xs[8 * a + b] + xs[8 * b + a];   // (a == b: 2 X_aa, as in uni_fwd_item)
+  }
+  if (lane == 0) s_part[P] += tr;
+  __syncwarp();
+}
+
 // Mean-part moments (gp_model.py:138-153), lane-per-output: lane o = a * nOut + q of every warp sums its output over the
 // warp's slice of training points,
 //   q = 0: h_a = sum_i e_i beta_a,i ;  q = 1 + d: g_a,d = sum_i e_i beta_a,i nu_i,d ,
@@ -287,6 +647,8 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
   const double* il2 = p.il2;            // row 0 (all rows equal)
   const double s2 = p.s2[0];
   exp2s_fill(p.exp2tab, tid, NT);
+  // beta_a,j of the hot-loop records does not depend on the candidate or the step: written once per CTA
+  for (int o = tid; o < NP * E; o += NT) s_rec[(o / E) * (2 * EV + 2) + EV + 1 + (o % E)] = __ldg(p.betaT + o);
   __syncthreads();
 
   long long clk_ = clock64();
@@ -371,15 +733,12 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
       }
       // ---- P1: nu, shared exponent terms, hot-loop record (thread per training point)
       // two training points per thread in flight: this phase is load / dependent-FMA latency (P1a 16.6 k -> 13.8 k clocks)
-#if UNI_P1_UNROLL == 2
-#pragma unroll 2
-#else
-#pragma unroll 1
-#endif
+      constexpr int P1U = (UNI_P1_UNROLL == 2 && EV <= 5) ? 2 : 1;   // (the 255-register kernels spill with two in flight)
+#pragma unroll P1U
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
-        for (int d = 0; d < GPMPC_MAX_D; d++) nu[d] = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
+        for (int d = 0; d < GPMPC_MAX_D; d++) nu[d] = (i < N && d < D) ? (uni_ldg_x(p.x + (size_t)i * D + d) - s_m[d]) : 0.0;
         double quad = 0.0, head = 0.0, tail = 0.0, zqz = 0.0;
 #pragma unroll
         for (int e = 0; e < EV; e++) {
@@ -401,8 +760,6 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
 #pragma unroll
         for (int e = 0; e < EV; e++) rec[e] = nu[e];
         rec[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;   // table units; log s2 factored out (s2^2 applied at the end)
-#pragma unroll
-        for (int a = 0; a < E; a++) rec[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
         rec[2 * EV + 1] = ei;   // spare slot of the (even-length) record
 #pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
@@ -412,15 +769,17 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
       UNI_CLK(4);
       // ---- P1b: mean-part moments h_a, g_a (lane per output, warp per slice of points; summed over warps in P4)
       {
-        const int per = NP / nwarps;
-        uni_moments_slice<EV>(s_rec, s_tail, L.tlen, nOut, warp * per, (warp + 1) * per, lane, s_wp + warp * L.wplen);
+        const int per = ((NP + nwarps - 1) / nwarps + 3) & ~3;   // slices of whole groups of 4 points (NP is a multiple of 64)
+        const int ibeg = min(NP, warp * per);
+        uni_moments_slice<EV>(s_rec, s_tail, L.tlen, nOut, ibeg, min(NP, ibeg + per), lane, s_wp + warp * L.wplen);
       }
       UNI_CLK(1);
       // ---- P3: one sweep over the upper tile triangle for all pairs.  Static balanced split: row block I (64 rows)
       //      holds (64 / p.seg) (nrb - I) chunks of p.seg columns from its diagonal on; the chunks of all row blocks,
       //      in row-major order, are dealt to the warps in equal contiguous runs (cut at row-block boundaries).
       {
-        const int CH = p.seg, nrb = NP / 64, cpt = 64 / CH;       // chunks per 64-column tile
+        constexpr int TR = (UNI_USE_QUAD_FWD(EV) || UNI_USE_MMA8(EV)) ? 32 : 64;        // rows (and columns) of a tile
+        const int CH = min(p.seg, TR), nrb = NP / TR, cpt = TR / CH;       // chunks per tile
         const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps * C - 1) / (nwarps * C);
         int c0 = (crank * nwarps + warp) * per;
         const int c1 = min(T, c0 + per);
@@ -428,8 +787,15 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
         while (c0 < c1) {
           while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
           const int ce = min(c1, base + cpt * (nrb - I));
-          uni_fwd_item<EV>(p, s_rec, s_Q, il2, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base), lane,
-                           s_part + warp * L.partlen);
+          if (UNI_USE_MMA8(EV))
+            uni_fwd_item_mma8<EV>(p, s_rec, s_Q, il2, I, TR * I + CH * (c0 - base), TR * I + CH * (ce - base), lane,
+                                  s_part + warp * L.partlen);
+          else if (UNI_USE_QUAD_FWD(EV))
+            uni_fwd_item_mma<EV>(p, s_rec, s_Q, il2, I, TR * I + CH * (c0 - base), TR * I + CH * (ce - base), lane,
+                                 s_part + warp * L.partlen);
+          else
+            uni_fwd_item<EV>(p, s_rec, s_Q, il2, I, TR * I + CH * (c0 - base), TR * I + CH * (ce - base), lane,
+                             s_part + warp * L.partlen);
           c0 = ce;
         }
       }
@@ -707,6 +1073,267 @@ __device__ __forceinline__ void uni_bwd_item(const RolloutParams& p, const doubl
   for (int e = 0; e < EV; e++) { uni_red_add(g_xi + (size_t)e * NP + i0, xi0[e]); uni_red_add(g_xi + (size_t)e * NP + i1, xi1[e]); }
 }
 
+// Tensor-core variant of the reverse sweep (UNI_USE_MMA, see uni_fwd_cols_mma for the tile layout): BOTH bilinear forms of
+// an element are DMMAs -- the exponent  t_ij = kap_j + u_i . nu_j  and the coefficient  c_ij = p_i . beta_j - wb_i iK_ij
+// (the trace part is the accumulator's initial value) -- so an element costs 15 float64 instructions + 2/8 DMMA instead
+// of 23.  Column sums: the lane's two columns summed over its 4 rows, then over the 8 row groups of the warp (three
+// exchanges, the first one halving); row sums stay in registers until the end of the item.
+template <int EV, bool SH>
+__device__ __forceinline__ void uni_bwd_cols_mma(const RolloutParams& p, const double* __restrict__ s_rec, int ib,
+                                                 int jbeg, int jend, int lane, const double (&ua)[4][(EV + 3) / 4],
+                                                 const double (&pa)[4][(EV + 3) / 4], const double (&kr)[4],
+                                                 const double (&wb)[4], double (&rho)[4], double (&xi)[4][EV],
+                                                 double* __restrict__ g_gam) {
+  constexpr int RLEN = 2 * EV + 2, KS = (EV + 3) / 4;
+  const int g = lane >> 2, q = lane & 3;
+  const size_t rs = 8 * (size_t)p.NP;
+  const double* __restrict__ ik = p.iK + (size_t)(ib + g) * p.NP + jbeg + 2 * q;
+  const double* __restrict__ rb = s_rec + (jbeg + g) * RLEN + q;     // B fragment sources: nu (slot q), beta (slot EV + 1 + q)
+  const double* __restrict__ rc = s_rec + (jbeg + 2 * q) * RLEN;     // the lane's two columns
+  const bool up = (lane & 16) != 0;
+  double* __restrict__ gcol = g_gam + jbeg + 2 * q + (up ? 1 : 0);
+#pragma unroll 1
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    double bfn[KS], bfb[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      bfn[ks] = rb[4 * ks];
+      bfb[ks] = (EV % 4 == 0 || 4 * ks + q < EV) ? rb[EV + 1 + 4 * ks] : 0.0;
+    }
+    const double ka0 = rc[EV], ka1 = rc[RLEN + EV];
+    double n0[EV], n1[EV];
+#pragma unroll
+    for (int e = 0; e < EV; e++) { n0[e] = rc[e]; n1[e] = rc[RLEN + e]; }
+    double2 ikv[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) ikv[m] = ldg_stream2<(EV <= 5)>(ik + m * rs);
+    double t[8], c[8], w[8];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      double c0 = -wb[m] * ikv[m].x, c1 = -wb[m] * ikv[m].y;
+      double d0 = SH ? ka0 + kr[m] : ka0, d1 = SH ? ka1 + kr[m] : ka1;
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        dmma_m8n8k4(c0, c1, pa[m][ks], bfb[ks]);
+        dmma_m8n8k4(d0, d1, ua[m][ks], bfn[ks]);
+      }
+      c[2 * m] = c0; c[2 * m + 1] = c1;
+      t[2 * m] = d0; t[2 * m + 1] = d1;
+    }
+    exp2s_xn<8, false>(t, w);
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] *= c[k];
+#pragma unroll
+    for (int m = 0; m < 4; m++) rho[m] += w[2 * m] + w[2 * m + 1];
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int e = 0; e < EV; e++) xi[m][e] = fma(w[2 * m], n0[e], xi[m][e]);
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int e = 0; e < EV; e++) xi[m][e] = fma(w[2 * m + 1], n1[e], xi[m][e]);
+    const double v0 = (w[0] + w[2]) + (w[4] + w[6]), v1 = (w[1] + w[3]) + (w[5] + w[7]);
+    // lanes 0-15 keep column 2 q, lanes 16-31 column 2 q + 1; then the sum over the row groups g
+    double a = (up ? v1 : v0) + __shfl_xor_sync(0xffffffffu, up ? v0 : v1, 16);
+    a += __shfl_xor_sync(0xffffffffu, a, 8);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    if ((lane & 12) == 0) uni_red_add(gcol, a);
+    gcol += 8;
+    ik += 8;
+    rb += 8 * RLEN;
+    rc += 8 * RLEN;
+  }
+}
+
+// One run of columns [jbeg, jend) (multiples of 8, jbeg >= 32 I) of the 32-row block I: see uni_bwd_item for the algebra.
+template <int EV>
+__device__ __forceinline__ void uni_bwd_item_mma(const RolloutParams& p, const double* __restrict__ s_rec,
+                                                 const double* __restrict__ Qm, const double* __restrict__ il2,
+                                                 const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
+                                                 int lane, double* __restrict__ g_gam, double* __restrict__ g_rho,
+                                                 double* __restrict__ g_xi) {
+  constexpr int E = EV, RLEN = 2 * EV + 2, KS = (EV + 3) / 4;
+  const int NP = p.NP;
+  const int g = lane >> 2, q = lane & 3, ib = 32 * I;
+  double ua[4][KS], pa[4][KS], kr[4], wb[4], ei[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double* rec = s_rec + (ib + 8 * m + g) * RLEN;
+    kr[m] = rec[EV];
+    ei[m] = uni_row_factor(kr[m]);   // kr becomes the residual shift
+    wb[m] = wbar * ei[m];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      const int ee = 4 * ks + q;
+      double acc = 0.0, pv = 0.0;
+      if (ee < EV) {
+#pragma unroll
+        for (int f = 0; f < EV; f++) acc = fma(Qm[ee * EV + f], rec[f] * il2[f], acc);
+        acc *= (2.0 * GPMPC_EXP2S_SCALE) * il2[ee];   // exponent in table units (exp2s)
+#pragma unroll
+        for (int b = 0; b < E; b++) pv = fma(Om[ee * E + b], rec[EV + 1 + b], pv);
+        pv *= ei[m];                                  // row factor of the exponential folded into the coefficients
+      }
+      ua[m][ks] = acc;
+      pa[m][ks] = pv;
+    }
+  }
+  double rho[4], xi[4][EV];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    rho[m] = 0.0;
+#pragma unroll
+    for (int e = 0; e < EV; e++) xi[m][e] = 0.0;
+  }
+  const int jd1 = ib + 32;
+  jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns contribute exact zeros: skip them
+  const bool far = __any_sync(0xffffffffu, kr[0] != 0.0 || kr[1] != 0.0 || kr[2] != 0.0 || kr[3] != 0.0);
+  if (jbeg < jd1) {   // diagonal tile: swept in full with HALF weights
+    double ph[4][KS], wh[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      wh[m] = 0.5 * wb[m];
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) ph[m][ks] = 0.5 * pa[m][ks];
+    }
+    if (far) uni_bwd_cols_mma<EV, true>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, ph, kr, wh, rho, xi, g_gam);
+    else uni_bwd_cols_mma<EV, false>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, ph, kr, wh, rho, xi, g_gam);
+  }
+  if (far) uni_bwd_cols_mma<EV, true>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, pa, kr, wb, rho, xi, g_gam);
+  else uni_bwd_cols_mma<EV, false>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, pa, kr, wb, rho, xi, g_gam);
+  // a row's sums are spread over the 4 lanes of its quad: add them up, lane q = 0 sends them to the scratch
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    double v = rho[m];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (q == 0) uni_red_add(g_rho + ib + 8 * m + g, v);
+#pragma unroll
+    for (int e = 0; e < EV; e++) {
+      double x = xi[m][e];
+      x += __shfl_xor_sync(0xffffffffu, x, 1);
+      x += __shfl_xor_sync(0xffffffffu, x, 2);
+      if (q == (e & 3)) uni_red_add(g_xi + (size_t)e * NP + ib + 8 * m + g, x);
+    }
+  }
+}
+
+// Reverse sweep, large state dimensions (see uni_fwd_cols_mma8): exponent, coefficient and the xi row sums are DMMAs.
+template <int EV, bool SH>
+__device__ __forceinline__ void uni_bwd_cols_mma8(const RolloutParams& p, const double* __restrict__ s_rec, int ib,
+                                                  int jbeg, int jend, int lane, const double (&ua)[4][2],
+                                                  const double (&pa)[4][2], const double (&kr)[4], const double (&wb)[4],
+                                                  double (&rho)[4], double (&xi)[4][2], double* __restrict__ g_gam) {
+  constexpr int RLEN = 2 * EV + 2;
+  const int g = lane >> 2, q = lane & 3;
+  const size_t rs = 8 * (size_t)p.NP;
+  const double* __restrict__ ik = p.iK + (size_t)(ib + g) * p.NP + jbeg + 2 * q;
+  const double* __restrict__ rb = s_rec + (jbeg + g) * RLEN + q;     // B fragments of column j0 + g: nu (slots q, 4 + q), beta (EV + 1 + ...)
+  const double* __restrict__ rc = s_rec + (jbeg + 2 * q) * RLEN;     // the lane's two columns
+  const bool up = (lane & 16) != 0;
+  double* __restrict__ gcol = g_gam + jbeg + 2 * q + (up ? 1 : 0);
+#pragma unroll 1
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    const double bfn0 = rb[0], bfn1 = rb[4], bfb0 = rb[EV + 1], bfb1 = rb[EV + 5];
+    const double ka0 = rc[EV], ka1 = rc[RLEN + EV];
+    const double bx0 = rc[g], bx1 = rc[RLEN + g];   // xi B fragments: nu_{column, g}
+    double2 ikv[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) ikv[m] = ldg_stream2<false>(ik + m * rs);
+    double t[8], c[8], w[8];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      double c0 = -wb[m] * ikv[m].x, c1 = -wb[m] * ikv[m].y;
+      double d0 = SH ? ka0 + kr[m] : ka0, d1 = SH ? ka1 + kr[m] : ka1;
+      dmma_m8n8k4(c0, c1, pa[m][0], bfb0);
+      dmma_m8n8k4(d0, d1, ua[m][0], bfn0);
+      dmma_m8n8k4(c0, c1, pa[m][1], bfb1);
+      dmma_m8n8k4(d0, d1, ua[m][1], bfn1);
+      c[2 * m] = c0; c[2 * m + 1] = c1;
+      t[2 * m] = d0; t[2 * m + 1] = d1;
+    }
+    exp2s_xn<8>(t, w);
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] *= c[k];
+#pragma unroll
+    for (int m = 0; m < 4; m++) dmma_m8n8k4(xi[m][0], xi[m][1], w[2 * m], bx0);
+#pragma unroll
+    for (int m = 0; m < 4; m++) dmma_m8n8k4(xi[m][0], xi[m][1], w[2 * m + 1], bx1);
+#pragma unroll
+    for (int m = 0; m < 4; m++) rho[m] += w[2 * m] + w[2 * m + 1];
+    const double v0 = (w[0] + w[2]) + (w[4] + w[6]), v1 = (w[1] + w[3]) + (w[5] + w[7]);
+    // lanes 0-15 keep column 2 q, lanes 16-31 column 2 q + 1; then the sum over the row groups g
+    double a = (up ? v1 : v0) + __shfl_xor_sync(0xffffffffu, up ? v0 : v1, 16);
+    a += __shfl_xor_sync(0xffffffffu, a, 8);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    if ((lane & 12) == 0) uni_red_add(gcol, a);
+    gcol += 8;
+    ik += 8;
+    rb += 8 * RLEN;
+    rc += 8 * RLEN;
+  }
+}
+
+template <int EV>
+__device__ __forceinline__ void uni_bwd_item_mma8(const RolloutParams& p, const double* __restrict__ s_rec,
+                                                  const double* __restrict__ Qm, const double* __restrict__ il2,
+                                                  const double* __restrict__ Om, double wbar, int I, int jbeg, int jend,
+                                                  int lane, double* __restrict__ g_gam, double* __restrict__ g_rho,
+                                                  double* __restrict__ g_xi) {
+  constexpr int E = EV, RLEN = 2 * EV + 2;
+  const int NP = p.NP;
+  const int g = lane >> 2, q = lane & 3, ib = 32 * I;
+  double ua[4][2], pa[4][2], kr[4], wb[4], ei[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double* rec = s_rec + (ib + 8 * m + g) * RLEN;
+    kr[m] = rec[EV];
+    ei[m] = uni_row_factor(kr[m]);   // kr becomes the residual shift
+    wb[m] = wbar * ei[m];
+#pragma unroll
+    for (int ks = 0; ks < 2; ks++) {
+      const int ee = 4 * ks + q;
+      double acc = 0.0, pv = 0.0;
+      if (ee < EV) {
+#pragma unroll
+        for (int f = 0; f < EV; f++) acc = fma(Qm[ee * EV + f], rec[f] * il2[f], acc);
+        acc *= (2.0 * GPMPC_EXP2S_SCALE) * il2[ee];   // exponent in table units (exp2s)
+#pragma unroll
+        for (int b = 0; b < E; b++) pv = fma(Om[ee * E + b], rec[EV + 1 + b], pv);
+        pv *= ei[m];                                  // row factor of the exponential folded into the coefficients
+      }
+      ua[m][ks] = acc;
+      pa[m][ks] = pv;
+    }
+  }
+  double rho[4], xi[4][2];
+#pragma unroll
+  for (int m = 0; m < 4; m++) { rho[m] = 0.0; xi[m][0] = 0.0; xi[m][1] = 0.0; }
+  const int jd1 = ib + 32;
+  jend = min(jend, (p.N + 7) & ~7);   // zero-padded columns contribute exact zeros: skip them
+  const bool far = __any_sync(0xffffffffu, kr[0] != 0.0 || kr[1] != 0.0 || kr[2] != 0.0 || kr[3] != 0.0);
+  if (jbeg < jd1) {   // diagonal tile: swept in full with HALF weights
+    double ph[4][2], wh[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) { wh[m] = 0.5 * wb[m]; ph[m][0] = 0.5 * pa[m][0]; ph[m][1] = 0.5 * pa[m][1]; }
+    if (far) uni_bwd_cols_mma8<EV, true>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, ph, kr, wh, rho, xi, g_gam);
+    else uni_bwd_cols_mma8<EV, false>(p, s_rec, ib, jbeg, min(jend, jd1), lane, ua, ph, kr, wh, rho, xi, g_gam);
+  }
+  if (far) uni_bwd_cols_mma8<EV, true>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, pa, kr, wb, rho, xi, g_gam);
+  else uni_bwd_cols_mma8<EV, false>(p, s_rec, ib, max(jbeg, jd1), jend, lane, ua, pa, kr, wb, rho, xi, g_gam);
+  // xi: the accumulator entries are complete (outputs 2 q, 2 q + 1 of the lane's rows); rho: spread over the quad
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    double v = rho[m];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (q == 0) uni_red_add(g_rho + ib + 8 * m + g, v);
+    if (2 * q < EV) uni_red_add(g_xi + (size_t)(2 * q) * NP + ib + 8 * m + g, xi[m][0]);
+    if (2 * q + 1 < EV) uni_red_add(g_xi + (size_t)(2 * q + 1) * NP + ib + 8 * m + g, xi[m][1]);
+  }
+}
+
 // O(N) reductions of the reverse sweep.  Every thread has summed, over its own training points, P "pair" values
 // (k <= l, row-major) and up to GPMPC_MAX_D "single" values; the warp adds them up with halving exchanges (16 values
 // per round, 16 shuffles instead of 80) and stores its totals as row[o]: o < D singles, o = D + pr pairs.  The per-warp
@@ -798,7 +1425,7 @@ __device__ inline void uni_stage_adjoint(const RolloutParams& p, int Na, double 
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
 template <int EV>
-__global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
+__global__ void __launch_bounds__(UNI_BWD_MAXT(EV), UNI_BWD_MINCTAS(EV)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -821,7 +1448,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
   double* g_xi = g_rho + NP;
   int gstep = 0;
   const int warp = tid >> 5, nwarps = NT >> 5;
-  double* s_wp = sm + L.wp; double* s_wp2 = s_wp + 8 * L.wplen;   // per-warp rows of the B1 / B3 point sums
+  double* s_wp = sm + L.wp; double* s_wp2 = s_wp + (UNI_MAXT(EV) / 32) * L.wplen;   // per-warp rows of the B1 / B3 point sums
   double* s_m = sm + L.m; double* s_A = sm + L.A; double* s_Q = sm + L.Q;
   double* s_acc = sm + L.acc; int* s_int = reinterpret_cast<int*>(sm + L.ints);
   double* s2p = sm + L.small2;
@@ -838,6 +1465,8 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
   const double s2 = p.s2[0];
   const double wmu = 1.0 / (double)(H + 1);
   exp2s_fill(p.exp2tab, tid, NT);
+  // beta_a,j of the hot-loop records does not depend on the candidate or the step: written once per CTA
+  for (int o = tid; o < NP * E; o += NT) s_rec[(o / E) * (2 * EV + 2) + EV + 1 + (o % E)] = __ldg(p.betaT + o);
   if (C == 1)
     for (int i = tid; i < NP * (2 + EV); i += NT) g_gam[i] = 0.0;   // B3 re-zeroes after every step (clusters: host memset)
   __syncthreads();
@@ -989,7 +1618,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
       for (int i = tid; i < NP; i += NT) {
         double nu[GPMPC_MAX_D];
 #pragma unroll
-        for (int d = 0; d < GPMPC_MAX_D; d++) nu[d] = (i < N && d < D) ? (p.x[(size_t)i * D + d] - s_m[d]) : 0.0;
+        for (int d = 0; d < GPMPC_MAX_D; d++) nu[d] = (i < N && d < D) ? (uni_ldg_x(p.x + (size_t)i * D + d) - s_m[d]) : 0.0;
         double quad = 0.0, head = 0.0, tail = 0.0, zqz = 0.0, an[GPMPC_MAX_D];
 #pragma unroll
         for (int e = 0; e < EV; e++) {
@@ -1015,8 +1644,6 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
         for (int e = 0; e < EV; e++) rcd[e] = nu[e];
         rcd[EV] = (i < N) ? GPMPC_EXP2S_SCALE * (-0.5 * (head + tail) + zqz) : 0.0;
 #pragma unroll
-        for (int a = 0; a < E; a++) rcd[EV + 1 + a] = __ldg(p.betaT + (size_t)i * E + a);
-#pragma unroll
         for (int d = EV; d < GPMPC_MAX_D; d++)
           if (d < D) s_tail[i * L.tlen + d - EV] = nu[d];
         // mean part weight phi_i = sum_a e_i beta_a,i (h_bar_a + g_bar_a . nu_i^E), kept in the record's spare slot
@@ -1026,7 +1653,7 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
           double w = s_hbar[a];
 #pragma unroll
           for (int e = 0; e < EV; e++) w = fma(s_gbar[a * E + e], nu[e], w);
-          phi = fma(ei * __ldg(p.betaT + (size_t)i * E + a), w, phi);
+          phi = fma(ei * rcd[EV + 1 + a], w, phi);
         }
         // raw moments of the mean part: sum_i phi_i nu_i,d (D) and sum_i phi_i nu_i,k nu_i,l (P)
 #pragma unroll
@@ -1049,7 +1676,8 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
       // ---- B2: adjoint-weighted sweep over the upper tile triangle (static balanced split as in the forward, P3)
       {
         const double wbar = s_scal[3];
-        const int CH = p.seg_bwd, nrb = NP / 64, cpt = 64 / CH;
+        constexpr int TR = (UNI_USE_MMA(EV) || UNI_USE_MMA8(EV)) ? 32 : 64;             // rows (and columns) of a tile
+        const int CH = min(p.seg_bwd, TR), nrb = NP / TR, cpt = TR / CH;
         const int T = cpt * nrb * (nrb + 1) / 2, per = (T + nwarps * C - 1) / (nwarps * C);
         int c0 = (crank * nwarps + warp) * per;
         const int c1 = min(T, c0 + per);
@@ -1062,8 +1690,15 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT, UNI_BWD_MINCTAS(EV)) uniform_bwd
         while (c0 < c1) {
           while (c0 >= base + cpt * (nrb - I)) { base += cpt * (nrb - I); I++; }
           const int ce = min(c1, base + cpt * (nrb - I));
-          uni_bwd_item<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, 64 * I + CH * (c0 - base), 64 * I + CH * (ce - base),
-                           lane, g_gam, g_rho, g_xi, sm + L.colred + warp * COLRED_WARP);
+          if (UNI_USE_MMA8(EV))
+            uni_bwd_item_mma8<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, TR * I + CH * (c0 - base), TR * I + CH * (ce - base),
+                                  lane, g_gam, g_rho, g_xi);
+          else if (UNI_USE_MMA(EV))
+            uni_bwd_item_mma<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, TR * I + CH * (c0 - base), TR * I + CH * (ce - base),
+                                 lane, g_gam, g_rho, g_xi);
+          else
+            uni_bwd_item<EV>(p, s_rec, s_Q, il2, s_Om, wbar, I, TR * I + CH * (c0 - base), TR * I + CH * (ce - base),
+                             lane, g_gam, g_rho, g_xi, sm + L.colred + warp * COLRED_WARP);
           c0 = ce;
         }
       }
@@ -1284,14 +1919,14 @@ cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, 
     e = cudaLaunchKernelEx(&cfg, uniform_bwd_kernel<EV>, p, grad);
   } else {
     if (EV <= 5 && threads <= 128) {   // three-CTAs-per-SM build (see UNI_FWD_MINCTAS)
-      constexpr int T = EV <= 5 ? 128 : UNIFORM_MAX_THREADS;   // (no extra instantiation for the larger state dims)
+      constexpr int T = EV <= 5 ? 128 : UNI_MAXT(EV);   // (no extra instantiation for the larger state dims)
       e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       e = cudaLaunchKernelEx(&cfg, uniform_fwd_kernel<EV, T>, p);
     } else {
-      e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, UNI_MAXT(EV)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      e = cudaLaunchKernelEx(&cfg, uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, p);
+      e = cudaLaunchKernelEx(&cfg, uniform_fwd_kernel<EV, UNI_MAXT(EV)>, p);
     }
   }
   if (e != cudaSuccess) return e;
@@ -1319,9 +1954,9 @@ cudaError_t max_clusters_uniform_inst(bool bwd, int cluster, int threads, size_t
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveClusters(nclusters, uniform_bwd_kernel<EV>, &cfg);
   }
-  e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, UNI_MAXT(EV)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveClusters(nclusters, uniform_fwd_kernel<EV, UNIFORM_MAX_THREADS>, &cfg);
+  return cudaOccupancyMaxActiveClusters(nclusters, uniform_fwd_kernel<EV, UNI_MAXT(EV)>, &cfg);
 }
 
 }  // namespace gpmpc

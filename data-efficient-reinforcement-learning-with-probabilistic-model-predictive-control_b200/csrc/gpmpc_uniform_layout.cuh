@@ -27,12 +27,14 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.pre = o; if (bwd && premat) o += H * L.prelen;
   L.nOut = 1 + D;
   L.out = o; o += E * L.nOut;
-  // per-warp accumulator rows of the forward sweep (P + 1 sums, padded to the 16-wide halving reduction), 8 warps max
+  // per-warp accumulator rows of the forward sweep (P + 1 sums, padded to the 16-wide halving reduction)
   L.partlen = ((P + 1) + 15) & ~15;
-  L.part = o; if (!bwd) o += 8 * L.partlen;
+  if (UNI_USE_MMA8(EV)) L.partlen += 64;   // + the warp's E x E scratch of the tensor-core sweep (uni_fwd_item_mma8)
+  const int MW = UNI_MAXT(EV) / 32;   // warps per CTA at most
+  L.part = o; if (!bwd) o += MW * L.partlen;
   // per-warp partial rows of the O(N) reductions (lane per output): forward E (1 + D) outputs, reverse sweep D + P
   L.wplen = bwd ? (D + P) : (E * L.nOut);
-  L.wp = o; o += (bwd ? 16 : 8) * L.wplen;   // reverse sweep: two sets (B1, B3)
+  L.wp = o; o += (bwd ? 2 * MW : MW) * L.wplen;   // reverse sweep: two sets (B1, B3)
   // reverse sweep, optional (UNI_BWD_COLRED_SMEM): per-warp scratch of col_reduce8s (COLRED_WARP doubles, <= 8 warps)
   o = (o + 1) & ~1;
   L.colred = o;

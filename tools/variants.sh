@@ -14,7 +14,7 @@
 #   tools/variants.sh build b3 "-DSOME_TUNING_MACRO=3"; tools/variants.sh sass b3 uniform_fwd
 #   gpurun -- 'GPMPC_UNI_FWD_THREADS=128 GPMPC_UNI_FWD_CTAS=3 tools/variants.sh bench b3 --steps 2 --no-cpu-baseline'
 # Prepared for the next round -- the reverse-sweep kernel as three 128-thread CTAs per SM with 168 registers:
-#   tools/variants.sh build-all bw3 "-DUNI_BWD_MAXT=128 -DUNI_BWD_MINCTAS_ALL=3 -DGPMPC_BWD_NO_CST"
+#   tools/variants.sh build-all bw3 "-DUNI_BWD_MAXT_ALL=128 -DUNI_BWD_MINCTAS_ALL=3 -DGPMPC_BWD_NO_CST"
 #   gpurun -- 'GPMPC_UNI_PREMAT=0 GPMPC_UNI_BWD_THREADS=128 GPMPC_UNI_BWD_CTAS=3 tools/variants.sh bench bw3 --steps 2 --no-cpu-baseline'
 # (big batches only: the cluster launches of small batches use 256 threads, beyond the variant's launch bounds)
 # The variant libraries are git-ignored (*.so) but travel to the GPU box; each adds ~37 MB to the push, so delete
