@@ -316,7 +316,7 @@ __device__ __forceinline__ void gen_cols(const double* __restrict__ s_nu, int DP
         exp2s_x4_signed(t, w, ca.y, cb.y);
       }
       if (DIAG) {
-        const double2 bb2 = __ldg(reinterpret_cast<const double2*>(beta_b + j));
+        const double2 bb2 = make_double2(ca.y, cb.y);   // beta_b,j: second slot of the column record (diagonal pairs)
 #if GEN_IK_PREFETCH      // the prefetched rows are taken from L1
         const double2 ika = __ldg(reinterpret_cast<const double2*>(ik0));
         const double2 ikb = __ldg(reinterpret_cast<const double2*>(ik0 + NP));
@@ -983,6 +983,7 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
             s_kap[2 * o + 1] = cc.y;
           } else {
             kap *= GPMPC_EXP2S_SCALE;
+            s_kap[2 * o + 1] = __ldg(p.beta + (size_t)b * NP + j);   // diagonal pairs: the coefficient itself rides in the record
           }
           s_kap[2 * o] = kap;
         }
