@@ -183,27 +183,30 @@ def sass_counts(E):
         out = {"source": "profiles/sass_loop_counts.json (tools/sass_counts.py: cuobjdump -sass of the built library)"}
         out["uniform_fwd"] = tab["uniform_fwd"]["float64_per_element"]
         out["uniform_bwd"] = tab["uniform_bwd"]["float64_per_element"]
+        out["uniform_tile_rows"] = tab["uniform_bwd"].get("tile_rows", 64)   # 32: tensor-core sweeps (E >= 6), a DMMA = 8 instructions
         for key in ("general_grad", "general_value"):      # (off-diagonal 2 rows per lane, diagonal, off-diagonal 4 rows per lane)
             t = tab[key]
             out[key] = (t["float64_per_element_off_diagonal"], t["float64_per_element_diagonal"],
                         t.get("float64_per_element_off_diagonal_rows4", t["float64_per_element_off_diagonal"]))
         return out
     except Exception:
-        return {"source": "source-level count (profiles/sass_loop_counts.json not readable)",
-                "uniform_fwd": E + 7 + E + 1, "uniform_bwd": E + 7 + (E + 1) + 3.06 + E,
+        return {"source": "source-level count (profiles/sass_loop_counts.json not readable)", "uniform_tile_rows": 32 if E >= 6 else 64,
+                "uniform_fwd": 24.0 if E >= 6 else E + 7 + E + 1, "uniform_bwd": 35.12 if E >= 6 else E + 7 + (E + 1) + 3.06 + E,
                 "general_grad": (E + 7 + 1 + E + 1.56, E + 7 + 4 + E + 1.31, E + 7 + 1 + E + 1.28),
                 "general_value": (E + 8, E + 10, E + 8)}
 
 
-def sweep_elements(uniform, E, N):
-    """(i, j) elements one prediction sweeps: the uniform kernels visit the 64 x 64 tiles on or above the diagonal once
-    for all output pairs; the general kernel visits them per diagonal pair and the full N x N per off-diagonal pair.
-    Rows are padded to a multiple of 64, padded columns are skipped."""
+def sweep_elements(uniform, E, N, tile_rows=64):
+    """(i, j) elements one prediction sweeps: the uniform kernels visit the tiles (64 x 64; 32 x 32 in the tensor-core
+    sweeps of E >= 6) on or above the diagonal once for all output pairs; the general kernel visits them per diagonal pair
+    and the full N x N per off-diagonal pair.  Rows are padded to a multiple of 64, padded columns are skipped."""
     NP = (N + 63) // 64 * 64
     nrb = NP // 64
     cols = (N + 7) // 8 * 8
     tri = sum(64 * max(0, cols - 64 * I) for I in range(nrb))
     if uniform:
+        if tile_rows != 64:
+            tri = sum(tile_rows * max(0, cols - tile_rows * I) for I in range(NP // tile_rows))
         return {"triangle": tri}
     return {"diagonal": E * tri, "off_diagonal": E * (E - 1) // 2 * NP * cols}
 
@@ -211,7 +214,7 @@ def sweep_elements(uniform, E, N):
 def fp64_model(kernel, E, N, counts):
     """Executed float64 instructions per prediction of one kernel's hot loops (each = one 2-flop FMA slot of the pipe)."""
     if kernel in ("uniform_fwd", "uniform_bwd"):
-        return sweep_elements(True, E, N)["triangle"] * counts[kernel]
+        return sweep_elements(True, E, N, counts.get("uniform_tile_rows", 64))["triangle"] * counts[kernel]
     el = sweep_elements(False, E, N)
     off, dia, off4 = counts[kernel]
     rows4 = ((N + 63) // 64 * 64) % 128 == 0        # 128-row warp tiles for the off-diagonal pairs (gen_cols4)
@@ -426,7 +429,7 @@ def main():
                                "general_grad", m["fwd_ms"])
             kernels = [dom]
         # bytes the kernels read per prediction from L2 (iK triangle once per uniform sweep / per diagonal pair)
-        el = sweep_elements(m["uniform"], E, N)
+        el = sweep_elements(m["uniform"], E, N, counts.get("uniform_tile_rows", 64))
         l2_bytes = 8.0 * (el["triangle"] if m["uniform"] else el["diagonal"])
         roofline = {
             "bound": "fp64", "unit": "TFLOP/s", "achieved": dom["achieved_tflops"], "peak": fp64_peak / 1e12,

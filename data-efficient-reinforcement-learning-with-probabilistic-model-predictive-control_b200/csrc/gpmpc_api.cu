@@ -46,7 +46,7 @@ struct gpmpc_handle {
   DevBuf c_target, c_W, c_WT, c_smin, c_smax;
   double kappa = 0.0;
   int use_constraints = 0, clip = 0;
-  DevBuf dbg_clk, ws_uni, queue, ws_cl;
+  DevBuf dbg_clk, ws_uni, queue, ws_cl, ws_pre;
   DevBuf ws_kk, ws_gam, colcoef, t_mu, t_var, t_r, t_rv, t_am, t_cost, records, step_in;
   long long launches = 0;
   bool timing = false;
@@ -164,7 +164,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* all[] = {&h->x, &h->il2, &h->s2, &h->ls, &h->noise, &h->beta, &h->betaT, &h->iK, &h->Kbuf, &h->Zbuf, &h->info,
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->ws_gam, &h->colcoef, &h->t_mu, &h->t_var,
-                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue, &h->ws_cl};
+                   &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue, &h->ws_cl, &h->ws_pre};
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -460,9 +460,9 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       const size_t with = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true);
       const size_t two = 112 * 1024 - GPMPC_STATIC_SMEM;   // two CTAs per SM
       const size_t lim = smb <= two ? two : h->smem_optin;
-      p.premat = with <= lim ? 1 : 0;
-      if (const char* e = getenv("GPMPC_UNI_PREMAT")) p.premat = (atoi(e) != 0 && with <= lim) ? 1 : 0;
-      if (p.premat) smb = with;
+      p.premat = with <= lim ? 1 : 2;     // 2: the precomputed records go to a per-CTA global scratch (allocated below)
+      if (const char* e = getenv("GPMPC_UNI_PREMAT")) { const int v = atoi(e); p.premat = v == 0 ? 0 : ((v == 1 && with <= lim) ? 1 : 2); }
+      if (p.premat == 1) smb = with;
     }
     if (smf > h->smem_optin || (want_grad && smb > h->smem_optin))
       return fail(h, GPMPC_ERR_UNSUPPORTED, "rollout: training set too large for the shared-memory plan (N, D)");
@@ -545,6 +545,11 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
         CU(h->ws_uni.ensure(scr * grid_b));   // zeroed by the kernel itself
       }
       p.ws_uni = h->ws_uni.as<double>();
+      p.ws_pre = nullptr;
+      if (p.premat == 2) {
+        CU(h->ws_pre.ensure(sizeof(double) * (size_t)grid_b * H * uniform_premat_len(E, h->NP, h->DP, D, H, Na)));
+        p.ws_pre = h->ws_pre.as<double>();
+      }
       if (h->timing) CU(cudaEventRecord(h->ev[2], st));
       CU(launch_uniform(E, true, p, grad, grid_b, thr_b, smb, st));
       h->launches += 1;

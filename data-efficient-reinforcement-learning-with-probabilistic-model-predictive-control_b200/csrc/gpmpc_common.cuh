@@ -198,6 +198,44 @@ __device__ __forceinline__ void uni_cluster_sync() {   // all threads of all CTA
 // ---------------------------------------------------------------------------------------------
 // Small dense SPD helpers (n <= 8), used once per step per GP / pair.
 // ---------------------------------------------------------------------------------------------
+// The same for a matrix in SHARED memory, by one whole warp, in place: n Gauss-Jordan sweeps (no pivoting: the pivots of an
+// SPD matrix are its positive Schur complements, their product is the determinant), every lane owning the entries
+// lane, lane + 32 -- O(n) dependent steps of ~150 clocks instead of the O(n^3) dependent operations of the serial
+// routine (33 k clocks per step at n = 8, 8 k at n = 4, with the CTA's other warps waiting at the barrier).
+// A non-positive pivot yields NaN, as in spd_inv_det.  Returns det(a) in every lane.
+template <int n>
+__device__ __forceinline__ double warp_spd_inv_det(double* a, int lane) {
+  constexpr int NR = (n * n + 31) / 32;
+  double det = 1.0;
+#pragma unroll 1
+  for (int k = 0; k < n; k++) {
+    double pv = a[k * n + k];
+    if (!(pv > 0.0)) pv = nan("");
+    const double ip = 1.0 / pv;
+    det *= pv;
+    double nv[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const int o = lane + 32 * r;
+      nv[r] = 0.0;
+      if (o < n * n) {
+        const int i = o / n, j = o - i * n;
+        const double aik = a[i * n + k] * ip, akj = a[k * n + j];
+        if (i == k) nv[r] = (j == k) ? ip : akj * ip;
+        else nv[r] = (j == k) ? -aik : fma(-aik, akj, a[o]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const int o = lane + 32 * r;
+      if (o < n * n) a[o] = nv[r];
+    }
+    __syncwarp();
+  }
+  return det;
+}
+
 // inv = a^-1, det = det(a) for symmetric positive definite a (n x n, row-major).  A non-positive
 // pivot yields NaN, which then propagates like the reference's det/solve would.
 template <int n>

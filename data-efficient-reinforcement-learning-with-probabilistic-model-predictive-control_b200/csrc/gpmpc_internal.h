@@ -41,7 +41,9 @@ struct RolloutParams {
   // ---- launch geometry
   int group;           // pairs per N^2 phase
   int seg;             // columns per work item
-  int premat;          // uniform reverse sweep: per-step matrices / stage-cost adjoints precomputed for all steps
+  int premat;          // uniform reverse sweep: per-step matrices / stage-cost adjoints precomputed for all steps of a candidate
+                       // (1: kept in shared memory, 2: in the per-CTA global scratch ws_pre when the shared-memory plan is tight)
+  double* ws_pre;      // (gridDim.x, H, prelen) -- premat == 2
   double* ws_uni;      // uniform reverse sweep: (grid, NP * (2 + EV)) row / column sums of the sweep, reduced at L2
   int seg_bwd;         // columns per work item of the uniform reverse sweep (triangular: finer for balance)
   int* queue;          // candidate counters of the dynamic scheduling (SMs differ in speed by up to ~25 % on this workload:
@@ -73,6 +75,7 @@ cudaError_t launch_rollout(int EV, bool grad, const RolloutParams& p, int grid, 
 inline int rollout_max_threads(int EV) { return GEN_MAXT(EV); }
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
 size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat);
+int uniform_premat_len(int EV, int NP, int DP, int D, int H, int Na);
 cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t uniform_max_clusters(int EV, bool bwd, int cluster, int threads, size_t smem, int* nclusters);
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,

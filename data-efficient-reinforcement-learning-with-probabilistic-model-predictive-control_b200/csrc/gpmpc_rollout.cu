@@ -74,6 +74,9 @@ cudaError_t uniform_max_clusters(int EV, bool bwd, int cluster, int threads, siz
   }
 }
 
+int uniform_premat_len(int EV, int NP, int DP, int D, int H, int Na) {   // doubles per step of the precomputed records
+  return make_uni_layout(EV, true, NP, DP, D, H, Na, false).prelen;
+}
 size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat) {
   return (size_t)make_uni_layout(EV, bwd, NP, DP, D, H, Na, premat).total * sizeof(double);
 }

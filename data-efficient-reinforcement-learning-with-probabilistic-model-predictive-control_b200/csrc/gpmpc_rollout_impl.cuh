@@ -28,6 +28,11 @@ namespace gpmpc {
 // ---------------------------------------------------------------------------------------------
 // cost (setpoint_distance_reward_mapper.py:12-68, :124-142)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_early(double v) {   // (warp_sum, defined with the other warp helpers below)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 struct CostView {
   const double* target; const double* W; const double* WT; const double* smin; const double* smax;
   double kappa; int use_constraints;
@@ -70,6 +75,47 @@ __device__ inline void stage_cost(const CostView& c, int E, int Na, const double
       cmu += 0.5 * (1.0 + erf(zmin)) + (1.0 - 0.5 * (1.0 + erf(zmax)));
     }
   }
+}
+
+// stage_cost by one whole warp (uniform forward kernel, P0: the serial routine kept the CTA at the barrier for ~8 k clocks
+// per step).  scr: E * E + Dc doubles of shared memory private to the warp.  Results in every lane.
+__device__ inline void stage_cost_warp(const CostView& c, int E, int Na, const double* mu, const double* s, const double* a,
+                                       int lane, double* scr, double& cmu, double& cvar) {
+  const int Dc = E + Na, E2 = E * E;
+  double* TS = scr;            // Wss s
+  double* We = scr + E2;       // W (x - target)
+  for (int d = lane; d < Dc; d += 32) {
+    double v = 0.0;
+    for (int k = 0; k < Dc; k++) v += c.W[d * Dc + k] * ((k < E ? mu[k] : a[k - E]) - c.target[k]);
+    We[d] = v;
+  }
+  double tr1 = 0.0;
+  for (int o = lane; o < E2; o += 32) {
+    const int i = o / E, k = o - i * E;
+    tr1 += s[o] * c.W[k * Dc + i];
+    double v = 0.0;
+    for (int l = 0; l < E; l++) v += c.W[i * Dc + l] * s[l * E + k];
+    TS[o] = v;
+  }
+  __syncwarp();
+  double quad = 0.0, tr2 = 0.0, q2 = 0.0, pen = 0.0;
+  for (int d = lane; d < Dc; d += 32) quad += ((d < E ? mu[d] : a[d - E]) - c.target[d]) * We[d];
+  for (int o = lane; o < E2; o += 32) {
+    const int i = o / E, k = o - i * E;
+    tr2 += TS[o] * TS[k * E + i];
+    q2 += We[i] * s[o] * We[k];
+  }
+  if (c.use_constraints) {  // variance used as sigma: setpoint_distance_reward_mapper.py:60-64
+    const double rt2 = 1.4142135623730951;
+    for (int d = lane; d < E; d += 32) {
+      double sig = s[d * E + d];
+      double zmin = (c.smin[d] - mu[d]) / (sig * rt2), zmax = (c.smax[d] - mu[d]) / (sig * rt2);
+      pen += 0.5 * (1.0 + erf(zmin)) + (1.0 - 0.5 * (1.0 + erf(zmax)));
+    }
+  }
+  cmu = warp_sum_early(tr1 + quad + pen);
+  cvar = warp_sum_early(2.0 * tr2 + 4.0 * q2);
+  __syncwarp();
 }
 
 __device__ inline void terminal_cost(const CostView& c, int E, const double* mu, const double* s, double& cmu,

@@ -699,27 +699,46 @@ __global__ void __launch_bounds__(MAXT, UNI_FWD_MINCTAS(EV, MAXT)) uniform_fwd_k
         else v = (double)(p.iter_ctrl + t - 1);
         s_m[tid] = v;
       }
-      if (tid == 32) {
+      if (warp == 1) {
         double cmu, cvar;
-        stage_cost(cv, E, Na, s_mu, s_s, s_am + (t - 1) * Na, cmu, cvar);
-        s_r[t - 1] = -cmu;
-        s_rv[t - 1] = cvar;
+        stage_cost_warp(cv, E, Na, s_mu, s_s, s_am + (t - 1) * Na, lane, sm + L.cstw, cmu, cvar);
+        if (lane == 0) { s_r[t - 1] = -cmu; s_rv[t - 1] = cvar; }
       }
-      if (tid == 64) {
-        double Ca[EV * EV], Ai[EV * EV], det, pl = 1.0;
-        for (int e = 0; e < EV; e++)
-          for (int f = 0; f < EV; f++) Ca[e * EV + f] = s_s[e * EV + f] + (e == f ? 1.0 / il2[e] : 0.0);
-        spd_inv_det<EV>(Ca, Ai, det);
-        for (int e = 0; e < EV; e++) pl *= il2[e];
-        for (int e = 0; e < EV * EV; e++) s_A[e] = Ai[e];
-        s_misc[0] = s2 / sqrt(det * pl);   // c (same for all GPs)
+      // the two E x E inverses of the step, one warp each (warp_spd_inv_det): these used to be serial single-thread
+      // routines with the whole CTA waiting at the barrier below
+      if (warp == 2) {   // A = (s + diag(1 / il2))^-1, c = s2 / sqrt(det(.) prod il2)   (same for all GPs)
+        for (int o = lane; o < EV * EV; o += 32) s_A[o] = s_s[o] + ((o / EV == o % EV) ? 1.0 / il2[o / EV] : 0.0);
+        __syncwarp();
+        const double det = warp_spd_inv_det<EV>(s_A, lane);
+        if (lane == 0) {
+          double pl = 1.0;
+          for (int e = 0; e < EV; e++) pl *= il2[e];
+          s_misc[0] = s2 / sqrt(det * pl);
+        }
       }
-      if (tid == 96) {
-        double Wd[EV], Rinv[EV * EV], Qm[EV * EV], detR;
-        for (int e = 0; e < EV; e++) Wd[e] = 2.0 * il2[e];
-        pair_matrices<EV>(s_s, Wd, Rinv, Qm, detR);
-        for (int e = 0; e < EV * EV; e++) s_Q[e] = Qm[e];
-        s_misc[1] = detR;
+      if (warp == 3) {   // pair matrices (pair_matrices in gpmpc_common.cuh): T = I + sq s sq, Rinv = sq^-1 T^-1 sq, Q = Rinv s / 2
+        double* s_sq = s_S + EV * EV;   // s_S (2 E^2 doubles) is free until P4
+        if (lane < EV) s_sq[lane] = sqrt(2.0 * il2[lane]);
+        __syncwarp();
+        for (int o = lane; o < EV * EV; o += 32) {
+          const int e = o / EV, f = o - e * EV;
+          s_Q[o] = s_sq[e] * s_s[o] * s_sq[f] + (e == f ? 1.0 : 0.0);
+        }
+        __syncwarp();
+        const double detR = warp_spd_inv_det<EV>(s_Q, lane);
+        for (int o = lane; o < EV * EV; o += 32) {
+          const int e = o / EV, f = o - e * EV;
+          s_S[o] = s_Q[o] * s_sq[f] / s_sq[e];
+        }
+        __syncwarp();
+        for (int o = lane; o < EV * EV; o += 32) {
+          const int e = o / EV, f = o - e * EV;
+          double v = 0.0;
+#pragma unroll
+          for (int k = 0; k < EV; k++) v += s_S[e * EV + k] * s_s[k * EV + f];
+          s_Q[o] = 0.5 * v;
+        }
+        if (lane == 0) s_misc[1] = detR;
       }
       for (int o = tid; o < nwarps * L.partlen; o += NT) s_part[o] = 0.0;
       if (tid == 0) s_int[0] = 0;
@@ -1431,8 +1450,9 @@ __global__ void __launch_bounds__(UNI_BWD_MAXT(EV), UNI_BWD_MINCTAS(EV)) uniform
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
   const int D = p.D, N = p.N, NP = p.NP, DP = p.DP, Na = p.Na, H = p.H;
   const bool premat = p.premat != 0;
-  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, premat);
-  double* s_pre = sm + L.pre;
+  const UniLayout L = make_uni_layout(EV, true, NP, DP, D, H, Na, p.premat == 1);
+  // premat == 2: the per-step records live in this CTA's global scratch (written and read by this CTA only, between barriers)
+  double* s_pre = p.premat == 2 ? p.ws_pre + (size_t)blockIdx.x * H * L.prelen : sm + L.pre;
   const int oA = 0, oQ = EV * EV, oRi = 2 * EV * EV, odS = 3 * EV * EV, oc = 4 * EV * EV, odet = oc + 1, odmu = oc + 2,
             oda = odmu + EV;
   double* s_rec = sm + L.rec; double* s_tail = sm + L.tail;

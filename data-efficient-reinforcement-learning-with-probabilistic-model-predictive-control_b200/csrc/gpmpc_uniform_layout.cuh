@@ -6,7 +6,7 @@
 namespace gpmpc {
 
 struct UniLayout {
-  int rec, tail, tlen, rhot, pre, prelen, out, nOut, part, partlen, wp, wplen, S, cst, colred;
+  int rec, tail, tlen, rhot, pre, prelen, out, nOut, part, partlen, wp, wplen, S, cst, cstw, colred;
   int m, s, mu, A, Q, misc, M, V, acc, accN, am, r, rv, ints, small2, total;
 };
 
@@ -42,6 +42,7 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   if (bwd) o += 8 * 320;
 #endif
   L.S = o; o += 2 * E * E;          // S and s V^T of the recurrence stage
+  L.cstw = o; if (!bwd) o += E * E + GPMPC_MAX_D;   // forward: scratch of the warp-wide stage cost (stage_cost_warp)
   L.cst = o;                        // target, W, WT (read from shared memory by the forward kernel only)
 #ifdef GPMPC_BWD_NO_CST              // tuning variant (tools/variants.sh build-all): 2.7 KB less for the reverse sweep
   if (!bwd)

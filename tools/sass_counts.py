@@ -6,7 +6,8 @@
 Per kernel the hot loops are the backward branches whose body holds >= 100 DFMA/DADD/DMUL (tools/sass_loops.py); a loop
 iteration covers 2 rows x 4 columns (uniform forward sweep) or 2 rows x 8 columns (reverse sweep, general kernel) per
 lane.  Loops that read iK (LDG.E.128) belong to the diagonal pairs of the general kernel; of the variants with / without
-the residual row shift (far-away rows) the cheaper, common one is reported."""
+the residual row shift (far-away rows) the cheaper, common one is reported.  The tensor-core sweeps of the large state dimensions (DMMA.8x8x4 in the loop)
+cover 32 rows x 8 columns per round (8 elements per lane); a DMMA counts as the 8 warp-wide DFMAs whose work it does."""
 import collections
 import json
 import os
@@ -36,9 +37,11 @@ def loops_of(sass):
             continue
         body = [t for _, t in ins[index[tgt]:i + 1]]
         ops = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0] for t in body)
-        fp64 = sum(v for k, v in ops.items() if k.split(".")[0] in ("DFMA", "DADD", "DMUL"))
+        plain = sum(v for k, v in ops.items() if k.split(".")[0] in ("DFMA", "DADD", "DMUL"))
+        dmma = sum(v for k, v in ops.items() if k.startswith("DMMA"))
+        fp64 = plain + 8 * dmma     # a DMMA m8n8k4 = 256 FMAs = the work (and the pipe time) of 8 warp-wide DFMAs
         if fp64 >= 100:
-            out.append({"instructions": len(body), "float64": fp64, "other": len(body) - fp64,
+            out.append({"instructions": len(body), "float64": fp64, "other": len(body) - plain - dmma, "dmma": dmma,
                         "ldg128": sum(v for k, v in ops.items() if k.startswith("LDG.E.128")),
                         "lds": sum(v for k, v in ops.items() if k.startswith("LDS")),
                         "shfl": sum(v for k, v in ops.items() if k.startswith("SHFL")),
@@ -64,14 +67,16 @@ def main():
             sass = subprocess.run(["cuobjdump", "-sass", "-fun", fn, lib], capture_output=True, text=True).stdout
             # a sweep iteration evaluates one exp per element: exactly `elems` clamps (VIMNMX) per iteration
             all_loops = loops_of(sass)
-            loops = [l for l in all_loops if l["vimnmx"] == elems]
+            loops = [l for l in all_loops if l["vimnmx"] == elems and not l["dmma"]]
+            mma = [l for l in all_loops if l["dmma"] and l["vimnmx"] == 8]   # tensor-core sweeps: 8 elements per lane and round
             loops4 = [l for l in all_loops if l["vimnmx"] == 2 * elems and l["ldg128"] == 0]   # general kernel: 4 rows per lane
             if key.startswith("uniform"):
-                sweep = loops
+                sweep, el = (mma, 8) if mma else (loops, elems)
                 best = min(sweep, key=lambda l: l["float64"]) if sweep else None
                 if best:
-                    entry[key] = {"function": fn, "elements_per_iteration": elems, "loop": best,
-                                  "float64_per_element": best["float64"] / elems, "other_per_element": best["other"] / elems}
+                    entry[key] = {"function": fn, "elements_per_iteration": el, "loop": best, "tile_rows": 32 if mma else 64,
+                                  "float64_per_element": best["float64"] / el, "other_per_element": best["other"] / el,
+                                  "dmma_per_element": best["dmma"] / el}
             else:
                 sweeps = loops
                 off = [l for l in sweeps if l["ldg128"] == 0]
