@@ -143,6 +143,9 @@ def test_c5_dims_full_training_set_one_step(path):
     dict(E=5, Na=2, N=130, H=3, B=2, ls=0.6, seed=15, distinct_lengthscales=True),
     dict(E=8, Na=3, N=96, H=2, B=2, ls=0.7, seed=16),                     # C5 dims, small N
     dict(E=3, Na=1, N=70, H=4, B=3, ls=0.5, seed=17, limit_action_change=True, include_time_model=True, iter_ctrl=9),
+    # tensor-core sweeps of the uniform path (E >= 6) with zero-padded k steps / unused output columns, N off the 32-row grid
+    dict(E=6, Na=2, N=150, H=3, B=2, ls=0.7, seed=18),
+    dict(E=7, Na=1, N=100, H=2, B=3, ls=0.8, seed=19, include_time_model=True),
 ])
 @pytest.mark.parametrize("path", [0, 1])
 def test_cuda_matches_cpu_oracle(kw, path):
@@ -380,6 +383,23 @@ def test_kernel_path_selection_follows_the_hyperparameters():
     assert not eng.uses_uniform_path()
     eng.prepare(cfg["x"], cfg["y"], full_lengthscale(cfg), cfg["outputscale"], cfg["noise"])
     assert eng.uses_uniform_path()
+
+
+@pytest.mark.parametrize("kw", [dict(E=4, Na=2, N=200, H=6, B=3, ls=0.3, seed=61), dict(E=8, Na=3, N=130, H=4, B=2, ls=0.7, seed=62)])
+def test_reverse_sweep_records_in_global_scratch_match_shared_memory(kw, monkeypatch):
+    """The per-step small matrices / stage-cost adjoints of the reverse sweep are precomputed per candidate either into
+    shared memory or (shapes whose plan is tight: config 5) into a per-CTA global scratch, or recomputed per step: same
+    arithmetic, same gradient."""
+    cfg = make_workload(**kw)
+    out = {}
+    for mode in ("1", "2", "0"):
+        monkeypatch.setenv("GPMPC_UNI_PREMAT", mode)
+        eng = make_engine(cfg)
+        assert eng.uses_uniform_path()
+        out[mode] = rollout(eng, cfg)
+    np.testing.assert_allclose(out["2"]["cost"], out["1"]["cost"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["2"]["grad"], out["1"]["grad"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out["0"]["grad"], out["1"]["grad"], rtol=0, atol=1e-10)
 
 
 def test_uniform_path_large_state_dimension():
