@@ -340,8 +340,21 @@ static int fill_common(gpmpc_handle* h, RolloutParams& p, int EV, bool grad, int
   // (rollout_kernel).  Worth it once the N^2 sweeps dominate (NP >= 128).
   p.cluster = 1;
   if (H > 0) {
+    // the clusters of a launch must all be resident at once (their CTAs walk the steps in lock step): capacity from the
+    // driver -- a cluster lives inside one GPC, so e.g. 16 clusters of 8 one-CTA-per-SM kernels do NOT fit 148 SMs
+    // (B = 16 candidates took 10.2 ms with c = 8 in two waves, 5.9 ms with 8 candidates); cached per (c, plan)
+    auto capacity = [&](int c) -> int {
+      const size_t sm_c = rollout_smem_bytes(EV, grad, h->NP, h->DP, h->D, h->E, G1, H, Na, maxt / 32, p.lb_global != 0);
+      const size_t key = (sm_c * 16 + c) * 2 + (grad ? 1 : 0) + ((size_t)1 << 60);
+      for (int k = 0; k < 8; k++)
+        if (h->cl_cap_key[k] == key) return h->cl_cap[k];
+      int n = 0;
+      if (rollout_max_clusters(EV, grad, c, maxt, sm_c, &n) != cudaSuccess) { cudaGetLastError(); n = h->num_sms / (2 * c); }
+      h->cl_cap_key[h->cl_cap_next] = key; h->cl_cap[h->cl_cap_next] = n; h->cl_cap_next = (h->cl_cap_next + 1) % 8;
+      return n;
+    };
     int c = 8;
-    while (c > 1 && (B * c > h->num_sms || P < c || h->NP < 128)) c /= 2;
+    while (c > 1 && (B * c > h->num_sms || P < c || h->NP < 128 || B > capacity(c))) c /= 2;
     if (const char* e = getenv("GPMPC_GEN_CLUSTER")) { int v = atoi(e); if (v == 1 || ((v == 2 || v == 4 || v == 8) && B * v <= h->num_sms && P >= v)) c = v; }
     p.cluster = c;
     if (c > 1) ctas = 1;

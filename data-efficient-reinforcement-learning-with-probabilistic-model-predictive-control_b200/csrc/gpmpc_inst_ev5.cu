@@ -5,4 +5,5 @@ template cudaError_t launch_rollout_inst<5>(bool, const RolloutParams&, int, int
 template cudaError_t launch_backward_inst<5>(const BackwardParams&, cudaStream_t);
 template cudaError_t launch_uniform_inst<5>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t);
 template cudaError_t max_clusters_uniform_inst<5>(bool, int, int, size_t, int*);
+template cudaError_t max_clusters_rollout_inst<5>(bool, int, int, size_t, int*);
 }  // namespace gpmpc

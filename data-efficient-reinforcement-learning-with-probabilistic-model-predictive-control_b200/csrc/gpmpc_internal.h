@@ -76,6 +76,7 @@ inline int rollout_max_threads(int EV) { return GEN_MAXT(EV); }
 cudaError_t launch_backward(int E, const BackwardParams& p, cudaStream_t st);
 size_t uniform_smem_bytes(int EV, bool bwd, int NP, int DP, int D, int H, int Na, bool premat);
 int uniform_premat_len(int EV, int NP, int DP, int D, int H, int Na);
+cudaError_t rollout_max_clusters(int EV, bool grad, int cluster, int threads, size_t smem, int* nclusters);
 cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* grad, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t uniform_max_clusters(int EV, bool bwd, int cluster, int threads, size_t smem, int* nclusters);
 cudaError_t launch_prepare(const double* x, const double* y, const double* ls, const double* s2,

@@ -24,11 +24,13 @@ template <int EV> cudaError_t launch_uniform_inst(bool bwd, const RolloutParams&
 template <int EV> cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, int threads, size_t smem, cudaStream_t st);
 template <int E> cudaError_t launch_backward_inst(const BackwardParams& p, cudaStream_t st);
 template <int EV> cudaError_t max_clusters_uniform_inst(bool bwd, int cluster, int threads, size_t smem, int* nclusters);
+template <int EV> cudaError_t max_clusters_rollout_inst(bool grad, int cluster, int threads, size_t smem, int* nclusters);
 #define GPMPC_DECL(n)                                                                                             \
   extern template cudaError_t launch_rollout_inst<n>(bool, const RolloutParams&, int, int, size_t, cudaStream_t);      \
   extern template cudaError_t launch_backward_inst<n>(const BackwardParams&, cudaStream_t);                       \
   extern template cudaError_t launch_uniform_inst<n>(bool, const RolloutParams&, double*, int, int, size_t, cudaStream_t); \
-  extern template cudaError_t max_clusters_uniform_inst<n>(bool, int, int, size_t, int*);
+  extern template cudaError_t max_clusters_uniform_inst<n>(bool, int, int, size_t, int*);                         \
+  extern template cudaError_t max_clusters_rollout_inst<n>(bool, int, int, size_t, int*);
 GPMPC_DECL(1) GPMPC_DECL(2) GPMPC_DECL(3) GPMPC_DECL(4) GPMPC_DECL(5) GPMPC_DECL(6) GPMPC_DECL(7) GPMPC_DECL(8)
 #undef GPMPC_DECL
 
@@ -56,6 +58,20 @@ cudaError_t launch_uniform(int EV, bool bwd, const RolloutParams& p, double* gra
     case 6: return launch_uniform_inst<6>(bwd, p, grad, grid, threads, smem, st);
     case 7: return launch_uniform_inst<7>(bwd, p, grad, grid, threads, smem, st);
     case 8: return launch_uniform_inst<8>(bwd, p, grad, grid, threads, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t rollout_max_clusters(int EV, bool grad, int cluster, int threads, size_t smem, int* nclusters) {
+  switch (EV) {
+    case 1: return max_clusters_rollout_inst<1>(grad, cluster, threads, smem, nclusters);
+    case 2: return max_clusters_rollout_inst<2>(grad, cluster, threads, smem, nclusters);
+    case 3: return max_clusters_rollout_inst<3>(grad, cluster, threads, smem, nclusters);
+    case 4: return max_clusters_rollout_inst<4>(grad, cluster, threads, smem, nclusters);
+    case 5: return max_clusters_rollout_inst<5>(grad, cluster, threads, smem, nclusters);
+    case 6: return max_clusters_rollout_inst<6>(grad, cluster, threads, smem, nclusters);
+    case 7: return max_clusters_rollout_inst<7>(grad, cluster, threads, smem, nclusters);
+    case 8: return max_clusters_rollout_inst<8>(grad, cluster, threads, smem, nclusters);
     default: return cudaErrorInvalidValue;
   }
 }

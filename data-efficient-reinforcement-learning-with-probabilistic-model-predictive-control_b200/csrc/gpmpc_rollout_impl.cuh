@@ -1543,6 +1543,32 @@ cudaError_t launch_rollout_inst(bool grad, const RolloutParams& p, int grid, int
   return cudaGetLastError();
 }
 
+// Clusters of `cluster` CTAs of the general kernel the device holds at once (cudaOccupancyMaxActiveClusters: a cluster
+// must fit one GPC, so this is less than SMs / cluster -- 16 clusters of 8 single-CTA-per-SM kernels do NOT fit 148 SMs).
+template <int EV>
+cudaError_t max_clusters_rollout_inst(bool grad, int cluster, int threads, size_t smem, int* nclusters) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster * 64);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (grad) {
+    e = cudaFuncSetAttribute(rollout_kernel<EV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveClusters(nclusters, rollout_kernel<EV, true>, &cfg);
+  }
+  e = cudaFuncSetAttribute(rollout_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveClusters(nclusters, rollout_kernel<EV, false>, &cfg);
+}
+
 template <int E>
 cudaError_t launch_backward_inst(const BackwardParams& p, cudaStream_t st) {
   const int blk = 128, grid = (p.B + blk - 1) / blk;
