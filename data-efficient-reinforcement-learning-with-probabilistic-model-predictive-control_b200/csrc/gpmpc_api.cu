@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, 
 
 extern "C" {
 
-int gpmpc_version(void) { return 100; }
+int gpmpc_version(void) { return 200; }   // 100: round 1; 200: round 2 (gpmpc_lbfgs_update added, tensor-core sweeps, general path rebuilt)
 
 int gpmpc_fp64_peak(int device, double* flops_per_s) {
   if (!flops_per_s) return GPMPC_ERR_BAD_ARG;
