@@ -469,11 +469,20 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
     }
     const size_t smf = uniform_smem_bytes(E, false, h->NP, h->DP, D, H, Na, false);
     size_t smb = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, false);
+    // Reverse sweep as 3 CTAs x 128 threads (168-register build) instead of 2 x 256: more co-resident CTAs hide the serial
+    // phases better (+9 % at N=200, +4 % at N=300, +1.8 % at N=500), but 444 slots of 4 warps make a longer last wave than
+    // 296 slots of 8 (-3.4 % at 1024 candidates, N=500): taken from ~4 waves on, from 2 for small training sets
+    // (profiles/r02x_reverse_sweep_plans.txt)
+    const bool bwd3 = E <= 5 && (B >= 12 * h->num_sms || (h->NP <= 320 && B >= 6 * h->num_sms));
     {  // precomputed per-step matrices: only if they do not cost a resident CTA (or the launch itself)
       const size_t with = uniform_smem_bytes(E, true, h->NP, h->DP, D, H, Na, true);
       const size_t two = 112 * 1024 - GPMPC_STATIC_SMEM;   // two CTAs per SM
       const size_t lim = smb <= two ? two : h->smem_optin;
       p.premat = with <= lim ? 1 : 2;     // 2: the precomputed records go to a per-CTA global scratch (allocated below)
+      // E <= 5: three 128-thread CTAs per SM (the 168-register build) beat two of 256 when they fit; at the headline shape
+      // they do once the records are in the global scratch (reading them from L2 costs nothing measurable)
+      auto fits3 = [&](size_t sm) { return (size_t)(227 * 1024) / (sm + GPMPC_STATIC_SMEM + 1024) >= 3; };
+      if (bwd3 && !fits3(with) && fits3(smb)) p.premat = 2;
       if (const char* e = getenv("GPMPC_UNI_PREMAT")) { const int v = atoi(e); p.premat = v == 0 ? 0 : ((v == 1 && with <= lim) ? 1 : 2); }
       if (p.premat == 1) smb = with;
     }
@@ -486,8 +495,8 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
       if (fit < 1) fit = 1;
       int ctas = fit > 2 ? 2 : fit;      // tuned on B200: 2 CTAs x 256 threads per SM (16 warps, <= 128 registers)
       *thr = 256;
-      // forward kernel, state dimensions <= 5: 3 CTAs x 128 threads with <= 168 registers when they fit (57.9 vs 60.6 ms)
-      if (fwd && E <= 5 && fit >= 3) { ctas = 3; *thr = 128; }
+      // state dimensions <= 5: 3 CTAs x 128 threads with <= 168 registers when they fit (forward: 57.9 vs 60.6 ms)
+      if (E <= 5 && fit >= 3 && (fwd || bwd3)) { ctas = 3; *thr = 128; }
       if (const char* e = getenv(env_thr)) { int v = atoi(e); if (v == 128 || v == 256 || (!fwd && v == 192)) *thr = v; }   // tuning aid
       if (const char* e = getenv(env_ctas)) { int v = atoi(e); if (v >= 1 && v <= fit) ctas = v; }
       if (E > 5) { *thr = UNI_MAXT(E); ctas = 1; }   // large state dims: one CTA per SM (tensor-core sweeps: 384 threads)

@@ -66,17 +66,10 @@ constexpr int UNI_CL_ACC = 64;   // doubles per accumulator buffer of the forwar
 // budget ptxas hoists the record / iK loads of a loop body to its top and interleaves the stages of both column pairs
 // (forward 60.6 -> 57.9 ms at the headline shape).  The host picks it when three CTAs fit the shared memory.
 #define UNI_FWD_MINCTAS(EV, MAXT) ((MAXT) == 128 && (EV) <= 5 ? 3 : UNI_MINB(EV))
-// tuning hook (tools/variants.sh): launch bounds of the reverse-sweep kernel, e.g. -DUNI_BWD_MAXT_ALL=128 -DUNI_BWD_MINCTAS_ALL=3
-#ifdef UNI_BWD_MAXT_ALL
-#define UNI_BWD_MAXT(EV) UNI_BWD_MAXT_ALL
-#else
-#define UNI_BWD_MAXT(EV) UNI_MAXT(EV)
-#endif
-#ifdef UNI_BWD_MINCTAS_ALL
-#define UNI_BWD_MINCTAS(EV) UNI_BWD_MINCTAS_ALL
-#else
-#define UNI_BWD_MINCTAS(EV) UNI_MINB(EV)
-#endif
+// The reverse sweep has the same two builds: 3 CTAs x 128 threads (<= 168 registers) for E <= 5 when three fit the shared
+// memory -- they do at the headline shape once the precomputed per-step records live in the global scratch (premat = 2)
+// -- else 2 x 256 (128 registers).  Measured: 81.6 vs 82.5 ms (profiles/r02s_dmma_experiments.txt).
+#define UNI_BWD_MINCTAS(EV, MAXT) ((MAXT) == 128 && (EV) <= 5 ? 3 : UNI_MINB(EV))
 
 // ---------------------------------------------------------------------------------------------
 // forward hot loop: full sweep, rows {64 I + lane, +32}, columns [jbeg, jend)
@@ -1443,8 +1436,8 @@ __device__ inline void uni_stage_adjoint(const RolloutParams& p, int Na, double 
 // ---------------------------------------------------------------------------------------------
 // uniform reverse-sweep kernel: one CTA per candidate, t = H .. 1
 // ---------------------------------------------------------------------------------------------
-template <int EV>
-__global__ void __launch_bounds__(UNI_BWD_MAXT(EV), UNI_BWD_MINCTAS(EV)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
+template <int EV, int MAXT>
+__global__ void __launch_bounds__(MAXT, UNI_BWD_MINCTAS(EV, MAXT)) uniform_bwd_kernel(const RolloutParams p, double* __restrict__ grad) {
   extern __shared__ __align__(16) double sm[];
   constexpr int E = EV, P = E * (E + 1) / 2;
   const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -1934,9 +1927,16 @@ cudaError_t launch_uniform_inst(bool bwd, const RolloutParams& p, double* grad, 
     cfg.numAttrs = 1;
   }
   if (bwd) {
-    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaLaunchKernelEx(&cfg, uniform_bwd_kernel<EV>, p, grad);
+    if (EV <= 5 && threads <= 128) {   // three-CTAs-per-SM build (see UNI_BWD_MINCTAS)
+      constexpr int T = EV <= 5 ? 128 : UNI_MAXT(EV);   // (no extra instantiation for the larger state dims)
+      e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaLaunchKernelEx(&cfg, uniform_bwd_kernel<EV, T>, p, grad);
+    } else {
+      e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, UNI_MAXT(EV)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaLaunchKernelEx(&cfg, uniform_bwd_kernel<EV, UNI_MAXT(EV)>, p, grad);
+    }
   } else {
     if (EV <= 5 && threads <= 128) {   // three-CTAs-per-SM build (see UNI_FWD_MINCTAS)
       constexpr int T = EV <= 5 ? 128 : UNI_MAXT(EV);   // (no extra instantiation for the larger state dims)
@@ -1970,9 +1970,9 @@ cudaError_t max_clusters_uniform_inst(bool bwd, int cluster, int threads, size_t
   cfg.numAttrs = 1;
   cudaError_t e;
   if (bwd) {
-    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(uniform_bwd_kernel<EV, UNI_MAXT(EV)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveClusters(nclusters, uniform_bwd_kernel<EV>, &cfg);
+    return cudaOccupancyMaxActiveClusters(nclusters, uniform_bwd_kernel<EV, UNI_MAXT(EV)>, &cfg);
   }
   e = cudaFuncSetAttribute(uniform_fwd_kernel<EV, UNI_MAXT(EV)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

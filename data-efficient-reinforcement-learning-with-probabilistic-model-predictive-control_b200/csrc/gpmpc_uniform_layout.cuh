@@ -44,10 +44,7 @@ HD UniLayout make_uni_layout(int EV, bool bwd, int NP, int DP, int D, int H, int
   L.S = o; o += 2 * E * E;          // S and s V^T of the recurrence stage
   L.cstw = o; if (!bwd) o += E * E + GPMPC_MAX_D;   // forward: scratch of the warp-wide stage cost (stage_cost_warp)
   L.cst = o;                        // target, W, WT (read from shared memory by the forward kernel only)
-#ifdef GPMPC_BWD_NO_CST              // tuning variant (tools/variants.sh build-all): 2.7 KB less for the reverse sweep
-  if (!bwd)
-#endif
-  o += GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + GPMPC_MAX_EV * GPMPC_MAX_EV;
+  if (!bwd) o += GPMPC_MAX_D + GPMPC_MAX_D * GPMPC_MAX_D + GPMPC_MAX_EV * GPMPC_MAX_EV;
   L.m = o; o += GPMPC_MAX_D;
   L.s = o; o += EV * EV;
   L.mu = o; o += GPMPC_MAX_EV;
