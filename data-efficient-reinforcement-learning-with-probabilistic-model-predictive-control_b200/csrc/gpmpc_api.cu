@@ -54,6 +54,14 @@ struct gpmpc_handle {
   bool ev_fwd = false, ev_bwd = false;
   size_t cl_cap_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cache of uniform_max_clusters (key: shared-memory plan, cluster size)
   int cl_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cl_cap_next = 0;
+  // gpmpc_fit_eval: the factorisation + marginal-likelihood kernels of one objective evaluation as a CUDA graph
+  cudaStream_t fit_stream = nullptr;
+  cudaGraphExec_t fit_exec = nullptr;
+  double* fit_pin = nullptr;               // pinned host staging: theta as {ls (E,D), s2 (E), noise (E)}, then out (E,3+D), then info (E ints)
+  DevBuf fit_out;
+  const double *fit_x = nullptr, *fit_y = nullptr;
+  int fit_N = 0, fit_D = 0, fit_E = 0;
+  long long fit_launches = 0;
 };
 
 static int fail(gpmpc_handle* h, int code, const char* msg, cudaError_t ce = cudaSuccess) {
@@ -166,9 +174,28 @@ int gpmpc_destroy(gpmpc_handle* h) {
                    &h->c_target, &h->c_W, &h->c_WT, &h->c_smin, &h->c_smax, &h->ws_kk, &h->ws_gam, &h->colcoef, &h->t_mu, &h->t_var,
                    &h->t_r, &h->t_rv, &h->t_am, &h->t_cost, &h->records, &h->step_in, &h->exp2tab, &h->dbg_clk, &h->ws_uni, &h->queue, &h->ws_cl, &h->ws_pre};
   for (DevBuf* b : all) b->release();
+  h->fit_out.release();
+  if (h->fit_exec) cudaGraphExecDestroy(h->fit_exec);
+  if (h->fit_stream) cudaStreamDestroy(h->fit_stream);
+  if (h->fit_pin) cudaFreeHost(h->fit_pin);
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
+  return GPMPC_OK;
+}
+
+static int prepare_buffers(gpmpc_handle* h, int NP, int D, int E) {   // device buffers of the training block
+  CU(h->x.ensure(sizeof(double) * NP * D));   // room for gpmpc_append up to the padded size
+  CU(h->ls.ensure(sizeof(double) * E * D));
+  CU(h->il2.ensure(sizeof(double) * E * D));
+  CU(h->s2.ensure(sizeof(double) * E));
+  CU(h->noise.ensure(sizeof(double) * E));
+  CU(h->beta.ensure(sizeof(double) * E * NP));
+  CU(h->betaT.ensure(sizeof(double) * E * NP));
+  CU(h->iK.ensure(sizeof(double) * (size_t)E * NP * NP));
+  CU(h->Kbuf.ensure(sizeof(double) * (size_t)E * NP * NP));
+  CU(h->Zbuf.ensure(sizeof(double) * (size_t)E * NP * (NP + 64)));
+  CU(h->info.ensure(sizeof(int) * GPMPC_MAX_STATE));
   return GPMPC_OK;
 }
 
@@ -182,17 +209,7 @@ int gpmpc_prepare(gpmpc_handle* h, const double* x, const double* y, const doubl
   CU(cudaSetDevice(h->device));
   const int NP = (N + 63) / 64 * 64;
   h->prepared = false;
-  CU(h->x.ensure(sizeof(double) * NP * D));   // room for gpmpc_append up to the padded size
-  CU(h->ls.ensure(sizeof(double) * E * D));
-  CU(h->il2.ensure(sizeof(double) * E * D));
-  CU(h->s2.ensure(sizeof(double) * E));
-  CU(h->noise.ensure(sizeof(double) * E));
-  CU(h->beta.ensure(sizeof(double) * E * NP));
-  CU(h->betaT.ensure(sizeof(double) * E * NP));
-  CU(h->iK.ensure(sizeof(double) * (size_t)E * NP * NP));
-  CU(h->Kbuf.ensure(sizeof(double) * (size_t)E * NP * NP));
-  CU(h->Zbuf.ensure(sizeof(double) * (size_t)E * NP * (NP + 64)));
-  CU(h->info.ensure(sizeof(int) * GPMPC_MAX_STATE));
+  { const int rc = prepare_buffers(h, NP, D, E); if (rc != GPMPC_OK) return rc; }
   CU(cudaMemcpyAsync(h->x.ptr, x, sizeof(double) * N * D, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(h->ls.ptr, lengthscale, sizeof(double) * E * D, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(h->s2.ptr, outputscale, sizeof(double) * E, cudaMemcpyDeviceToDevice, st));
@@ -666,6 +683,83 @@ int gpmpc_mll(gpmpc_handle* h, const double* y, double* out, void* stream) {
   CU(cudaSetDevice(h->device));
   CU(launch_mll(h->x.as<double>(), y, h->ls.as<double>(), h->s2.as<double>(), h->Kbuf.as<double>(), h->iK.as<double>(),
                 h->beta.as<double>(), out, h->N, h->NP, h->D, h->E, 3 + h->D, st, &h->launches));
+  return GPMPC_OK;
+}
+
+// Everything one objective evaluation of the fit puts on the stream: trial hyper-parameters from the pinned staging
+// buffer, Gram + Cholesky + inverse (launch_prepare), LML + gradient (launch_mll), results back to the staging buffer.
+static int fit_enqueue(gpmpc_handle* h, const double* x, const double* y, int N, int NP, int D, int E, cudaStream_t st) {
+  double* pin = h->fit_pin;
+  double* pin_out = pin + E * (D + 2);
+  int* pin_info = reinterpret_cast<int*>(pin_out + E * (3 + D));
+  CU(cudaMemcpyAsync(h->x.ptr, x, sizeof(double) * N * D, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(h->ls.ptr, pin, sizeof(double) * E * D, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->s2.ptr, pin + E * D, sizeof(double) * E, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->noise.ptr, pin + E * D + E, sizeof(double) * E, cudaMemcpyHostToDevice, st));
+  CU(launch_il2(h->ls.as<double>(), h->il2.as<double>(), E * D, st));
+  h->launches += 1;
+  CU(launch_prepare(h->x.as<double>(), y, h->ls.as<double>(), h->s2.as<double>(), h->noise.as<double>(), N, NP, D, E,
+                    h->Kbuf.as<double>(), h->Zbuf.as<double>(), h->iK.as<double>(), h->beta.as<double>(),
+                    h->betaT.as<double>(), h->info.as<int>(), st, &h->launches));
+  CU(launch_mll(h->x.as<double>(), y, h->ls.as<double>(), h->s2.as<double>(), h->Kbuf.as<double>(), h->iK.as<double>(),
+                h->beta.as<double>(), h->fit_out.as<double>(), N, NP, D, E, 3 + D, st, &h->launches));
+  CU(cudaMemcpyAsync(pin_out, h->fit_out.ptr, sizeof(double) * E * (3 + D), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(pin_info, h->info.ptr, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
+  return GPMPC_OK;
+}
+
+int gpmpc_fit_eval(gpmpc_handle* h, const double* x, const double* y, const double* theta, int N, int D, int E,
+                   double* out, int* info, void* stream) {
+  if (!h) return GPMPC_ERR_BAD_ARG;
+  if (!x || !y || !theta || !out || !info || N < 1) return fail(h, GPMPC_ERR_BAD_ARG, "fit_eval: null pointer or N < 1");
+  if (E < 1 || E > GPMPC_MAX_STATE || D < E || D > GPMPC_MAX_INPUT)
+    return fail(h, GPMPC_ERR_UNSUPPORTED, "fit_eval: need 1 <= E <= 8 and E <= D <= 16");
+  CU(cudaSetDevice(h->device));
+  const int NP = (N + 63) / 64 * 64;
+  h->prepared = false;
+  if (!h->fit_stream) CU(cudaStreamCreateWithFlags(&h->fit_stream, cudaStreamNonBlocking));
+  if (!h->fit_pin) CU(cudaHostAlloc(reinterpret_cast<void**>(&h->fit_pin),
+                                    sizeof(double) * GPMPC_MAX_STATE * (2 * GPMPC_MAX_INPUT + 6), cudaHostAllocDefault));
+  double* pin = h->fit_pin;
+  for (int a = 0; a < E; a++) {           // theta rows {ls[D], s2, noise} -> {ls (E,D), s2 (E), noise (E)}
+    for (int d = 0; d < D; d++) pin[a * D + d] = theta[a * (D + 2) + d];
+    pin[E * D + a] = theta[a * (D + 2) + D];
+    pin[E * D + E + a] = theta[a * (D + 2) + D + 1];
+  }
+  if (!h->fit_exec || h->fit_x != x || h->fit_y != y || h->fit_N != N || h->fit_D != D || h->fit_E != E) {
+    // (re)capture: buffers first (no allocation inside a capture), the caller's stream drained once (x, y uploads)
+    if (h->fit_exec) { cudaGraphExecDestroy(h->fit_exec); h->fit_exec = nullptr; }
+    { const int rc = prepare_buffers(h, NP, D, E); if (rc != GPMPC_OK) return rc; }
+    CU(h->fit_out.ensure(sizeof(double) * GPMPC_MAX_STATE * (3 + GPMPC_MAX_INPUT)));
+    CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    const long long l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->fit_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = fit_enqueue(h, x, y, N, NP, D, E, h->fit_stream);
+    const cudaError_t ce = cudaStreamEndCapture(h->fit_stream, &graph);
+    if (rc != GPMPC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, "fit_eval: stream capture", ce);
+    const cudaError_t ci = cudaGraphInstantiate(&h->fit_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess) { h->fit_exec = nullptr; return fail(h, GPMPC_ERR_CUDA, "fit_eval: graph instantiation", ci); }
+    h->fit_launches = h->launches - l0;
+    h->launches = l0;
+    h->fit_x = x; h->fit_y = y; h->fit_N = N; h->fit_D = D; h->fit_E = E;
+  }
+  CU(cudaGraphLaunch(h->fit_exec, h->fit_stream));
+  h->launches += h->fit_launches;
+  CU(cudaStreamSynchronize(h->fit_stream));
+  const double* pin_out = pin + E * (D + 2);
+  const int* pin_info = reinterpret_cast<const int*>(pin_out + E * (3 + D));
+  bool ok = true;
+  for (int a = 0; a < E; a++) { info[a] = pin_info[a]; ok = ok && pin_info[a] == 0; }
+  for (int k = 0; k < E * (3 + D); k++) out[k] = pin_out[k];
+  bool uni = true;
+  for (int a = 1; a < E && uni; a++)
+    for (int k = 0; k < D + 2; k++) uni = uni && (theta[a * (D + 2) + k] == theta[k]);
+  h->uniform = uni;
+  h->N = N; h->NP = NP; h->D = D; h->DP = (D + 1) & ~1; h->E = E;
+  h->prepared = ok;
   return GPMPC_OK;
 }
 

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "gpmpc_rollout": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
                       + [ctypes.c_void_p] * 7 + [ctypes.c_void_p]),
     "gpmpc_mll": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "gpmpc_fit_eval": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3),
     "gpmpc_set_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gpmpc_uses_uniform_path": (ctypes.c_int, [ctypes.c_void_p]),
     "gpmpc_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -237,6 +238,25 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self._lib.gpmpc_mll(self._h, _ptr(y), _ptr(out), self._stream()))
         return out
+
+    def fit_eval(self, x, y, theta):
+        """One objective evaluation of the hyper-parameter fit for all E GPs as ONE CUDA-graph launch (gpmpc_fit_eval):
+        x (N,D), y (N,E) CUDA tensors that stay alive and unchanged during the fit, theta (E, D+2) host rows
+        {lengthscale[D], outputscale, noise}.  Returns (out, info): out (E, 3+D) host tensor as mll(), info (E) int32 --
+        non-zero where K + noise I of that GP is not positive definite (its row of out is meaningless)."""
+        if not (x.is_cuda and y.is_cuda and x.dtype == torch.float64 and y.dtype == torch.float64
+                and x.is_contiguous() and y.is_contiguous()):
+            raise ValueError("fit_eval: x and y must be contiguous float64 CUDA tensors")
+        N, D = x.shape
+        E = y.shape[1]
+        th = torch.as_tensor(theta, dtype=torch.float64, device="cpu").reshape(E, D + 2).contiguous()
+        out = torch.empty((E, 3 + D), dtype=torch.float64)
+        info = torch.zeros((E,), dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.gpmpc_fit_eval(self._h, _ptr(x), _ptr(y), th.data_ptr(), N, D, E, out.data_ptr(),
+                                                 info.data_ptr(), self._stream()))
+        self.N, self.D, self.E = N, D, E
+        return out, info
 
     def set_path(self, mode):
         """0: automatic (uniform-kernel fast path when all GPs share their hyper-parameters), 1: general path."""

@@ -224,20 +224,21 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
     def train(queue, saved_state, lr_train, num_iter_train, clip_grad_value, print_train=False, step_print_train=25,
               device=None, stop_event=None, lockstep=True):
         """Hyper-parameter fitting with the reference's procedure (gp_model.py:193-306): for every GP, uniform random
-        re-initialisation inside the Interval bounds, torch LBFGS (strong Wolfe) on the unconstrained parameters,
-        keep the best negative marginal log-likelihood (per data point, as gpytorch's ExactMarginalLogLikelihood
-        reports it) and fall back to the previous hyper-parameters when nothing better is found.  The objective and
-        its gradient come from the device (gpmpc_prepare + gpmpc_mll: Gram, Cholesky, K^-1, 1/2 tr((aa^T-K^-1) dK));
-        only the O(D) optimiser state lives on the host.  The result goes to `queue` as a list of
+        re-initialisation inside the Interval bounds, LBFGS with strong-Wolfe line search on the unconstrained
+        parameters (lbfgs_lockstep.LbfgsStrongWolfe: torch.optim.LBFGS's algorithm as a generator), keep the best
+        negative marginal log-likelihood (per data point, as gpytorch's ExactMarginalLogLikelihood reports it) and fall
+        back to the previous hyper-parameters when nothing better is found.  The objective and its gradient come from
+        the device (Gram, Cholesky, K^-1, 1/2 tr((aa^T-K^-1) dK)); only the O(D) optimiser state lives on the host.
+        The result goes to `queue` as a list of
         {'covar_module.base_kernel.lengthscale', 'covar_module.outputscale', 'likelihood.noise'} dicts.
 
-        lockstep (default): the E fits run as E host threads whose objective evaluations are BATCHED -- every round, the
-        trial hyper-parameters of all GPs still fitting go to the device in ONE gpmpc_prepare + gpmpc_mll (the engine
-        factorises E GPs at once; a GP that is waiting or done rides along with its last values).  Each GP sees exactly the
-        evaluations its own LBFGS asks for, so the result equals the serial procedure's (lockstep=False: one GP after
-        the other, E times as many device calls)."""
-        import threading
+        lockstep (default): the E fits advance side by side and their objective evaluations are BATCHED -- every round,
+        the trial hyper-parameters of all GPs still fitting go to the device in ONE CUDA-graph launch of the
+        factorisation + likelihood kernels (gpmpc_fit_eval; a GP that is done rides along with its last values).  Each GP
+        sees exactly the evaluations its own optimiser asks for, so the result equals the serial procedure's
+        (lockstep=False: one GP after the other with gpmpc_prepare + gpmpc_mll, E times as many device calls)."""
         import time
+        from .lbfgs_lockstep import LbfgsStrongWolfe, run_lockstep
         t0 = time.time()
         saved_state.to_tensors()
         x = torch.as_tensor(saved_state.inputs, dtype=torch.float64)
@@ -251,6 +252,8 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
             return
         n, d = x.shape
         n_gp = len(saved_state.parameters)
+        x_dev = x.to(engine.device).contiguous()
+        y_dev = y_all.to(engine.device).contiguous()
 
         def bounds(idx):
             lo = torch.cat([torch.as_tensor(cons["min_lengthscale"], dtype=torch.float64)[idx].reshape(-1),
@@ -259,159 +262,122 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
             hi = torch.cat([torch.as_tensor(cons["max_lengthscale"], dtype=torch.float64)[idx].reshape(-1),
                             torch.as_tensor(cons["max_outputscale"], dtype=torch.float64)[idx].reshape(1),
                             torch.as_tensor(cons["max_std_noise"], dtype=torch.float64)[idx].reshape(1) ** 2])
-            return lo, hi
+            return lo.numpy().copy(), hi.numpy().copy()
+
+        def unpack(row):
+            """(E, 3+D) row of the device result -> (-LML / n, gradient w.r.t. theta = [lengthscale (D), outputscale, noise])."""
+            row = np.asarray(row, dtype=np.float64)
+            return float(-row[0] / n), -np.concatenate([row[3:3 + d], row[1:3]]) / n
 
         def eval_one(idx, theta):
-            """-LML / n and its gradient w.r.t. theta = [lengthscale (D), outputscale, noise] of GP idx alone."""
+            """Objective of GP idx alone (gpmpc_prepare + gpmpc_mll with E = 1)."""
+            th = torch.as_tensor(theta, dtype=torch.float64)
             y_col = y_all[:, idx:idx + 1].contiguous()
-            engine.prepare(x, y_col, theta[:d].reshape(1, d), theta[d:d + 1], theta[d + 1:d + 2])
-            out = engine.mll(y_col)[0].cpu()
-            return -out[0] / n, -torch.cat([out[3:3 + d], out[1:3]]) / n
+            engine.prepare(x, y_col, th[:d].reshape(1, d), th[d:d + 1], th[d + 1:d + 2])
+            return unpack(engine.mll(y_col)[0].cpu().numpy())
 
-        def eval_all(thetas, want):
-            """One device round for all GPs (rows of `thetas`); falls back to GP-by-GP calls when the joint factorisation
-            fails (a trial point of ONE GP with a non positive definite kernel matrix must not hurt the others)."""
+        prev_thetas = [np.concatenate([np.asarray(p["covar_module.base_kernel.lengthscale"], dtype=np.float64).reshape(-1),
+                                       np.asarray(p["covar_module.outputscale"], dtype=np.float64).reshape(1),
+                                       np.asarray(p["likelihood.noise"], dtype=np.float64).reshape(1)])
+                       for p in saved_state.parameters]
+        last = [t.copy() for t in prev_thetas]         # the values a GP rides along with when it has nothing to evaluate
+
+        def eval_all(points):
+            """One device round for all GPs: ONE CUDA-graph launch (gpmpc_fit_eval); a GP whose trial point has a non
+            positive definite kernel matrix gets its error, the others their values.  GP by GP if the joint call fails."""
             try:
-                th = torch.stack(thetas)
-                engine.prepare(x, y_all, th[:, :d], th[:, d], th[:, d + 1])
-                out = engine.mll(y_all).cpu()
-                return {i: (-out[i, 0] / n, -torch.cat([out[i, 3:3 + d], out[i, 1:3]]) / n) for i in want}
+                thetas = np.stack([points.get(i, last[i]) for i in range(n_gp)])
+                out, info = engine.fit_eval(x_dev, y_dev, torch.as_tensor(thetas))
+                out = out.numpy()
+                res = {}
+                for i in points:
+                    if int(info[i]) != 0 or not np.isfinite(out[i]).all():
+                        res[i] = RuntimeError("prepare: K + noise*I of GP %d is not positive definite" % i)
+                    else:
+                        res[i] = unpack(out[i])
+                        last[i] = np.array(points[i], dtype=np.float64)
+                return res
             except Exception:
                 res = {}
-                for i in want:
+                for i in points:
                     try:
-                        res[i] = eval_one(i, thetas[i])
-                    except Exception as exc:      # noqa: BLE001 -- handed to the GP's own thread
+                        res[i] = eval_one(i, points[i])
+                    except Exception as exc:      # noqa: BLE001 -- handed to the GP's own fit
                         res[i] = exc
                 return res
 
-        class _Lockstep:
-            """Rendez-vous of the fitting threads: the last one to arrive runs the batched evaluation for everybody."""
-            def __init__(self, thetas0):
-                self.cv = threading.Condition()
-                self.active = set(range(n_gp))
-                self.pending, self.results, self.round = {}, {}, 0
-                self.last = [t.clone() for t in thetas0]
+        def eval_serial(points):
+            res = {}
+            for i in points:
+                try:
+                    res[i] = eval_one(i, points[i])
+                except Exception as exc:          # noqa: BLE001
+                    res[i] = exc
+            return res
 
-            def _run(self):                       # lock held; every other active thread is waiting
-                thetas = [self.pending.get(i, self.last[i]).detach() for i in range(n_gp)]
-                out = eval_all(thetas, list(self.pending))
-                for i in list(self.pending):
-                    self.results[i] = out[i]
-                    if not isinstance(out[i], Exception):
-                        self.last[i] = thetas[i].clone()
-                self.pending.clear()
-                self.round += 1
-                self.cv.notify_all()
-
-            def evaluate(self, idx, theta):
-                with self.cv:
-                    self.pending[idx] = theta
-                    rnd = self.round
-                    if set(self.pending) >= self.active:
-                        self._run()
-                    else:
-                        while self.round == rnd:
-                            self.cv.wait()
-                    res = self.results.pop(idx)
-                if isinstance(res, Exception):
-                    raise res
-                return res
-
-            def finish(self, idx):
-                with self.cv:
-                    self.active.discard(idx)
-                    if self.pending and set(self.pending) >= self.active:
-                        self._run()
-
-        prev_thetas = [torch.cat([torch.as_tensor(p["covar_module.base_kernel.lengthscale"], dtype=torch.float64).reshape(-1),
-                                  torch.as_tensor(p["covar_module.outputscale"], dtype=torch.float64).reshape(1),
-                                  torch.as_tensor(p["likelihood.noise"], dtype=torch.float64).reshape(1)])
-                       for p in saved_state.parameters]
-        starts = [torch.rand(d + 2, dtype=torch.float64) for _ in range(n_gp)]       # random restarts (:229-247)
-        sync = _Lockstep(prev_thetas) if (lockstep and n_gp > 1) else None
-        results = [None] * n_gp
+        starts = [torch.rand(d + 2, dtype=torch.float64).numpy() for _ in range(n_gp)]       # random restarts (:229-247)
 
         def fit(idx):
-            evaluate = (lambda th: sync.evaluate(idx, th)) if sync is not None else (lambda th: eval_one(idx, th))
-
-            class _NegMll(torch.autograd.Function):
-                @staticmethod
-                def forward(ctx, theta):
-                    if stop_event is not None and stop_event.is_set():
-                        raise InterruptedError("training stopped")
-                    loss, grad = evaluate(theta.detach())
-                    ctx.save_for_backward(grad)
-                    return loss
-
-                @staticmethod
-                def backward(ctx, g):
-                    return g * ctx.saved_tensors[0]
-
+            """Generator: yields trial hyper-parameters theta of GP idx, receives (loss, d loss / d theta)."""
             lo, hi = bounds(idx)
             prev_theta = prev_thetas[idx]
-            best_theta = prev_theta.clone()
+            best_theta = prev_theta.copy()
             stopped = False
             try:
                 try:
-                    best_loss = float(_NegMll.apply(prev_theta))
+                    best_loss, _ = yield prev_theta
                 except InterruptedError:
                     raise
                 except Exception:
                     best_loss = float("inf")
                 prev_loss = best_loss
                 start = lo + starts[idx] * (hi - lo)
-                p0 = ((start - lo) / (hi - lo)).clamp(1e-6, 1 - 1e-6)
-                raw = (torch.log(p0) - torch.log1p(-p0)).requires_grad_(True)
-                opt = torch.optim.LBFGS([raw], lr=lr_train, line_search_fn="strong_wolfe")
+                p0 = np.clip((start - lo) / (hi - lo), 1e-6, 1 - 1e-6)
+                opt = LbfgsStrongWolfe(np.log(p0) - np.log1p(-p0), lr=lr_train)
                 try:
                     for it in range(num_iter_train):
-                        def closure():
-                            opt.zero_grad()
-                            theta = lo + (hi - lo) * torch.sigmoid(raw)
-                            loss = _NegMll.apply(theta)
-                            loss.backward()
-                            if print_train and it % step_print_train == 0:
-                                print("Iter %d/%d - Loss: %.5f" % (it + 1, num_iter_train, loss.item()))
-                            return loss
-                        loss = float(opt.step(closure))
+                        step = opt.step()
+                        try:
+                            raw = next(step)
+                            while True:
+                                sig = 1.0 / (1.0 + np.exp(-raw))
+                                loss, g_theta = yield lo + (hi - lo) * sig
+                                if print_train and it % step_print_train == 0:
+                                    print("Iter %d/%d - Loss: %.5f" % (it + 1, num_iter_train, loss))
+                                raw = step.send((loss, g_theta * (hi - lo) * sig * (1.0 - sig)))
+                        except StopIteration as done:
+                            loss = done.value            # as torch's optimizer.step: the loss at the START of the step
                         if loss < best_loss:
                             best_loss = loss
-                            best_theta = (lo + (hi - lo) * torch.sigmoid(raw)).detach().clone()
+                            best_theta = lo + (hi - lo) / (1.0 + np.exp(-opt.x))
                 except InterruptedError:
                     raise
                 except Exception as exc:               # e.g. a trial point with a non positive definite kernel matrix
                     print(exc)
                 print("training - model %d - time %.2f s - loss %.5f -> %.5f - outputscale %s - lengthscales %s - noise %s" % (
-                    idx, time.time() - t0, prev_loss, best_loss, best_theta[d].numpy(), best_theta[:d].numpy(),
-                    best_theta[d + 1].numpy()))
+                    idx, time.time() - t0, prev_loss, best_loss, best_theta[d], best_theta[:d], best_theta[d + 1]))
             except InterruptedError:                   # controller shut down: this GP keeps what it has
                 stopped = True
-            finally:
-                if sync is not None:
-                    sync.finish(idx)
-            if stopped and torch.equal(best_theta, prev_theta):
-                results[idx] = {k: np.asarray(v) for k, v in saved_state.parameters[idx].items()}
-            else:
-                results[idx] = {"covar_module.base_kernel.lengthscale": best_theta[:d].reshape(1, d).numpy(),
-                                "covar_module.outputscale": best_theta[d].reshape(()).numpy(),
-                                "likelihood.noise": best_theta[d + 1].reshape(1).numpy()}
+            if stopped and np.array_equal(best_theta, prev_theta):
+                return {k: np.asarray(v) for k, v in saved_state.parameters[idx].items()}
+            return {"covar_module.base_kernel.lengthscale": best_theta[:d].reshape(1, d).copy(),
+                    "covar_module.outputscale": np.asarray(best_theta[d]).reshape(()),
+                    "likelihood.noise": best_theta[d + 1].reshape(1).copy()}
 
-        if sync is not None:
-            threads = [threading.Thread(target=fit, args=(i,), daemon=True) for i in range(n_gp)]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
+        should_stop = (lambda: stop_event.is_set()) if stop_event is not None else None
+        if lockstep and n_gp > 1:
+            results = run_lockstep({i: fit(i) for i in range(n_gp)}, eval_all, should_stop)
         else:
+            results = {}
             for i in range(n_gp):
-                fit(i)
+                results.update(run_lockstep({i: fit(i)}, eval_serial, should_stop))
                 if stop_event is not None and stop_event.is_set():
                     break
+        out = []
         for i in range(n_gp):
-            if results[i] is None:
-                results[i] = {k: np.asarray(v) for k, v in saved_state.parameters[i].items()}
-        queue.put(results)
+            r = results.get(i)
+            out.append(r if r is not None else {k: np.asarray(v) for k, v in saved_state.parameters[i].items()})
+        queue.put(out)
 
     def save_state(self):
         return SavedState(inputs=self.x_mem, states_change=self.y_mem,

@@ -121,6 +121,20 @@ int gpmpc_rollout(gpmpc_handle* h, const double* actions_mpc, const double* obs_
  */
 int gpmpc_mll(gpmpc_handle* h, const double* y, double* out, void* stream);
 
+/*
+ * One objective evaluation of the hyper-parameter fit -- what `loss = -mll(model(train_x), train_y); loss.backward()`
+ * computes in control_objects/models/gp_model.py:262-277 -- for all E GPs at their trial hyper-parameters, as ONE CUDA
+ * graph launch: gpmpc_prepare + gpmpc_mll are ~85 dependent kernels and launch-bound at N = 500 (2.1 ms as separate
+ * launches), and a fit evaluates them several hundred times on the same (x, y).
+ *   x (N,D), y (N,E): DEVICE pointers, fixed during a fit (the graph is re-captured when they, N, D or E change);
+ *   theta (E, D+2): HOST, per GP { lengthscale[D], outputscale, noise };
+ *   out (E, 3+D): HOST, as gpmpc_mll;  info (E): HOST, 0 or 1 + the pivot at which K + noise I stopped being positive
+ *   definite (that GP's row of `out` is then meaningless; the other GPs are not affected).
+ * Synchronous (returns after the results are on the host).  Leaves the handle prepared at theta iff every info is 0.
+ */
+int gpmpc_fit_eval(gpmpc_handle* h, const double* x, const double* y, const double* theta, int N, int D, int E,
+                   double* out, int* info, void* stream);
+
 /* Kernel-path selection.  When every GP has bitwise-identical hyper-parameters (the reference's state before
  * hyper-parameter training, examples/<env>/config_<env>.py:41-45) gpmpc_rollout uses the "uniform-kernel" path
  * (one exp per (i,j) for all output pairs).  mode 0: automatic (default); mode 1: always the general path.

@@ -49,6 +49,39 @@ def test_marginal_likelihood_and_gradient_match_autograd(kw):
         assert abs(out[a, 2] - grads[a][2]) <= 1e-7 * scale
 
 
+def test_fit_eval_graph_equals_prepare_plus_mll_and_isolates_a_failing_gp():
+    """gpmpc_fit_eval (one CUDA-graph launch per objective evaluation of the fit) returns what gpmpc_prepare + gpmpc_mll
+    return, also when replayed with other hyper-parameters, leaves the handle prepared, and reports a GP whose kernel
+    matrix is not positive definite through `info` without touching the other GPs' rows."""
+    from rl_gp_mpc import _cabi
+    cfg = make_workload(E=3, Na=2, N=150, H=2, B=1, ls=0.4, seed=53, noise=1e-4, distinct_lengthscales=True)
+    ls = torch.as_tensor(full_lengthscale(cfg))
+    s2 = torch.as_tensor(cfg["outputscale"]).reshape(-1)
+    nz = torch.as_tensor(cfg["noise"]).reshape(-1)
+    E, D = ls.shape
+    eng = _cabi.Engine()
+    x_dev = torch.as_tensor(cfg["x"], dtype=torch.float64).to(eng.device).contiguous()
+    y_dev = torch.as_tensor(cfg["y"], dtype=torch.float64).to(eng.device).contiguous()
+    ref = _cabi.Engine()
+    for scale in (1.0, 1.3, 0.8):                       # capture, then two replays
+        theta = torch.cat([ls * scale, (s2 * scale)[:, None], nz[:, None]], dim=1)
+        out, info = eng.fit_eval(x_dev, y_dev, theta)
+        assert int(info.abs().sum()) == 0
+        ref.prepare(cfg["x"], cfg["y"], ls * scale, s2 * scale, nz)
+        want = ref.mll(cfg["y"]).cpu()
+        np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=1e-12, atol=1e-9)
+    iK, beta = eng.factorization()                      # the handle is prepared at the last theta
+    iK_ref, beta_ref = ref.factorization()
+    np.testing.assert_allclose(beta.cpu().numpy(), beta_ref.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    # GP 1 with a huge lengthscale and no noise: numerically singular K -> info[1] != 0, rows 0 and 2 as before
+    theta_bad = theta.clone()
+    theta_bad[1, :D] = 1e6
+    theta_bad[1, D + 1] = 0.0
+    out_bad, info_bad = eng.fit_eval(x_dev, y_dev, theta_bad)
+    assert int(info_bad[1]) != 0 and int(info_bad[0]) == 0 and int(info_bad[2]) == 0
+    np.testing.assert_allclose(out_bad[[0, 2]].numpy(), out[[0, 2]].numpy(), rtol=1e-12, atol=1e-9)
+
+
 def test_training_procedure_improves_the_marginal_likelihood_and_feeds_the_controller():
     from rl_gp_mpc import GpMpcController
     from rl_gp_mpc.config_classes.controller_config import ControllerConfig
@@ -133,3 +166,68 @@ def test_lockstep_fit_of_all_gps_equals_the_serial_fit():
     np.testing.assert_allclose(neg_mll(out[True]), neg_mll(out[False]), rtol=0, atol=1e-6)
     for a, b in zip(out[True], out[False]):
         np.testing.assert_allclose(a["covar_module.base_kernel.lengthscale"], b["covar_module.base_kernel.lengthscale"], rtol=1e-5)
+
+
+def test_fit_ends_where_the_torch_lbfgs_procedure_of_the_reference_ends():
+    """train() drives its own generator form of LBFGS / strong Wolfe; the reference drives torch.optim.LBFGS
+    (gp_model.py:262-277).  Same random restart (torch seed), same objective (device marginal likelihood): the final
+    losses must agree within 1e-6."""
+    from rl_gp_mpc import _cabi
+    from rl_gp_mpc.config_classes.model_config import ModelConfig
+    from rl_gp_mpc.control_objects.models.gp_model import GpStateTransitionModel
+    cfg = make_workload(E=2, Na=1, N=100, H=3, B=1, ls=0.5, seed=58)
+    E, D, n = 2, 3, cfg["N"]
+    mc = ModelConfig(gp_init={"noise_covar.noise": [1e-3] * E, "base_kernel.lengthscale": [1.5] * E, "outputscale": [0.3] * E},
+                     min_std_noise=1e-3, max_std_noise=1e-1, min_outputscale=1e-4, max_outputscale=1.0,
+                     min_lengthscale=5e-2, max_lengthscale=10.0)
+    tm = GpStateTransitionModel(mc, dim_state=E, dim_action=1)
+    tm.prepare_inference(torch.as_tensor(cfg["x"]), torch.as_tensor(cfg["y"]))
+    lr, iters = 0.5, 5
+    torch.manual_seed(9)
+    q = queue_mod.Queue()
+    st = tm.save_state(); st.to_arrays()
+    GpStateTransitionModel.train(q, st, lr, iters, 1e-3)
+    new = q.get(timeout=5)
+    eng = _cabi.Engine()
+    x = torch.as_tensor(cfg["x"]); y = torch.as_tensor(cfg["y"])
+
+    def neg_mll_one(idx, theta):
+        eng.prepare(x, y[:, idx:idx + 1].contiguous(), theta[:D].reshape(1, D), theta[D:D + 1], theta[D + 1:D + 2])
+        out = eng.mll(y[:, idx:idx + 1].contiguous())[0].cpu()
+        return -out[0] / n, -torch.cat([out[3:3 + D], out[1:3]]) / n
+
+    torch.manual_seed(9)
+    starts = [torch.rand(D + 2, dtype=torch.float64) for _ in range(E)]       # as train() draws them
+    lo = torch.tensor([5e-2] * D + [1e-4, 1e-6], dtype=torch.float64)
+    hi = torch.tensor([10.0] * D + [1.0, 1e-2], dtype=torch.float64)
+    for idx in range(E):
+        class _F(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, theta):
+                loss, grad = neg_mll_one(idx, theta.detach())
+                ctx.save_for_backward(grad)
+                return loss
+
+            @staticmethod
+            def backward(ctx, g):
+                return g * ctx.saved_tensors[0]
+        prev = torch.tensor([1.5] * D + [0.3, 1e-3], dtype=torch.float64)
+        best = float(_F.apply(prev))
+        p0 = ((lo + starts[idx] * (hi - lo) - lo) / (hi - lo)).clamp(1e-6, 1 - 1e-6)
+        raw = (torch.log(p0) - torch.log1p(-p0)).requires_grad_(True)
+        opt = torch.optim.LBFGS([raw], lr=lr, line_search_fn="strong_wolfe")
+        best_theta = prev
+        for _ in range(iters):
+            def closure():
+                opt.zero_grad()
+                loss = _F.apply(lo + (hi - lo) * torch.sigmoid(raw))
+                loss.backward()
+                return loss
+            loss = float(opt.step(closure))
+            if loss < best:
+                best, best_theta = loss, (lo + (hi - lo) * torch.sigmoid(raw)).detach().clone()
+        got = torch.cat([torch.as_tensor(new[idx]["covar_module.base_kernel.lengthscale"]).reshape(-1),
+                         torch.as_tensor(new[idx]["covar_module.outputscale"]).reshape(1),
+                         torch.as_tensor(new[idx]["likelihood.noise"]).reshape(1)])
+        assert abs(float(neg_mll_one(idx, got)[0]) - float(neg_mll_one(idx, best_theta)[0])) <= 1e-6
+        np.testing.assert_allclose(got.numpy(), best_theta.numpy(), rtol=1e-4, atol=1e-9)
