@@ -281,13 +281,17 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
                                        np.asarray(p["likelihood.noise"], dtype=np.float64).reshape(1)])
                        for p in saved_state.parameters]
         last = [t.copy() for t in prev_thetas]         # the values a GP rides along with when it has nothing to evaluate
+        stats = [0, 0.0]                               # rounds of batched evaluations, seconds inside the device call
 
         def eval_all(points):
             """One device round for all GPs: ONE CUDA-graph launch (gpmpc_fit_eval); a GP whose trial point has a non
             positive definite kernel matrix gets its error, the others their values.  GP by GP if the joint call fails."""
             try:
                 thetas = np.stack([points.get(i, last[i]) for i in range(n_gp)])
+                tc = time.time()
                 out, info = engine.fit_eval(x_dev, y_dev, torch.as_tensor(thetas))
+                stats[0] += 1
+                stats[1] += time.time() - tc
                 out = out.numpy()
                 res = {}
                 for i in points:
@@ -373,6 +377,9 @@ class GpStateTransitionModel(AbstractStateTransitionModel):
                 results.update(run_lockstep({i: fit(i)}, eval_serial, should_stop))
                 if stop_event is not None and stop_event.is_set():
                     break
+        if stats[0]:
+            print("training - %d rounds of batched evaluations, %.2f s in the device calls of %.2f s" % (
+                stats[0], stats[1], time.time() - t0))
         out = []
         for i in range(n_gp):
             r = results.get(i)
