@@ -418,9 +418,10 @@ def main():
                     "achieved_tflops": ach / 1e12, "frac": ach / fp64_peak}
 
         if m["uniform"]:
-            kf = kernel_block("gpmpc::uniform_fwd_kernel<%d> (forward sweep, one exp per (i,j) for all output pairs)" % E,
+            # (second template argument = threads per CTA of the build the host plan picks: 128 = three CTAs per SM)
+            kf = kernel_block("gpmpc::uniform_fwd_kernel<%d, MAXT> (forward sweep, one exp per (i,j) for all output pairs)" % E,
                               "uniform_fwd", m["fwd_ms"])
-            kb = kernel_block("gpmpc::uniform_bwd_kernel<%d> (reverse sweep: adjoint-weighted upper-triangle N^2 sweep)" % E,
+            kb = kernel_block("gpmpc::uniform_bwd_kernel<%d, MAXT> (reverse sweep: adjoint-weighted upper-triangle N^2 sweep)" % E,
                               "uniform_bwd", m["bwd_ms"])
             dom = kb if m["bwd_ms"] >= m["fwd_ms"] else kf
             kernels = [kf, kb]
