@@ -402,6 +402,29 @@ def test_reverse_sweep_records_in_global_scratch_match_shared_memory(kw, monkeyp
     np.testing.assert_allclose(out["0"]["grad"], out["1"]["grad"], rtol=0, atol=1e-10)
 
 
+@pytest.mark.parametrize("kw", [dict(E=2, Na=1, N=150, H=4, B=5, ls=0.5, seed=71), dict(E=3, Na=1, N=200, H=3, B=4, ls=0.5, seed=72),
+                                dict(E=4, Na=2, N=260, H=3, B=3, ls=0.3, seed=73),
+                                dict(E=5, Na=2, N=130, H=3, B=2, ls=0.6, seed=74, include_time_model=True)])
+def test_both_builds_of_the_uniform_kernels_agree(kw, monkeypatch):
+    """The uniform kernels exist in two builds for E <= 5 -- 256 threads at <= 128 registers and 128 threads at <= 168
+    (three CTAs per SM; the host takes it for large batches) -- and must return the same costs and gradients."""
+    cfg = make_workload(**kw)
+    out = {}
+    for thr in ("256", "128"):
+        monkeypatch.setenv("GPMPC_UNI_FWD_THREADS", thr)
+        monkeypatch.setenv("GPMPC_UNI_BWD_THREADS", thr)
+        monkeypatch.setenv("GPMPC_UNI_CLUSTER", "1")
+        eng = make_engine(cfg)
+        assert eng.uses_uniform_path()
+        out[thr] = rollout(eng, cfg)
+    # (4 instead of 8 warps split the sums differently; the 1e6..1e8 cancellation of the covariance sums turns that
+    # into ~1e-10, as between any two schedules of the same build)
+    np.testing.assert_allclose(out["128"]["cost"], out["256"]["cost"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(out["128"]["grad"], out["256"]["grad"], rtol=0, atol=1e-8)
+    want = orc.evaluate_workload(cfg)
+    np.testing.assert_allclose(out["128"]["grad"], want["grad"], rtol=0, atol=ATOL_GRAD)
+
+
 def test_uniform_path_large_state_dimension():
     """C5 dims (E=8, Na=3, D=11) on the uniform path (255-register kernels, owner-lane reductions)."""
     cfg = make_workload(E=8, Na=3, N=200, H=2, B=2, ls=0.7, seed=42)
