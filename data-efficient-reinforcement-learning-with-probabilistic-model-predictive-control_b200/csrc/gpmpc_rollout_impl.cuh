@@ -893,53 +893,81 @@ __global__ void __launch_bounds__(GEN_MAXT(EV), 1) rollout_kernel(const RolloutP
       __syncthreads();
       GEN_CLK(2);
       // ================================================================ P2: O(N) moment sums
-      // lane per output (all lanes read the SAME training point: multicast LDS, no bank conflicts), the 32-output groups
-      // x 4 slices of the training points dealt to the warps; the slice sums meet in s_out (zeroed in P1)
+      // (round 2) lane per training POINT: a task = (GP a, state dimension e1) owns the sums that share the factor
+      // lb_a,i nu_i,e1 -- Gam[e1][d] (D) and T[e1][k<=l] (PV) -- plus, for e1 = 0, h and g_d; the lane loads nu_i and
+      // lb_a,i ONCE per point (4 shared-memory loads for ~25 FMAs; the lane-per-output form took 4 loads per FMA and was
+      // bound by the shared-memory pipe: 42.6 k clocks per step), keeps the sums of its points in registers, and the warp
+      // adds them up with halving exchanges.  Every output has exactly one owner: plain stores, no atomics.
       {
-        const int nTot = E * nOut, ngrp = (nTot + 31) >> 5, nsl = 4, slen = (N + nsl - 1) / nsl;
-        for (int task = tid >> 5; task < ngrp * nsl; task += NT >> 5) {
-          const int o = (task / nsl) * 32 + lane, sl = task % nsl;
-          const int ibeg = sl * slen, iend = min(N, ibeg + slen);
-          if (o < nTot) {
-            const int a = o / nOut, q = o - a * nOut;
-            const double* lb = s_lb + a * NP;
-            // value = lb_i * f1 * f2 * f3 with up to three factors nu_i[.]; an absent factor reads the constant 1.0
-            // (stride 0), so that all lanes run the same instruction stream whatever their output is
-            const double* b1 = &s_one; const double* b2 = &s_one; const double* b3 = &s_one;
-            int st1 = 0, st2 = 0, st3 = 0;
-            if (q == 0) {
-            } else if (q <= D) {
-              b1 = s_nu + (q - 1); st1 = DP;
-            } else if (q < 1 + D + EV * D) {
-              const int qq = q - 1 - D, e1 = qq / D;
-              b1 = s_nu + e1; st1 = DP;
-              b2 = s_nu + (qq - e1 * D); st2 = DP;
-            } else {
-              const int qq = q - 1 - D - EV * D, e1 = qq / PV;
-              int kl = qq - e1 * PV, k1 = 0;
-              while (kl >= EV - k1) { kl -= EV - k1; k1++; }
-              b1 = s_nu + e1; st1 = DP;
-              b2 = s_nu + k1; st2 = DP;
-              b3 = s_nu + (k1 + kl); st3 = DP;
-            }
-            // four independent accumulation chains (the loop is LDS -> DMUL -> DFMA latency, not throughput), running
-            // pointers instead of index * stride
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            const double* q0 = lb + ibeg;
-            const double* q1 = b1 + (size_t)ibeg * st1;
-            const double* q2 = b2 + (size_t)ibeg * st2;
-            const double* q3 = b3 + (size_t)ibeg * st3;
-            int i = ibeg;
-            for (; i + 3 < iend; i += 4) {
+        constexpr int PVc = EV * (EV + 1) / 2;
+        const int ntask = GRAD ? E * EV : E;   // (splitting a task's points over several warps was slower: 25 k vs 20.6 k clocks)
+        for (int task = tid >> 5; task < ntask; task += NT >> 5) {
+          const int a = GRAD ? task / EV : task, e1 = GRAD ? task - a * EV : 0;
+          const double* lbp = s_lb + a * NP;
+          double hs = 0.0, gs[GPMPC_MAX_D], gam[GPMPC_MAX_D], tt[PVc];
 #pragma unroll
-              for (int k = 0; k < 4; k++) acc[k] = fma(q0[k] * q1[k * st1], q2[k * st2] * q3[k * st3], acc[k]);
-              q0 += 4; q1 += 4 * st1; q2 += 4 * st2; q3 += 4 * st3;
+          for (int d = 0; d < GPMPC_MAX_D; d++) { gs[d] = 0.0; gam[d] = 0.0; }
+#pragma unroll
+          for (int k = 0; k < PVc; k++) tt[k] = 0.0;
+          for (int i = lane; i < NP; i += 32) {       // padded points carry lb = 0
+            const double lb = lbp[i];
+            double nu[GPMPC_MAX_D];
+#pragma unroll
+            for (int d = 0; d < GPMPC_MAX_D; d++) nu[d] = (d < DP) ? s_nu[i * DP + d] : 0.0;
+            if (e1 == 0) {
+              hs += lb;
+#pragma unroll
+              for (int d = 0; d < GPMPC_MAX_D; d++) gs[d] = fma(lb, nu[d], gs[d]);   // nu = 0 beyond D
             }
-            for (; i < iend; i++) {
-              acc[0] = fma(q0[0] * q1[0], q2[0] * q3[0], acc[0]);
-              q0 += 1; q1 += st1; q2 += st2; q3 += st3;
+            if (GRAD) {
+              double ne = nu[0];
+#pragma unroll
+              for (int e = 1; e < EV; e++) ne = (e == e1) ? nu[e] : ne;
+              const double w = lb * ne;
+#pragma unroll
+              for (int d = 0; d < GPMPC_MAX_D; d++) gam[d] = fma(w, nu[d], gam[d]);
+              int pr = 0;
+#pragma unroll
+              for (int k = 0; k < EV; k++) {
+                const double wk = w * nu[k];
+#pragma unroll
+                for (int l = k; l < EV; l++) { tt[pr] = fma(wk, nu[l], tt[pr]); pr++; }
+              }
             }
-            atomicAdd(s_out + o, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+          }
+          double* out = s_out + a * nOut;
+          // warp totals, 16 values per round of halving exchanges (warp_reduce_multi); value idx lands in the even lanes
+          if (e1 == 0) {
+            double v16[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) v16[k] = (k == 0) ? hs : gs[k - 1];      // h, g_0 .. g_14
+            int idx;
+            double tot = warp_reduce_multi<16>(v16, lane, idx);
+            if ((lane & 1) == 0 && idx < 1 + D) out[idx] = tot;
+            if (D == GPMPC_MAX_D) {                                                // g_15 (D = 16 only)
+              tot = warp_sum(gs[GPMPC_MAX_D - 1]);
+              if (lane == 0) out[D] = tot;
+            }
+          }
+          if (GRAD) {
+            {
+              double v16[16];
+#pragma unroll
+              for (int k = 0; k < 16; k++) v16[k] = gam[k];
+              int idx;
+              const double tot = warp_reduce_multi<16>(v16, lane, idx);
+              if ((lane & 1) == 0 && idx < D) out[1 + D + e1 * D + idx] = tot;
+            }
+            constexpr int NCH = (PVc + 15) / 16;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+              double v16[16];
+#pragma unroll
+              for (int k = 0; k < 16; k++) v16[k] = (16 * ch + k < PVc) ? tt[(16 * ch + k < PVc) ? 16 * ch + k : 0] : 0.0;
+              int idx;
+              const double tot = warp_reduce_multi<16>(v16, lane, idx);
+              if ((lane & 1) == 0 && 16 * ch + idx < PVc) out[1 + D + EV * D + e1 * PVc + 16 * ch + idx] = tot;
+            }
           }
         }
       }
