@@ -93,8 +93,8 @@ cudaError_t launch_colcoef(const double* beta, double* colcoef, int n, cudaStrea
 
 // static shared memory of the rollout kernels: the 16 KB table of exp2s (gpmpc_common.cuh) + a few scalars
 constexpr size_t GPMPC_STATIC_SMEM = 16 * 1024 + 128;   // sizeof(GpmpcStaticSmem) rounded up
-// Large state dimensions (E >= 6): tensor-core sweeps (uni_*_mma8 in gpmpc_uniform_impl.cuh), one CTA of 384 threads
-// (<= 168 registers) per SM instead of 256 threads at 255 registers + spills.
+// Large state dimensions (E >= 6): float64 tensor-core sweeps (uni_*_mma8 in gpmpc_uniform_impl.cuh), one CTA of 256
+// threads per SM (UNI_MMA8_THREADS; 384 threads at <= 168 registers measured no faster).
 #ifndef UNI_MMA8
 #define UNI_MMA8 1
 #endif

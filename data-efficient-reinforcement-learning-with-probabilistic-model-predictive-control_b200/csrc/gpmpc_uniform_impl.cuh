@@ -14,6 +14,11 @@
 // from which dS/dm and dS/dQ follow exactly as for a diagonal pair of the general path (rho, gamma, xi sums).
 // uniform_fwd_kernel stores only (M, V^E, h, g^E, S^raw) per step; uniform_bwd_kernel runs the reverse sweep
 // with one CTA per candidate.  tests/algo_spec.py remains the executable spec of the mathematics.
+//
+// Round 2: both kernels exist in two builds for E <= 5 (256 threads at <= 128 registers, 128 threads at <= 168 -- three
+// CTAs per SM; the host plan picks, gpmpc_api.cu); for E >= 6 the sweeps run on the float64 tensor cores (uni_*_mma8:
+// exponent, coefficient and the E-wide row sums as DMMA m8n8k4 tile products on 32 x 32 tiles); the E = 4 DMMA variants
+// that were measured and lost stay behind -DUNI_MMA=1/2 (profiles/r02s_dmma_experiments.txt).
 #pragma once
 #include "gpmpc_rollout_impl.cuh"
 #include "gpmpc_uniform_layout.cuh"
