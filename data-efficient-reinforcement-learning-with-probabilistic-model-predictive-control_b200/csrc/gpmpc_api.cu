@@ -61,6 +61,7 @@ struct gpmpc_handle {
   DevBuf fit_out;
   const double *fit_x = nullptr, *fit_y = nullptr;
   int fit_N = 0, fit_D = 0, fit_E = 0;
+  size_t fit_bufs = 0;                     // fingerprint of the device buffers the graph was captured with
   long long fit_launches = 0;
 };
 
@@ -686,6 +687,16 @@ int gpmpc_mll(gpmpc_handle* h, const double* y, double* out, void* stream) {
   return GPMPC_OK;
 }
 
+// The captured graph holds raw device pointers: any other call that re-allocates a buffer of the handle (a larger
+// gpmpc_prepare in between) must invalidate it.
+static size_t fit_buffer_fingerprint(const gpmpc_handle* h) {
+  const void* ptrs[] = {h->x.ptr, h->ls.ptr, h->il2.ptr, h->s2.ptr, h->noise.ptr, h->beta.ptr, h->betaT.ptr, h->iK.ptr,
+                        h->Kbuf.ptr, h->Zbuf.ptr, h->info.ptr, h->fit_out.ptr};
+  size_t f = 1469598103934665603ull;
+  for (const void* q : ptrs) f = (f ^ reinterpret_cast<size_t>(q)) * 1099511628211ull;
+  return f;
+}
+
 // Everything one objective evaluation of the fit puts on the stream: trial hyper-parameters from the pinned staging
 // buffer, Gram + Cholesky + inverse (launch_prepare), LML + gradient (launch_mll), results back to the staging buffer.
 static int fit_enqueue(gpmpc_handle* h, const double* x, const double* y, int N, int NP, int D, int E, cudaStream_t st) {
@@ -726,7 +737,8 @@ int gpmpc_fit_eval(gpmpc_handle* h, const double* x, const double* y, const doub
     pin[E * D + a] = theta[a * (D + 2) + D];
     pin[E * D + E + a] = theta[a * (D + 2) + D + 1];
   }
-  if (!h->fit_exec || h->fit_x != x || h->fit_y != y || h->fit_N != N || h->fit_D != D || h->fit_E != E) {
+  if (!h->fit_exec || h->fit_x != x || h->fit_y != y || h->fit_N != N || h->fit_D != D || h->fit_E != E ||
+      h->fit_bufs != fit_buffer_fingerprint(h)) {
     // (re)capture: buffers first (no allocation inside a capture), the caller's stream drained once (x, y uploads)
     if (h->fit_exec) { cudaGraphExecDestroy(h->fit_exec); h->fit_exec = nullptr; }
     { const int rc = prepare_buffers(h, NP, D, E); if (rc != GPMPC_OK) return rc; }
@@ -745,6 +757,7 @@ int gpmpc_fit_eval(gpmpc_handle* h, const double* x, const double* y, const doub
     h->fit_launches = h->launches - l0;
     h->launches = l0;
     h->fit_x = x; h->fit_y = y; h->fit_N = N; h->fit_D = D; h->fit_E = E;
+    h->fit_bufs = fit_buffer_fingerprint(h);
   }
   CU(cudaGraphLaunch(h->fit_exec, h->fit_stream));
   h->launches += h->fit_launches;

@@ -70,6 +70,12 @@ def test_fit_eval_graph_equals_prepare_plus_mll_and_isolates_a_failing_gp():
         ref.prepare(cfg["x"], cfg["y"], ls * scale, s2 * scale, nz)
         want = ref.mll(cfg["y"]).cpu()
         np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=1e-12, atol=1e-9)
+    # a larger prepare() on the same handle re-allocates its buffers: the captured graph must not be replayed
+    big = make_workload(E=3, Na=2, N=400, H=2, B=1, ls=0.4, seed=54, noise=1e-4)
+    eng.prepare(big["x"], big["y"], full_lengthscale(big), big["outputscale"], big["noise"])
+    out2, info2 = eng.fit_eval(x_dev, y_dev, theta)
+    assert int(info2.abs().sum()) == 0
+    np.testing.assert_allclose(out2.numpy(), want.numpy(), rtol=1e-12, atol=1e-9)
     iK, beta = eng.factorization()                      # the handle is prepared at the last theta
     iK_ref, beta_ref = ref.factorization()
     np.testing.assert_allclose(beta.cpu().numpy(), beta_ref.cpu().numpy(), rtol=1e-12, atol=1e-12)
